@@ -1,0 +1,123 @@
+/*
+ * phyngsc_b200.h -- C ABI of the B200-native phyNGSC subblock compressor.
+ *
+ * The reference (pcdslab/PHYNGSC) has no plugin / FFI seam: the path is the body of the
+ * `while (p_bytes_read < p_working_region)` loop in main() (phyNGSC.cpp:168-840).  This header cuts
+ * that seam.  Each entry point names the reference lines it replaces; INTEGRATION.md shows the
+ * patch to phyNGSC.cpp a maintainer would apply.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All compute runs in hand-written sm_100a
+ * CUDA kernels; there is no CPU fallback -- every call fails with PHY_ERR_CUDA when no device or no
+ * kernel image is usable.
+ *
+ * Threading: one phy_ctx per rank / GPU, calls on a ctx serialised by the caller.  The library
+ * never calls MPI (the reference initialises MPI_THREAD_FUNNELED, phyNGSC.cpp:57).
+ */
+#ifndef PHYNGSC_B200_H
+#define PHYNGSC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHY_ABI_VERSION 1
+
+enum {
+  PHY_OK = 0,
+  PHY_ERR_MALFORMED = -1,   /* line 3 is not "+", or quality length != sequence length (reference: UB)      */
+  PHY_ERR_FIELDS = -2,      /* separator count differs between titles (reference: warning then UB, :417-421) */
+  PHY_ERR_COLORSPACE = -3,  /* colour-space reads (phyNGSC.cpp:473-547) are not implemented                  */
+  PHY_ERR_UNSUPPORTED = -4, /* outside the reference's defined domain: >32 title fields, token >512 B,
+                               field max_len == 128 (Q11), Huffman code > 32 bits, read longer than 512, NUL  */
+  PHY_ERR_CAPACITY = -5,    /* a ctx buffer (batch bytes, records, subblocks, output) is too small            */
+  PHY_ERR_CUDA = -6,        /* CUDA runtime error / no device; see phy_last_error()                          */
+  PHY_ERR_ARG = -7
+};
+
+typedef struct phy_ctx phy_ctx;
+
+/* Region geometry, exactly the reference's (phyNGSC.cpp:113-124): region = file_size / np, rank r
+ * owns [r*region, r*region + region + overlap - 1] (last rank: to EOF). */
+typedef struct {
+  uint64_t file_size;     /* FASTQ_size                                                     */
+  int32_t np;             /* g_size (>= 1; the reference itself refuses np < 2, :91-97)     */
+  int32_t rank;           /* p_rank                                                         */
+  uint64_t window_bytes;  /* READ_BUFFER_SIZE, 8 MiB in the reference (defs.h:20)           */
+  uint32_t overlap;       /* 500 (phyNGSC.cpp:48)                                           */
+  uint32_t record_cap;    /* records_per_th at threads = 1: 100000 (phyNGSC.cpp:51,321)     */
+} phy_region_params;
+
+/* One subblock as the reference's loop body produces it. */
+typedef struct {
+  uint64_t win_off;        /* absolute file offset of the window (r_buffer_curr_pos)         */
+  uint64_t win_len;        /* r_buffer_size used for this window                             */
+  uint32_t rec_start;      /* rec_start_pos (non-zero only in the first window of rank > 0)  */
+  int32_t overlap;         /* overlap in force (500 or 0, phyNGSC.cpp:123,751)               */
+  uint32_t n_records;      /* no_records                                                     */
+  uint32_t warnings;       /* bit0: record cap hit (phyNGSC.cpp:321-326)                     */
+  uint64_t bytes_consumed; /* the increment of p_bytes_read (phyNGSC.cpp:745)                */
+  uint32_t sec_len[4];     /* info, title, quality, dna stream lengths                       */
+  uint64_t out_off;        /* offset of this payload in the output buffer                    */
+  uint32_t out_len;        /* p_bytes_to_copy (phyNGSC.cpp:799)                              */
+  int32_t status;          /* PHY_OK or the error raised for this subblock                   */
+} phy_subblock_desc;
+
+typedef struct {
+  uint32_t n_subblocks;
+  uint32_t n_batches;
+  uint64_t bytes_in;         /* sum of bytes_consumed                                       */
+  uint64_t bytes_out;        /* sum of out_len                                              */
+  int32_t wr_overlap;        /* wr_ov_used, for the footer (phyNGSC.cpp:160)                */
+  uint32_t kernel_launches;  /* kernels launched by the last compress call                  */
+  float kernel_ms;           /* CUDA-event time, first kernel launch to last kernel done    */
+  float h2d_ms, d2h_ms;      /* copy times of the last phy_compress_region (0 if resident)  */
+} phy_region_result;
+
+/* Create a context on cuda_device.  max_batch_bytes bounds the bytes resident per batch (input
+ * buffer size; <= 3 GiB because window offsets inside a batch are 32-bit); max_subblocks bounds the
+ * windows planned per batch.  0 picks defaults (1.25 GiB / 192). */
+int phy_ctx_create(phy_ctx **out, int cuda_device, uint64_t max_batch_bytes, uint32_t max_subblocks);
+void phy_ctx_destroy(phy_ctx *ctx);
+
+/* Replaces phyNGSC.cpp:168-840 for a whole working region: partition sync (:131-156), window chaining
+ * (:744-755), record split, tokenise, analyse, Huffman, emit, section concat.
+ *   region      host bytes starting at file offset rank*region (p_wr_start); region_len bytes are
+ *               readable (at least up to p_wr_end + 1; more is fine and gives the read-slack
+ *               semantics for records longer than `overlap`)
+ *   out         host buffer receiving the subblock payloads back to back (info|title|quality|dna)
+ *   descs       receives one descriptor per subblock, in order; *inout_n_descs = capacity in, count out
+ * Host buffers may be pageable or pinned (pinned makes the copies asynchronous). */
+int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
+                        uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
+                        phy_region_result *result);
+
+/* The same work split into its three legs, for callers that keep data resident (and for kernel-only
+ * timing): upload copies host bytes into the ctx input buffer; compress_resident runs the kernels over
+ * what is resident (single batch: region_len <= max_batch_bytes) leaving payloads in device memory;
+ * download copies them out. */
+int phy_upload(phy_ctx *ctx, const uint8_t *region, uint64_t region_len);
+int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params,
+                          phy_subblock_desc *descs, uint32_t *inout_n_descs, phy_region_result *result);
+int phy_download(phy_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
+/* Raw device pointers of the ctx buffers (for zero-copy producers such as a torch tensor). */
+void *phy_device_input(phy_ctx *ctx, uint64_t *capacity);
+void *phy_device_output(phy_ctx *ctx, uint64_t *capacity);
+
+/* Block header exactly as MakeHeader writes it (tasks.cpp:1179-1200); returns bytes written or 0. */
+uint32_t phy_make_block_header(int32_t wrid, int32_t bewr, int32_t bhs, int32_t beso, int32_t bcss,
+                               const uint32_t *sbol, uint32_t nosb, uint8_t *out, uint32_t cap);
+/* Footer exactly as MakeFooter writes it (tasks.cpp:1104-1176) for the given block order. */
+int32_t phy_make_footer(int32_t np, uint64_t fastq_size, uint32_t n_blocks, uint32_t n_subblocks,
+                        const int32_t *overlaps, const int32_t *block_order, const uint32_t *lb_sizes,
+                        uint8_t *out, uint32_t cap);
+
+const char *phy_strerror(int code);
+const char *phy_last_error(phy_ctx *ctx); /* detail of the last failure on ctx (may be "") */
+int phy_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

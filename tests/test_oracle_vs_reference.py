@@ -1,0 +1,58 @@
+"""The oracle against the reference itself, compiled unmodified into oracle/_ref (oracle/Makefile).
+Only meaningful where /root/reference exists (the build container); skipped elsewhere."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import phy_oracle as O
+from phyngsc_b200 import container, synth
+
+pytestmark = pytest.mark.skipif(not (O.have_reference() and os.path.exists(O.REF_KAT)), reason="oracle/_ref not built")
+
+
+def _rand_freqs(rng, n):
+    kind = rng.integers(0, 6)
+    if kind == 0:
+        f = rng.integers(0, 5, n)
+    elif kind == 1:
+        f = rng.integers(0, 2, n) * rng.integers(1, 1000, n)
+    elif kind == 2:
+        f = np.zeros(n, np.int64); f[rng.integers(0, n)] = rng.integers(1, 100)
+    elif kind == 3:
+        f = np.full(n, rng.integers(1, 9))
+    elif kind == 4:
+        f = (2 ** rng.integers(0, 20, n)).astype(np.int64)
+    else:
+        f = rng.integers(0, 100000, n)
+    return f.astype(np.uint32)
+
+
+def test_huffman_known_answers_against_reference_classes(oracle):
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 3, 4, 5, 7, 8, 16, 31, 41, 64, 100, 255, 256, 300, 512]
+    for it in range(400):
+        n = sizes[it % len(sizes)]
+        f = _rand_freqs(rng, n)
+        if n > 2 and not f.any():
+            f[0] = 1
+        c0, l0, t0 = O.ref_huffman(f, True)
+        if l0.max() > 32:
+            continue
+        c1, l1, t1 = oracle.huffman(f, True)
+        assert (c0 == c1).all() and (l0 == l1).all() and t0 == t1, (n, f.tolist())
+
+
+@pytest.mark.parametrize("shape,mb,npr", [("36bp", 9, 2), ("100bp", 20, 2), ("100bp_huffdna", 6, 3), ("150bp_paired", 6, 4),
+                                          ("var50_205", 12, 2), ("title_stress", 5, 2), ("degrade", 2, 2), ("mixed_amb", 3, 5),
+                                          ("100bp", 60, 2)])
+def test_rank_payloads_and_blocks_match_reference(shape, mb, npr, tmp_path, oracle):
+    data = synth.fastq(shape, 100 + mb, target_bytes=mb * 1_000_000 + 4321)
+    src = tmp_path / "in.fastq"
+    data.tofile(src)
+    oracle.run_reference(str(src), str(tmp_path / "out.ngsc"), np_ranks=npr, threads=1)
+    ng = container.read_ngsc(str(tmp_path / "out.ngsc"))
+    for r in range(npr):
+        mine = oracle.compress_rank(data, npr, r)
+        assert ng["per_rank_subblocks"][r] == mine["subblocks"]
+        assert [b["raw"] for b in ng["per_rank_blocks"][r]] == mine["blocks"]
