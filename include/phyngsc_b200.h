@@ -7,8 +7,8 @@
  * patch to phyNGSC.cpp a maintainer would apply.
  *
  * Plain pointers and sizes only; no C++ or torch types.  All compute runs in hand-written sm_100a
- * CUDA kernels; there is no CPU fallback -- every call fails with PHY_ERR_CUDA when no device or no
- * kernel image is usable.
+ * CUDA kernels; there is no CPU fallback -- every compute call fails with PHY_ERR_CUDA when no
+ * device or no kernel image is usable.
  *
  * Threading: one phy_ctx per rank / GPU, calls on a ctx serialised by the caller.  The library
  * never calls MPI (the reference initialises MPI_THREAD_FUNNELED, phyNGSC.cpp:57).
@@ -29,8 +29,8 @@ enum {
   PHY_ERR_FIELDS = -2,      /* separator count differs between titles (reference: warning then UB, :417-421) */
   PHY_ERR_COLORSPACE = -3,  /* colour-space reads (phyNGSC.cpp:473-547) are not implemented                  */
   PHY_ERR_UNSUPPORTED = -4, /* outside the reference's defined domain: >32 title fields, token >512 B,
-                               field max_len == 128 (Q11), Huffman code > 32 bits, read longer than 512, NUL  */
-  PHY_ERR_CAPACITY = -5,    /* a ctx buffer (batch bytes, records, subblocks, output) is too small            */
+                               field max_len == 128 (Q11), Huffman code > 32 bits, read > 32767, NUL bytes    */
+  PHY_ERR_CAPACITY = -5,    /* a ctx buffer (batch bytes, records, arena, output) is too small               */
   PHY_ERR_CUDA = -6,        /* CUDA runtime error / no device; see phy_last_error()                          */
   PHY_ERR_ARG = -7
 };
@@ -50,7 +50,7 @@ typedef struct {
 
 /* One subblock as the reference's loop body produces it. */
 typedef struct {
-  uint64_t win_off;        /* absolute file offset of the window (r_buffer_curr_pos)         */
+  uint64_t win_off;        /* window start relative to the region start (r_buffer_curr_pos - p_wr_start) */
   uint64_t win_len;        /* r_buffer_size used for this window                             */
   uint32_t rec_start;      /* rec_start_pos (non-zero only in the first window of rank > 0)  */
   int32_t overlap;         /* overlap in force (500 or 0, phyNGSC.cpp:123,751)               */
@@ -58,7 +58,7 @@ typedef struct {
   uint32_t warnings;       /* bit0: record cap hit (phyNGSC.cpp:321-326)                     */
   uint64_t bytes_consumed; /* the increment of p_bytes_read (phyNGSC.cpp:745)                */
   uint32_t sec_len[4];     /* info, title, quality, dna stream lengths                       */
-  uint64_t out_off;        /* offset of this payload in the output buffer                    */
+  uint64_t out_off;        /* offset of this payload in the output buffer (16-byte aligned)  */
   uint32_t out_len;        /* p_bytes_to_copy (phyNGSC.cpp:799)                              */
   int32_t status;          /* PHY_OK or the error raised for this subblock                   */
 } phy_subblock_desc;
@@ -68,15 +68,16 @@ typedef struct {
   uint32_t n_batches;
   uint64_t bytes_in;         /* sum of bytes_consumed                                       */
   uint64_t bytes_out;        /* sum of out_len                                              */
+  uint64_t out_used;         /* bytes of the output buffer used (payloads are 16-byte aligned) */
   int32_t wr_overlap;        /* wr_ov_used, for the footer (phyNGSC.cpp:160)                */
-  uint32_t kernel_launches;  /* kernels launched by the last compress call                  */
-  float kernel_ms;           /* CUDA-event time, first kernel launch to last kernel done    */
-  float h2d_ms, d2h_ms;      /* copy times of the last phy_compress_region (0 if resident)  */
+  uint32_t kernel_launches;  /* kernels launched by the call                                */
+  float kernel_ms;           /* CUDA-event time of the kernel legs (first launch to last kernel done, per batch, summed) */
+  float h2d_ms, d2h_ms;      /* CUDA-event time of the copies (0 if resident)               */
 } phy_region_result;
 
-/* Create a context on cuda_device.  max_batch_bytes bounds the bytes resident per batch (input
- * buffer size; <= 3 GiB because window offsets inside a batch are 32-bit); max_subblocks bounds the
- * windows planned per batch.  0 picks defaults (1.25 GiB / 192). */
+/* Create a context on cuda_device.  max_batch_bytes bounds the region bytes resident per batch
+ * (< 4 GiB: positions inside a batch are 32-bit); max_subblocks bounds the windows per batch.
+ * 0 picks defaults (1 GiB + 16 MiB / 192). */
 int phy_ctx_create(phy_ctx **out, int cuda_device, uint64_t max_batch_bytes, uint32_t max_subblocks);
 void phy_ctx_destroy(phy_ctx *ctx);
 
@@ -85,25 +86,32 @@ void phy_ctx_destroy(phy_ctx *ctx);
  *   region      host bytes starting at file offset rank*region (p_wr_start); region_len bytes are
  *               readable (at least up to p_wr_end + 1; more is fine and gives the read-slack
  *               semantics for records longer than `overlap`)
- *   out         host buffer receiving the subblock payloads back to back (info|title|quality|dna)
+ *   out         host buffer receiving the subblock payloads (info|title|quality|dna), payload i at
+ *               out + descs[i].out_off
  *   descs       receives one descriptor per subblock, in order; *inout_n_descs = capacity in, count out
- * Host buffers may be pageable or pinned (pinned makes the copies asynchronous). */
+ * Host buffers may be pageable or pinned (phy_host_alloc; pinned makes the copies asynchronous). */
 int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
                         uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
                         phy_region_result *result);
 
 /* The same work split into its three legs, for callers that keep data resident (and for kernel-only
  * timing): upload copies host bytes into the ctx input buffer; compress_resident runs the kernels over
- * what is resident (single batch: region_len <= max_batch_bytes) leaving payloads in device memory;
- * download copies them out. */
+ * what is resident (single batch: region_len <= max_batch_bytes) leaving payloads in device memory
+ * (descs[i].out_off is then an offset into the device output buffer); download copies them out. */
 int phy_upload(phy_ctx *ctx, const uint8_t *region, uint64_t region_len);
 int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params,
                           phy_subblock_desc *descs, uint32_t *inout_n_descs, phy_region_result *result);
 int phy_download(phy_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 
-/* Raw device pointers of the ctx buffers (for zero-copy producers such as a torch tensor). */
+/* First record of a rank > 0 region: the '@' ... '\n' heuristic of phyNGSC.cpp:131-156.  Returns the
+ * offset inside `region`, or a negative error. */
+int64_t phy_find_first_record(const uint8_t *region, uint64_t region_len);
+
+/* Raw device pointers of the ctx buffers (for zero-copy producers) and pinned host memory. */
 void *phy_device_input(phy_ctx *ctx, uint64_t *capacity);
 void *phy_device_output(phy_ctx *ctx, uint64_t *capacity);
+void *phy_host_alloc(uint64_t bytes);
+void phy_host_free(void *p);
 
 /* Block header exactly as MakeHeader writes it (tasks.cpp:1179-1200); returns bytes written or 0. */
 uint32_t phy_make_block_header(int32_t wrid, int32_t bewr, int32_t bhs, int32_t beso, int32_t bcss,
@@ -112,6 +120,17 @@ uint32_t phy_make_block_header(int32_t wrid, int32_t bewr, int32_t bhs, int32_t 
 int32_t phy_make_footer(int32_t np, uint64_t fastq_size, uint32_t n_blocks, uint32_t n_subblocks,
                         const int32_t *overlaps, const int32_t *block_order, const uint32_t *lb_sizes,
                         uint8_t *out, uint32_t cap);
+
+/* Stage dumps for the parity tests: copies `bytes` bytes at byte offset `offset` of a named device
+ * buffer of the last batch ("te", "se", "rstart", "kx", "qoff", "doff", "plans", "acc", "cls", "arena",
+ * "hdr", "sbout") to dst.  Returns bytes copied or a negative error. */
+int64_t phy_debug_read(phy_ctx *ctx, const char *name, uint64_t offset, void *dst, uint64_t bytes);
+
+/* Per-stage timing for bench.py: with profiling enabled every batch records one CUDA event after each
+ * kernel launch (and synchronises at the end of the batch); phy_profile_read returns the stage names and
+ * their mean duration in ms per batch since profiling was enabled.  Returns the number of stages. */
+int phy_profile(phy_ctx *ctx, int enable);
+int phy_profile_read(phy_ctx *ctx, const char **names, float *ms, int cap);
 
 const char *phy_strerror(int code);
 const char *phy_last_error(phy_ctx *ctx); /* detail of the last failure on ctx (may be "") */

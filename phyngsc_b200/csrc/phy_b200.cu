@@ -1,0 +1,459 @@
+/*
+ * phy_b200.cu -- context, batch scheduling and the C ABI (include/phyngsc_b200.h) of the B200-native
+ * phyNGSC subblock compressor.  Kernels live in phy_kernels.cuh, format logic in phy_core.cuh.
+ * There is no CPU path: every compute entry point needs a CUDA device.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/phyngsc_b200.h"
+#include "phy_kernels.cuh"
+
+using namespace phy;
+
+#define NKERN 16
+
+static_assert(sizeof(phy_subblock_desc) == 72, "phy_subblock_desc layout is part of the ABI");
+
+struct phy_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  u64 max_batch = 0; u32 max_sb = 0; u32 maxrec = 0; u32 arena_words = 0; u64 out_cap = 0; u32 slack = 0;
+  u32 max_tiles = 0;
+  /* device buffers */
+  u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr;
+  u32 *tile_cnt = nullptr, *tile_off = nullptr;
+  PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
+  SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
+  /* pinned host mirrors */
+  BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; SbOut *h_sbout = nullptr; PlanState *h_state = nullptr;
+  u32 launches = 0;
+  u64 resident_len = 0, resident_out = 0;
+  u32 last_S = 0;
+  /* per-kernel timing (phy_profile): one event after every launch of run_batch */
+  bool profile = false;
+  cudaEvent_t pev[NKERN + 1] = {};
+  float pms[NKERN] = {};
+  u32 pcount = 0;
+  std::string err;
+};
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      char buf_[512];                                                                                  \
+      snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+      ctx->err = buf_;                                                                                 \
+      return PHY_ERR_CUDA;                                                                             \
+    }                                                                                                  \
+  } while (0)
+
+static const u32 SPAN_MAX = 96 * 1024;
+
+static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "classify", "zero_hist", "qhist",
+                                          "stat2", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
+
+extern "C" int phy_abi_version(void) { return PHY_ABI_VERSION; }
+
+extern "C" const char *phy_strerror(int code) {
+  switch (code) {
+    case PHY_OK: return "ok";
+    case PHY_ERR_MALFORMED: return "malformed FASTQ record";
+    case PHY_ERR_FIELDS: return "title field count differs between records";
+    case PHY_ERR_COLORSPACE: return "colour-space reads are not implemented";
+    case PHY_ERR_UNSUPPORTED: return "input outside the reference's defined domain";
+    case PHY_ERR_CAPACITY: return "context buffer too small";
+    case PHY_ERR_CUDA: return "CUDA error";
+    case PHY_ERR_ARG: return "bad argument";
+  }
+  return "unknown error";
+}
+
+extern "C" const char *phy_last_error(phy_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+extern "C" void *phy_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
+                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out};
+  for (void *p : dev) if (p) cudaFree(p);
+  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state};
+  for (void *p : host) if (p) cudaFreeHost(p);
+  for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : ctx->pev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { ctx->err = "no such CUDA device"; return PHY_ERR_CUDA; }
+  CK(cudaSetDevice(device));
+  ctx->device = device;
+  ctx->max_batch = max_batch ? max_batch : ((1ull << 30) + (16ull << 20));
+  if (ctx->max_batch >= (1ull << 32) - (1u << 20)) { ctx->err = "max_batch_bytes must be < 4 GiB"; return PHY_ERR_ARG; }
+  ctx->max_sb = max_sb ? max_sb : 192;
+  ctx->maxrec = (u32)(ctx->max_batch / 32) + 1024;
+  ctx->arena_words = (2u << 20) / 4;
+  ctx->out_cap = ctx->max_batch / 2 + (1u << 20);
+  ctx->slack = 64 * 1024;
+  ctx->max_tiles = (u32)((ctx->max_batch + TILE - 1) / TILE) + 1;
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+  CK(cudaMalloc(&ctx->in, ctx->max_batch + 4096));
+  CK(cudaMemset(ctx->in, 0, ctx->max_batch + 4096));
+  CK(cudaMalloc(&ctx->te, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->se, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->rstart, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->kx, (size_t)(ctx->maxrec + 4) * 2));
+  CK(cudaMalloc(&ctx->qoff, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->doff, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
+  CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
+  CK(cudaMalloc(&ctx->plan_state, sizeof(PlanState)));
+  CK(cudaMalloc(&ctx->plans, sizeof(SbPlan) * ctx->max_sb));
+  CK(cudaMalloc(&ctx->hdr, sizeof(BatchHdr)));
+  CK(cudaMalloc(&ctx->acc, sizeof(SbAcc) * ctx->max_sb));
+  CK(cudaMalloc(&ctx->cls, sizeof(SbClass) * ctx->max_sb));
+  CK(cudaMalloc(&ctx->sbout, sizeof(SbOut) * ctx->max_sb));
+  CK(cudaMalloc(&ctx->arena, (size_t)ctx->arena_words * 4 * ctx->max_sb));
+  CK(cudaMalloc(&ctx->out, ctx->out_cap + 64));
+  CK(cudaHostAlloc(&ctx->h_hdr, sizeof(BatchHdr), cudaHostAllocDefault));
+  CK(cudaHostAlloc(&ctx->h_plans, sizeof(SbPlan) * ctx->max_sb, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&ctx->h_sbout, sizeof(SbOut) * ctx->max_sb, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&ctx->h_state, sizeof(PlanState), cudaHostAllocDefault));
+  CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_SMEM));
+  CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
+  return PHY_OK;
+}
+
+extern "C" int phy_ctx_create(phy_ctx **out, int cuda_device, uint64_t max_batch_bytes, uint32_t max_subblocks) {
+  if (!out) return PHY_ERR_ARG;
+  phy_ctx *ctx = new phy_ctx();
+  int rc = ctx_init(ctx, cuda_device, max_batch_bytes, max_subblocks);
+  if (rc) { fprintf(stderr, "phyngsc_b200: %s\n", ctx->err.c_str()); phy_ctx_destroy(ctx); *out = nullptr; return rc; }
+  *out = ctx;
+  return PHY_OK;
+}
+
+extern "C" void *phy_device_input(phy_ctx *ctx, uint64_t *capacity) { if (capacity) *capacity = ctx->max_batch; return ctx->in; }
+extern "C" void *phy_device_output(phy_ctx *ctx, uint64_t *capacity) { if (capacity) *capacity = ctx->out_cap; return ctx->out; }
+
+/* phyNGSC.cpp:131-156 */
+extern "C" int64_t phy_find_first_record(const uint8_t *b, uint64_t lim) {
+  uint64_t c = 0;
+  while (c < lim && b[c] != '@') ++c;
+  uint64_t first_at = c;
+  while (c < lim && b[c] != '\n') ++c;
+  if (c + 1 >= lim) return PHY_ERR_MALFORMED;
+  return (int64_t)((b[c + 1] == '@') ? c + 1 : first_at);
+}
+
+/* Runs every kernel over the batch that is resident in ctx->in[0..len).  `start_pos` = first record of the
+ * next window inside the batch.  On return h_hdr / h_plans / h_sbout describe the batch. */
+static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
+  Dev d;
+  memset(&d, 0, sizeof d);
+  d.in = ctx->in; d.len = len; d.start_pos = start_pos;
+  d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
+  d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff;
+  d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.ntiles = (len + TILE - 1) / TILE;
+  d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
+  d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
+  d.out = ctx->out; d.out_cap = ctx->out_cap;
+  d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
+  d.span_bytes = 0;
+  cudaStream_t st = ctx->stream;
+  ctx->last_S = 0;
+  if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
+  int pi = 0;
+#define PMARK() do { if (ctx->profile) cudaEventRecord(ctx->pev[pi++], st); } while (0)
+  PMARK();
+  k_nl_count<<<d.ntiles, 256, 0, st>>>(d); PMARK();
+  k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
+  k_nl_emit<<<d.ntiles, 256, 0, st>>>(d); PMARK();
+  k_plan<<<1, 32, 0, st>>>(d); PMARK();
+  ctx->launches += 4;
+  CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_state, ctx->plan_state, sizeof(PlanState), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_plans, ctx->plans, sizeof(SbPlan) * ctx->max_sb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const BatchHdr H = *ctx->h_hdr;
+  if (H.status) { ctx->err = std::string("batch failed while splitting records: ") + phy_strerror(H.status); return H.status; }
+  const u32 S = H.S;
+  ctx->last_S = S;
+  if (S == 0) return PHY_OK;
+  u32 span = (u32)((u64)(CH + 1) * H.max_rec_bytes * 9 / 8) + 256;
+  span = (span + 1023) & ~1023u;
+  if (span < 8192) span = 8192;
+  if (span > SPAN_MAX) span = SPAN_MAX;
+  d.span_bytes = span;
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
+  dim3 gc(H.max_chunks, S), gq(H.max_qchunks, S);
+  PMARK();
+  k_stat1<<<gc, CH, span, st>>>(d); PMARK();
+  k_classify<<<S, 32, 0, st>>>(d); PMARK();
+  k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d); PMARK();
+  k_qhist<<<gq, 256, QH_SMEM, st>>>(d); PMARK();
+  k_stat2<<<gc, CH, span, st>>>(d); PMARK();
+  k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
+  k_lengths<<<gc, CH, span, st>>>(d); PMARK();
+  k_layout<<<S, 256, 0, st>>>(d); PMARK();
+  k_outscan<<<1, 256, 0, st>>>(d); PMARK();
+  k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
+  k_emit<<<gc, CH, span, st>>>(d); PMARK();
+  ctx->launches += 11;
+  CK(cudaGetLastError());
+  if (ctx->profile) {
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < NKERN && i + 1 < pi; ++i) { float t = 0; cudaEventElapsedTime(&t, ctx->pev[i], ctx->pev[i + 1]); ctx->pms[i] += t; }
+    ctx->pcount++;
+  }
+  CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_sbout, ctx->sbout, sizeof(SbOut) * S, cudaMemcpyDeviceToHost, st));
+  return PHY_OK;
+}
+
+static void fill_descs(phy_ctx *ctx, u32 S, u64 out_base, phy_subblock_desc *descs) {
+  for (u32 i = 0; i < S; ++i) {
+    const SbPlan &P = ctx->h_plans[i];
+    const SbOut &O = ctx->h_sbout[i];
+    phy_subblock_desc &D = descs[i];
+    D.win_off = P.win_off; D.win_len = P.win_len; D.rec_start = P.rec_start; D.overlap = P.overlap;
+    D.n_records = P.n_records; D.warnings = P.warnings; D.bytes_consumed = P.bytes_consumed;
+    for (int k = 0; k < 4; ++k) D.sec_len[k] = O.sec_len[k];
+    D.out_off = out_base + O.out_off; D.out_len = O.out_len; D.status = O.status;
+  }
+}
+
+static int init_plan(phy_ctx *ctx, const uint8_t *region_host, u64 region_len, const phy_region_params *p, u32 first_rec_start_known,
+                     bool have_first, PlanState &st) {
+  if (!p || p->np < 1 || p->rank < 0 || p->rank >= p->np || p->window_bytes == 0 || p->file_size == 0) { ctx->err = "bad region parameters"; return PHY_ERR_ARG; }
+  u32 first = 0;
+  if (p->rank != 0) {
+    if (have_first) first = first_rec_start_known;
+    else {
+      int64_t f = phy_find_first_record(region_host, region_len);
+      if (f < 0) { ctx->err = "no record start found at the beginning of the region"; return (int)f; }
+      first = (u32)f;
+    }
+  }
+  plan_init(st, p->file_size, p->np, p->rank, p->window_bytes, p->overlap, p->record_cap, first);
+  if ((u64)st.wr_len > region_len) { ctx->err = "region_len is shorter than the rank's working region"; return PHY_ERR_ARG; }
+  return PHY_OK;
+}
+
+extern "C" int phy_upload(phy_ctx *ctx, const uint8_t *region, uint64_t region_len) {
+  if (!ctx || !region) return PHY_ERR_ARG;
+  if (region_len == 0 || region_len > ctx->max_batch) { ctx->err = "region does not fit one batch"; return PHY_ERR_CAPACITY; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->in, region, region_len, cudaMemcpyHostToDevice, ctx->stream));
+  /* 64 bytes of zero padding behind the data: vector loads may run past the end */
+  CK(cudaMemsetAsync(ctx->in + region_len, 0, 64, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->resident_len = region_len;
+  return PHY_OK;
+}
+
+/* last rank whose file does not end in '\n': the reference's arithmetic still places the next record
+ * start one byte past the end; a virtual newline gives the splitter the same view */
+static int patch_trailing_newline(phy_ctx *ctx, u64 &len, bool is_last_rank, bool batch_final, u8 last_byte) {
+  if (is_last_rank && batch_final && last_byte != '\n') {
+    const u8 nl = '\n';
+    CK(cudaMemcpyAsync(ctx->in + len, &nl, 1, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    len += 1;
+  }
+  return PHY_OK;
+}
+
+extern "C" int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params,
+                                     phy_subblock_desc *descs, uint32_t *inout_n_descs, phy_region_result *result) {
+  if (!ctx || !descs || !inout_n_descs) return PHY_ERR_ARG;
+  if (region_len == 0 || region_len != ctx->resident_len) { ctx->err = "resident bytes do not match region_len"; return PHY_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  PlanState st;
+  u32 first = 0;
+  if (params && params->rank != 0) {
+    /* the head of the region is needed on the host for the '@' heuristic */
+    u64 n = region_len < 65536 ? region_len : 65536;
+    std::string head(n, '\0');
+    CK(cudaMemcpy(&head[0], ctx->in, n, cudaMemcpyDeviceToHost));
+    int64_t f = phy_find_first_record((const uint8_t *)head.data(), n);
+    if (f < 0) { ctx->err = "no record start found at the beginning of the region"; return (int)f; }
+    first = (u32)f;
+  }
+  int rc = init_plan(ctx, nullptr, region_len, params, first, true, st);
+  if (rc) return rc;
+  u8 last_byte = '\n';
+  if (st.is_last) CK(cudaMemcpy(&last_byte, ctx->in + region_len - 1, 1, cudaMemcpyDeviceToHost));
+  u64 len = region_len;
+  rc = patch_trailing_newline(ctx, len, st.is_last, true, last_byte);
+  if (rc) return rc;
+  *ctx->h_state = st;
+  ctx->launches = 0;
+  CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  rc = run_batch(ctx, (u32)len, first, 0, (i64)len, true);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const u32 S = ctx->last_S;
+  if (!ctx->h_state->done) { ctx->err = "batch did not cover the region (raise max_subblocks)"; return ctx->h_state->status ? ctx->h_state->status : PHY_ERR_CAPACITY; }
+  if (S > *inout_n_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
+  fill_descs(ctx, S, 0, descs);
+  *inout_n_descs = S;
+  ctx->resident_out = ctx->h_hdr->total_out;
+  int worst = 0;
+  if (result) {
+    memset(result, 0, sizeof *result);
+    result->n_subblocks = S; result->n_batches = 1; result->wr_overlap = (int32_t)first; result->kernel_launches = ctx->launches;
+    result->out_used = ctx->h_hdr->total_out;
+    CK(cudaEventElapsedTime(&result->kernel_ms, ctx->ev[0], ctx->ev[1]));
+    for (u32 i = 0; i < S; ++i) { result->bytes_in += descs[i].bytes_consumed; result->bytes_out += descs[i].out_len; }
+  }
+  for (u32 i = 0; i < S; ++i) if (descs[i].status < worst) worst = descs[i].status;
+  if (worst) ctx->err = std::string("a subblock failed: ") + phy_strerror(worst);
+  return worst;
+}
+
+extern "C" int phy_download(phy_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+  if (!ctx || !out) return PHY_ERR_ARG;
+  if (ctx->resident_out > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->out, ctx->resident_out, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (out_len) *out_len = ctx->resident_out;
+  return PHY_OK;
+}
+
+extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
+                                   uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
+                                   phy_region_result *result) {
+  if (!ctx || !region || !out || !descs || !inout_n_descs || region_len == 0) return PHY_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  PlanState st;
+  int rc = init_plan(ctx, region, region_len, params, 0, false, st);
+  if (rc) return rc;
+  const u32 first = st.rec_start;
+  *ctx->h_state = st;
+  ctx->launches = 0;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  const u32 cap_descs = *inout_n_descs;
+  u32 nd = 0, nb = 0;
+  u64 out_used = 0, base = 0, next_pos = 0; /* base: region-relative start of the batch; next_pos: chain position */
+  float k_ms = 0, h2d_ms = 0, d2h_ms = 0;
+  int worst = 0;
+  bool done = false;
+  while (!done) {
+    u64 blen = region_len - base;
+    if (blen > ctx->max_batch) blen = ctx->max_batch;
+    const bool final = base + blen == region_len;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaMemcpyAsync(ctx->in, region + base, blen, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->in + blen, 0, 64, s));
+    u64 len = blen;
+    rc = patch_trailing_newline(ctx, len, st.is_last, final, region[region_len - 1]);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[1], s));
+    u32 start_pos = (u32)(next_pos - base) + (nb == 0 ? first : 0u);
+    rc = run_batch(ctx, (u32)len, start_pos, (i64)base, (i64)region_len, final);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[2], s));
+    CK(cudaStreamSynchronize(s));
+    const u32 S = ctx->last_S;
+    const PlanState hs = *ctx->h_state;
+    if (hs.status) { ctx->err = std::string("window chaining failed: ") + phy_strerror(hs.status); return hs.status; }
+    if (S == 0 && !hs.done) { ctx->err = "a window does not fit one batch (raise max_batch_bytes)"; return PHY_ERR_CAPACITY; }
+    if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
+    const u64 tot = S ? ctx->h_hdr->total_out : 0;
+    if (out_used + tot > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
+    CK(cudaEventRecord(ctx->ev[3], s));
+    if (tot) CK(cudaMemcpyAsync(out + out_used, ctx->out, tot, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaStreamSynchronize(s));
+    fill_descs(ctx, S, out_used, descs + nd);
+    float t;
+    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1])); h2d_ms += t;
+    CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); k_ms += t;
+    CK(cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4])); d2h_ms += t;
+    nd += S; out_used += tot; ++nb;
+    done = hs.done != 0;
+    next_pos = (u64)hs.bytes_read;
+    if (!done) {
+      if (final) { ctx->err = "region exhausted before the working region was covered"; return PHY_ERR_MALFORMED; }
+      base = next_pos & ~(u64)255;
+    }
+  }
+  *inout_n_descs = nd;
+  if (result) {
+    memset(result, 0, sizeof *result);
+    result->n_subblocks = nd; result->n_batches = nb; result->wr_overlap = (int32_t)first; result->kernel_launches = ctx->launches;
+    result->kernel_ms = k_ms; result->h2d_ms = h2d_ms; result->d2h_ms = d2h_ms; result->out_used = out_used;
+    for (u32 i = 0; i < nd; ++i) { result->bytes_in += descs[i].bytes_consumed; result->bytes_out += descs[i].out_len; }
+  }
+  for (u32 i = 0; i < nd; ++i) if (descs[i].status < worst) worst = descs[i].status;
+  if (worst) ctx->err = std::string("a subblock failed: ") + phy_strerror(worst);
+  return worst;
+}
+
+extern "C" int phy_profile(phy_ctx *ctx, int enable) {
+  if (!ctx) return PHY_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (enable && !ctx->pev[0]) for (auto &e : ctx->pev) CK(cudaEventCreate(&e));
+  ctx->profile = enable != 0;
+  for (auto &m : ctx->pms) m = 0;
+  ctx->pcount = 0;
+  return PHY_OK;
+}
+
+extern "C" int phy_profile_read(phy_ctx *ctx, const char **names, float *ms, int cap) {
+  if (!ctx) return PHY_ERR_ARG;
+  int n = cap < NKERN ? cap : NKERN;
+  for (int i = 0; i < n; ++i) { if (names) names[i] = KERNEL_NAMES[i]; if (ms) ms[i] = ctx->pcount ? ctx->pms[i] / ctx->pcount : 0.f; }
+  return n;
+}
+
+extern "C" int64_t phy_debug_read(phy_ctx *ctx, const char *name, uint64_t offset, void *dst, uint64_t bytes) {
+  if (!ctx || !name || !dst) return PHY_ERR_ARG;
+  struct { const char *n; const void *p; u64 size; } tab[] = {
+      {"te", ctx->te, (u64)ctx->maxrec * 4}, {"se", ctx->se, (u64)ctx->maxrec * 4}, {"rstart", ctx->rstart, (u64)ctx->maxrec * 4},
+      {"kx", ctx->kx, (u64)ctx->maxrec * 2}, {"qoff", ctx->qoff, (u64)ctx->maxrec * 4}, {"doff", ctx->doff, (u64)ctx->maxrec * 4},
+      {"plans", ctx->plans, sizeof(SbPlan) * ctx->max_sb}, {"acc", ctx->acc, sizeof(SbAcc) * ctx->max_sb},
+      {"cls", ctx->cls, sizeof(SbClass) * ctx->max_sb}, {"arena", ctx->arena, (u64)ctx->arena_words * 4 * ctx->max_sb},
+      {"hdr", ctx->hdr, sizeof(BatchHdr)}, {"sbout", ctx->sbout, sizeof(SbOut) * ctx->max_sb}, {"out", ctx->out, ctx->out_cap}};
+  for (auto &e : tab)
+    if (!strcmp(e.n, name)) {
+      if (offset > e.size) return PHY_ERR_ARG;
+      u64 n = bytes < e.size - offset ? bytes : e.size - offset;
+      if (cudaMemcpy(dst, (const u8 *)e.p + offset, n, cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->err = "debug read failed"; return PHY_ERR_CUDA; }
+      return (int64_t)n;
+    }
+  /* sizes of the internal records, for test harnesses that want to decode the dumps */
+  if (!strcmp(name, "sizeof")) {
+    u32 v[6] = {(u32)sizeof(SbPlan), (u32)sizeof(SbAcc), (u32)sizeof(SbClass), (u32)sizeof(BatchHdr), (u32)sizeof(SbOut), ctx->arena_words};
+    u64 n = bytes < sizeof v ? bytes : sizeof v;
+    memcpy(dst, v, n);
+    return (int64_t)n;
+  }
+  return PHY_ERR_ARG;
+}

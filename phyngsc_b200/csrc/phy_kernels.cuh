@@ -1,0 +1,837 @@
+/*
+ * phy_kernels.cuh -- sm_100a kernels of the phyNGSC subblock compressor (included by phy_b200.cu).
+ *
+ * Data layout in HBM for one batch (a slice of one rank's working region):
+ *   in[len + slack]            the FASTQ bytes, batch-relative positions are uint32
+ *   te[r], se[r], rstart[r]    record table: newline ending the title line / the sequence line, first byte
+ *   kx[r]                      kept DNA length | transfer flag << 15          (phyNGSC.cpp:549-588)
+ *   qoff[r], doff[r]           bit offset of the record inside the quality / DNA body
+ *   plans[s], acc[s], cls[s]   per-subblock window, reduced statistics, coding decisions (phy_core.cuh)
+ *   arena[s][ARENA_WORDS]      per-subblock histograms, Huffman tables, tree blobs, header staging
+ *   out[]                      payloads info|title|quality|dna, 16-byte aligned per subblock
+ *
+ * Stages (one launch each, every launch covers all subblocks of the batch):
+ *   nl_count -> nl_scan -> nl_emit      record splitter            (phyNGSC.cpp:254-331)
+ *   plan                                window chaining            (phyNGSC.cpp:168-250, 744-755)
+ *   stat1                               validation, ambiguity transfer, DNA/quality alphabets, title field
+ *                                       reductions                 (phyNGSC.cpp:383-423, 462-653; tasks.cpp:22-223)
+ *   classify, zero                      coding decisions + arena   (tasks.cpp:196-257)
+ *   qhist, stat2                        per-position quality histogram, numeric/char histograms,
+ *                                       32-record block descriptors (tasks.cpp:64-93,127-182,260-286)
+ *   huff                                one warp per table         (huffman.cpp:18-118)
+ *   lengths -> layout -> outscan        bit lengths, scans, header assembly, payload offsets
+ *   zero_out -> emit                    BitStream emission         (tasks.cpp:393-509,544-557,609-619)
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include "phy_core.cuh"
+
+namespace phy {
+
+constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
+constexpr int TILE = 16384;        /* bytes per newline-index tile                                         */
+constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
+constexpr u32 QH_SMEM = 64 * 1024; /* private histogram rows of one quality-histogram CTA                  */
+constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
+
+struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
+  u32 NL, NR;          /* newlines found, complete records                                      */
+  u32 S;               /* subblocks planned in this batch                                       */
+  u32 max_chunks;      /* max over subblocks of ceil(n_records / CH)                            */
+  u32 max_rec_bytes;   /* max over subblocks of ceil(bytes / records)                           */
+  i32 status;          /* batch-level error (capacity ...)                                      */
+  u64 total_out;       /* bytes of output used                                                  */
+  u64 next_pos;        /* region-relative position where the next window starts                 */
+  u32 max_qchunks, pad;
+};
+
+struct SbOut {         /* device -> host, one per subblock */
+  u64 out_off; u32 out_len; i32 status; u32 sec_len[4];
+};
+
+struct Dev {
+  const u8 *in; u32 len;      /* batch bytes                                                   */
+  u32 start_pos;              /* first record start inside the batch                           */
+  u32 *te, *se, *rstart; u32 maxrec;
+  u16 *kx; u32 *qoff, *doff;
+  u32 *tile_cnt, *tile_off; u32 ntiles;
+  PlanState *plan_state; SbPlan *plans; u32 max_sb;
+  BatchHdr *hdr;
+  SbAcc *acc; SbClass *cls; SbOut *sbout;
+  u32 *arena; u32 arena_words;
+  u8 *out; u64 out_cap;
+  i64 batch_base, region_len; i32 batch_is_final; u32 slack;
+  u32 span_bytes;             /* dynamic shared memory available for record spans              */
+};
+
+/* ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ u32 nl_count16(uint4 v) {
+  const u32 NL4 = 0x0A0A0A0Au;
+  return (__popc(__vcmpeq4(v.x, NL4)) + __popc(__vcmpeq4(v.y, NL4)) + __popc(__vcmpeq4(v.z, NL4)) + __popc(__vcmpeq4(v.w, NL4))) >> 3;
+}
+
+/* newlines in this thread's 64 bytes [p, p+64) restricted to [lo, hi) */
+__device__ __forceinline__ u32 nl_count64(const u8 *in, u32 p, u32 lo, u32 hi) {
+  if (p >= hi || p + 64 <= lo) return 0;
+  u32 n = 0;
+  if (p >= lo && p + 64 <= hi) {
+    const uint4 *q = (const uint4 *)(in + p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n += nl_count16(__ldg(q + k));
+  } else {
+    for (u32 i = (p < lo ? lo : p); i < p + 64 && i < hi; ++i) n += in[i] == '\n';
+  }
+  return n;
+}
+
+__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warp_sums /*[8]*/, u32 &total) {
+  u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u32 x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
+  if (lane == 31) warp_sums[w] = x;
+  __syncthreads();
+  u32 base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { u32 s = warp_sums[k]; if ((u32)k < w) base += s; tot += s; }
+  total = tot;
+  __syncthreads();
+  return base + x - v;
+}
+
+/* (a) record splitter, pass 1: newline count per 16 KiB tile */
+__global__ void __launch_bounds__(256) k_nl_count(Dev d) {
+  __shared__ u32 ws[8];
+  u32 t = blockIdx.x;
+  u32 p = t * TILE + threadIdx.x * 64;
+  u32 n = nl_count64(d.in, p, d.start_pos, d.len);
+  u32 tot;
+  block_excl_scan_256(n, ws, tot);
+  if (threadIdx.x == 0) d.tile_cnt[t] = tot;
+}
+
+/* exclusive scan over tiles (single CTA) */
+__global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
+  __shared__ u32 part[1024];
+  u32 per = (d.ntiles + 1023) / 1024;
+  u32 b = threadIdx.x * per, e = min(b + per, d.ntiles);
+  u32 s = 0;
+  for (u32 i = b; i < e; ++i) s += d.tile_cnt[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 run = 0;
+    for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; }
+    d.hdr->NL = run; d.hdr->NR = run / 4;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_rec_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    if (run / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
+    d.rstart[0] = d.start_pos;
+  }
+  __syncthreads();
+  u32 run = part[threadIdx.x];
+  for (u32 i = b; i < e; ++i) { d.tile_off[i] = run; run += d.tile_cnt[i]; }
+}
+
+/* (a) record splitter, pass 2: line l = 4r+k ends at the l-th newline; k=0 title, 1 sequence, 3 quality */
+__global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
+  __shared__ u32 ws[8];
+  if (d.hdr->status) return;
+  u32 t = blockIdx.x;
+  u32 p = t * TILE + threadIdx.x * 64;
+  u32 n = nl_count64(d.in, p, d.start_pos, d.len);
+  u32 tot;
+  u32 l = d.tile_off[t] + block_excl_scan_256(n, ws, tot);
+  if (!n) return;
+  u32 lo = max(p, d.start_pos), hi = min(p + 64, d.len);
+  for (u32 i = lo; i < hi; ++i) {
+    if (d.in[i] != '\n') continue;
+    u32 r = l >> 2, k = l & 3;
+    if (k == 0) d.te[r] = i; else if (k == 1) d.se[r] = i; else if (k == 3) d.rstart[r + 1] = i + 1;
+    ++l;
+  }
+}
+
+/* ---- window chaining: one warp walks the rank's windows (phyNGSC.cpp:168-250, 744-755) -------------- */
+/* first j in [lo, hi) with a[j] >= target (hi if none); a is ascending.  32 probes per step: three windows
+ * of growing stride centred on `guess` (the caller's interpolation), then 32-ary narrowing. */
+__device__ __forceinline__ void wlb_probe(const u32 *a, i64 target, u32 base, u32 step, u32 &L, u32 &H) {
+  u32 lane = threadIdx.x & 31;
+  u64 idx = (u64)base + (u64)lane * step;
+  bool ge = idx < (u64)H ? ((i64)a[idx] >= target) : true;
+  u32 bal = __ballot_sync(0xFFFFFFFFu, ge);
+  if (bal == 0) { u64 nl = (u64)base + 31ull * step + 1; if (nl > L) L = (u32)(nl < H ? nl : H); return; }
+  u32 k = __ffs(bal) - 1;
+  u64 hit = (u64)base + (u64)k * step;
+  u32 nL = L;
+  if (k > 0) { u64 x = (u64)base + (u64)(k - 1) * step + 1; if (x > nL) nL = (u32)x; }
+  if (hit < (u64)H) H = (u32)hit;
+  L = nL < H ? nL : H;
+}
+__device__ u32 warp_lower_bound(const u32 *a, u32 lo, u32 hi, i64 target, i64 guess) {
+  u32 L = lo, H = hi;
+  const u32 strides[3] = {1, 8, 64};
+  for (int t = 0; t < 3 && L < H; ++t) {
+    i64 bs = guess - 16 * (i64)strides[t];
+    u32 base = bs < (i64)L ? L : (bs > (i64)H - 1 ? H - 1 : (u32)bs);
+    wlb_probe(a, target, base, strides[t], L, H);
+  }
+  while (L < H) wlb_probe(a, target, L, (H - L + 31) / 32, L, H);
+  return L;
+}
+
+__global__ void __launch_bounds__(32) k_plan(Dev d) {
+  PlanState st = *d.plan_state;
+  BatchHdr *H = d.hdr;
+  u32 lane = threadIdx.x;
+  if (H->status || st.done || st.status) { if (lane == 0) { H->S = 0; H->next_pos = (u64)st.bytes_read; } return; }
+  const u32 NR = H->NR, NL = H->NL;
+  u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0, max_rec_bytes = 0, max_qchunks = 0;
+  i64 avg = 128;
+  while (!st.done && S < d.max_sb) {
+    i64 ws = st.bytes_read - d.batch_base; /* batch-relative window start */
+    if (!d.batch_is_final && ws + st.rsize + (i64)d.slack > (i64)d.len) break;
+    i64 readable = (i64)d.len - ws;
+    i64 lim = st.rsize < readable ? st.rsize : readable;
+    SbPlan P;
+    P.win_off = (u64)st.bytes_read; P.win_len = (u64)st.rsize; P.rec_start = st.rec_start; P.overlap = st.overlap;
+    P.first_rec = F; P.n_records = 0; P.warnings = 0; P.status = 0; P.bytes_consumed = 0; P.chunk_base = chunk_base; P.pad = 0;
+    if (F >= NR) { st.status = E_MALFORMED; break; }
+    i64 target = ws + st.rsize - st.overlap, size_lim = ws + lim;
+    u32 last = F;
+    bool capped = false;
+    if (4ull * (F + 1) < NL && (i64)d.te[F + 1] < size_lim) {
+      i64 guess = (i64)F + (target - (ws + st.rec_start)) / avg;
+      u32 m = warp_lower_bound(d.rstart, F + 2, NR + 1, target, guess);
+      last = m - 1;
+      if (last > F + st.record_cap) { last = F + st.record_cap; capped = true; }
+      while (last > F && !(4ull * last < NL && (i64)d.te[last] < size_lim)) { --last; capped = false; }
+      if (last >= NR) { st.status = E_MALFORMED; break; }
+    }
+    P.n_records = last - F + 1;
+    P.warnings = capped ? 1u : 0u;
+    P.bytes_consumed = (u64)((i64)d.rstart[last + 1] - ws);
+    if (lane == 0) d.plans[S] = P;
+    u32 nch = (P.n_records + CH - 1) / CH;
+    chunk_base += nch;
+    max_chunks = max(max_chunks, nch);
+    max_qchunks = max(max_qchunks, (P.n_records + QCH - 1) / QCH);
+    avg = max((i64)16, (i64)(P.bytes_consumed / P.n_records));
+    max_rec_bytes = max(max_rec_bytes, (u32)((P.bytes_consumed + P.n_records - 1) / P.n_records));
+    ++S; F = last + 1;
+    /* phyNGSC.cpp:745-755 */
+    st.bytes_read += (i64)P.bytes_consumed;
+    if (st.bytes_read + st.rsize > st.wr_len - 1) { if (st.is_last) st.overlap = 0; st.rsize = st.wr_len - 1 - st.bytes_read; }
+    st.rec_start = 0;
+    st.done = st.bytes_read >= st.region;
+    st.n_subblocks_total++;
+  }
+  if (lane == 0) {
+    H->S = S; H->max_chunks = max_chunks; H->max_rec_bytes = max_rec_bytes; H->max_qchunks = max_qchunks;
+    H->next_pos = (u64)st.bytes_read;
+    if (st.status) H->status = st.status;
+    *d.plan_state = st;
+  }
+}
+
+/* ---- record spans in shared memory ------------------------------------------------------------------- */
+/* Copies bytes [lo, hi) of the batch (16-byte granules) into shared memory and returns a pointer p with
+ * p[pos] valid for batch positions pos in [lo, hi); falls back to the global buffer when the span does
+ * not fit.  All threads of the CTA must call it. */
+__device__ __forceinline__ const u8 *stage_span(const u8 *in, u32 lo, u32 hi, u8 *smem, u32 smem_bytes) {
+  u32 alo = lo & ~15u;
+  u32 n = hi - alo;
+  if (n > smem_bytes) return in;
+  for (u32 i = threadIdx.x * 16; i < n; i += blockDim.x * 16) *(uint4 *)(smem + i) = __ldg((const uint4 *)(in + alo + i));
+  __syncthreads();
+  return smem - alo;
+}
+
+/* per-CTA copy of what the per-record code needs from SbClass */
+struct ClsS {
+  u32 nf, nnc, nq, plain, R, nb_len;
+  u32 tabdesc_off, flagbits_off, blkoff_off, tq0, tdna;
+};
+
+/* ---- stat1 ---------------------------------------------------------------------------------------------- */
+struct Stat1S {
+  u32 facc[MAXF][8];
+  u32 mism[MAXF][MASKW];
+  u32 dna[256];
+  u32 qp[8];
+  u32 maxq, maxs;
+  i32 err;
+  u32 nf, ts0, te0;
+  u32 off0[MAXF], len0[MAXF];
+  u32 pvals0[MAXF];
+  u32 vals[MAXF][CH];
+  u8 r0[R0_MAX];
+};
+
+__global__ void __launch_bounds__(CH) k_stat1(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ Stat1S S;
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const SbPlan P = d.plans[s];
+  if (P.status || chunk * CH >= P.n_records) return;
+  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
+  for (u32 i = tid; i < sizeof(Stat1S) / 4 - R0_MAX / 4 - MAXF * CH; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
+  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  __syncthreads();
+  /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
+  const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
+  const bool r0_ok = te0 - ts0 + 1 <= R0_MAX;
+  if (r0_ok) for (u32 i = tid; i <= te0 - ts0; i += CH) S.r0[i] = d.in[ts0 + i];
+  __syncthreads();
+  if (tid == 0) {
+    S.ts0 = ts0; S.te0 = te0;
+    if (!r0_ok) S.err = E_UNSUPPORTED;
+    else {
+      TitleCursor c; c.init(S.r0, 0, te0 - ts0);
+      Tok t; u32 nf = 0;
+      while (c.next(t)) { if (nf < (u32)MAXF) { S.off0[nf] = t.start; S.len0[nf] = t.end - t.start; } ++nf; }
+      S.nf = nf;
+      if (nf == 0 || nf > (u32)MAXF) S.err = E_UNSUPPORTED;
+    }
+  }
+  __syncthreads();
+  const u32 nf = S.nf;
+  const bool seed_ok = S.err == 0;
+  const bool active = tid < nrec;
+  const u32 r = r0 + (active ? tid : 0);
+  const u32 ts = d.rstart[r], te = d.te[r], se = d.se[r], nx = d.rstart[r + 1];
+  const u32 L = se - te - 1, qs = se + 3;
+  i32 err = 0;
+  if (active) {
+    if (L == 0 || b[se + 1] != '+' || b[se + 2] != '\n' || nx != 2 * se - te + 3) err = E_MALFORMED;
+    else if (L > (u32)MAX_READ) err = E_UNSUPPORTED;
+    else if (r == P.first_rec) { /* colour space, phyNGSC.cpp:473-487: not implemented */
+      u8 c0 = b[te + 1], c1 = b[te + 2];
+      if ((c0 >= '0' && c0 <= '3') || (c1 >= '0' && c1 <= '3')) err = E_COLORSPACE;
+    }
+  }
+  /* sequence / quality */
+  u32 kept = 0, acgt0 = 0, acgt1 = 0, acgt2 = 0, acgt3 = 0, myL = 0;
+  if (active && !err) {
+    SeqStat st;
+    u64 qm = 0; /* quality bytes 33..96 seen by this thread */
+    seqqual_stat(b, te + 1, L, qs, st,
+                 [&](u8 c) { atomicAdd(&S.dna[c], 1u); },
+                 [&](u8 q) {
+                   u32 k = (u32)q - 33u;
+                   if (k < 64u) qm |= 1ull << k;
+                   else if (!((S.qp[q >> 5] >> (q & 31)) & 1u)) atomicOr(&S.qp[q >> 5], 1u << (q & 31));
+                 });
+    if (st.err) err = E_UNSUPPORTED;
+    kept = st.kept; myL = L;
+    acgt0 = st.acgt[0]; acgt1 = st.acgt[1]; acgt2 = st.acgt[2]; acgt3 = st.acgt[3];
+    d.kx[r] = (u16)(st.kept | (st.xfer << 15));
+    /* bits 33..63 -> word 1 bits 1..31; 64..95 -> word 2; 96 -> word 3 bit 0 */
+    u32 w1 = (u32)(qm << 1), w2 = (u32)(qm >> 31), w3 = (u32)(qm >> 63);
+    if (w1 & ~S.qp[1]) atomicOr(&S.qp[1], w1);
+    if (w2 & ~S.qp[2]) atomicOr(&S.qp[2], w2);
+    if (w3 & ~S.qp[3]) atomicOr(&S.qp[3], w3);
+  }
+  {
+    u32 a0 = __reduce_add_sync(0xFFFFFFFFu, acgt0), a1 = __reduce_add_sync(0xFFFFFFFFu, acgt1);
+    u32 a2 = __reduce_add_sync(0xFFFFFFFFu, acgt2), a3 = __reduce_add_sync(0xFFFFFFFFu, acgt3);
+    u32 mq = __reduce_max_sync(0xFFFFFFFFu, myL), ms = __reduce_max_sync(0xFFFFFFFFu, kept);
+    if (lane == 0) {
+      if (a0) atomicAdd(&S.dna['A'], a0);
+      if (a1) atomicAdd(&S.dna['C'], a1);
+      if (a2) atomicAdd(&S.dna['G'], a2);
+      if (a3) atomicAdd(&S.dna['T'], a3);
+      atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms);
+    }
+  }
+  /* title: field count, then per-field reductions (tasks.cpp:22-223 as closed forms) */
+  if (active && !err && seed_ok && count_seps(b, ts, te) != nf) err = E_FIELDS;
+  const bool ok = active && !err && seed_ok;
+  TitleCursor cur; cur.init(b, ts, te);
+  for (u32 f = 0; f < nf && seed_ok; ++f) {
+    Tok t; t.start = t.end = 0; t.v = 0; t.num = true;
+    u32 len = 0;
+    if (ok) {
+      cur.next(t);
+      len = t.end - t.start;
+      const u32 len0 = S.len0[f], m = len < len0 ? len : len0;
+      const u8 *d0 = S.r0 + S.off0[f];
+      for (u32 p = 0; p < m; ++p)
+        if (b[t.start + p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
+    }
+    S.vals[f][tid] = t.v;
+    u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
+    u32 mx = __reduce_max_sync(0xFFFFFFFFu, ok ? len : 0u);
+    u32 nn = __ballot_sync(0xFFFFFFFFu, ok && !t.num);
+    u32 kv = key_of((i32)t.v);
+    u32 kmax = __reduce_max_sync(0xFFFFFFFFu, ok ? kv : 0u);
+    u32 kinv = __reduce_max_sync(0xFFFFFFFFu, ok ? ~kv : 0u);
+    if (lane == 0) {
+      atomicMax(&S.facc[f][0], inv_min); atomicMax(&S.facc[f][1], mx);
+      if (nn) S.facc[f][2] = 1;
+      atomicMax(&S.facc[f][3], kmax); atomicMax(&S.facc[f][4], kinv);
+    }
+  }
+  /* the record before this chunk, for the first delta */
+  if (tid == 0 && chunk > 0 && seed_ok) {
+    u32 pts = d.rstart[r0 - 1], pte = d.te[r0 - 1];
+    TitleCursor pc; pc.init(b, pts, pte);
+    Tok t;
+    for (u32 f = 0; f < nf; ++f) { if (!pc.next(t)) break; S.pvals0[f] = t.v; }
+  }
+  __syncthreads();
+  for (u32 f = 0; f < nf && seed_ok; ++f) {
+    const bool hasd = ok && r > P.first_rec;
+    u32 pv = tid > 0 ? S.vals[f][tid - 1] : S.pvals0[f];
+    u32 kd = key_of((i32)(S.vals[f][tid] - pv));
+    u32 kmax = __reduce_max_sync(0xFFFFFFFFu, hasd ? kd : 0u);
+    u32 kinv = __reduce_max_sync(0xFFFFFFFFu, hasd ? ~kd : 0u);
+    if (lane == 0) { atomicMax(&S.facc[f][5], kmax); atomicMax(&S.facc[f][6], kinv); }
+  }
+  if (err) atomicMin(&S.err, err);
+  __syncthreads();
+  /* flush to the subblock accumulators */
+  SbAcc *A = d.acc + s;
+  if (tid == 0) {
+    if (S.err) atomicMin(&A->status, S.err);
+    atomicMax(&A->max_qlen, S.maxq); atomicMax(&A->max_slen, S.maxs);
+  }
+  if (tid < 8 && S.qp[tid]) atomicOr(&A->qpresent[tid], S.qp[tid]);
+  for (u32 i = tid; i < 256; i += CH) if (S.dna[i]) atomicAdd(&A->dna_occ[i], S.dna[i]);
+  if (seed_ok)
+    for (u32 i = tid; i < nf * 8; i += CH) {
+      u32 f = i >> 3, k = i & 7, v = S.facc[f][k];
+      u32 *dst = &A->f[f].inv_min_len + k;
+      if (v) atomicMax(dst, v);
+    }
+  if (seed_ok)
+    for (u32 i = tid; i < nf * MASKW; i += CH) {
+      u32 f = i / MASKW, k = i % MASKW, v = S.mism[f][k];
+      if (v) atomicOr(&A->f[f].mism[k], v);
+    }
+}
+
+/* ---- classify + zero ------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(32) k_classify(Dev d) {
+  u32 s = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const SbPlan P = d.plans[s];
+  SbClass &C = d.cls[s];
+  if (P.status) { C.status = P.status; C.R = P.n_records; C.payload_len = 0; return; }
+  u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
+  classify_subblock(d.in, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
+  C.payload_len = 0;
+}
+
+__global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
+  u32 s = blockIdx.y;
+  const SbClass &C = d.cls[s];
+  if (C.status) return;
+  u32 *a = d.arena + (size_t)s * d.arena_words;
+  for (u32 i = C.zero_begin + blockIdx.x * 256 + threadIdx.x; i < C.zero_end; i += gridDim.x * 256) a[i] = 0;
+}
+
+/* ---- per-position quality histogram (tasks.cpp:260-286) ----------------------------------------------------- */
+/* Row (position) p of a private histogram copy is owned by exactly one thread, so the increments need no
+ * atomics; the CTA flushes its non-zero counters to the subblock's table with atomicAdd at the end. */
+__global__ void __launch_bounds__(256) k_qhist(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ u32 m_qs[QCH];
+  __shared__ u16 m_len[QCH];
+  __shared__ u8 m_x[QCH];
+  __shared__ u8 qcode[256];
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const SbClass &C = d.cls[s];
+  if (C.status || chunk * QCH >= C.R) return;
+  const SbPlan P = d.plans[s];
+  const u32 r0 = P.first_rec + chunk * QCH, nrec = min((u32)QCH, C.R - chunk * QCH);
+  const u32 Lp = C.max_qlen, nq = C.nq, stride = nq | 1u;
+  u32 *gq = d.arena + (size_t)s * d.arena_words + C.qstat_off;
+  for (u32 i = tid; i < 256; i += 256) qcode[i] = C.qua_code[i];
+  for (u32 i = tid; i < nrec; i += 256) {
+    u32 te = d.te[r0 + i], se = d.se[r0 + i];
+    m_qs[i] = se + 3; m_len[i] = (u16)(se - te - 1); m_x[i] = (u8)(d.kx[r0 + i] >> 15);
+  }
+  u32 *hist = (u32 *)dyn_smem;
+  u32 slots = Lp <= 256 ? 256 / Lp : 1;
+  u32 fit = QH_SMEM / (Lp * stride * 4);
+  if (slots > fit) slots = fit;
+  if (slots == 0) { /* rows do not fit in shared memory: count straight into the global table */
+    __syncthreads();
+    for (u32 i = 0; i < nrec; ++i) {
+      u32 qs = m_qs[i], L = m_len[i];
+      for (u32 p = tid; p < L; p += 256) {
+        u8 q = d.in[qs + p];
+        if (m_x[i]) { u32 a = amb_code(d.in[qs - 3 - L + p]); if (a > 1) q = xfer_qual(a, q); }
+        u32 c = qcode[q];
+        atomicAdd(&gq[(p + 1) * nq + c], 1u); atomicAdd(&gq[c], 1u);
+      }
+    }
+    return;
+  }
+  for (u32 i = tid; i < slots * Lp * stride; i += 256) hist[i] = 0;
+  __syncthreads();
+  if (Lp <= 256) {
+    const u32 slot = tid / Lp, p = tid % Lp;
+    if (slot < slots) {
+      u32 *row = hist + (slot * Lp + p) * stride;
+      for (u32 i = slot; i < nrec; i += slots) {
+        u32 L = m_len[i];
+        if (p < L) {
+          u32 qs = m_qs[i];
+          u8 q = d.in[qs + p];
+          if (m_x[i]) { u32 a = amb_code(d.in[qs - 3 - L + p]); if (a > 1) q = xfer_qual(a, q); }
+          row[qcode[q]]++;
+        }
+      }
+    }
+  } else {
+    for (u32 i = 0; i < nrec; ++i) {
+      u32 L = m_len[i], qs = m_qs[i];
+      for (u32 p = tid; p < L; p += 256) {
+        u8 q = d.in[qs + p];
+        if (m_x[i]) { u32 a = amb_code(d.in[qs - 3 - L + p]); if (a > 1) q = xfer_qual(a, q); }
+        hist[p * stride + qcode[q]]++;
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 i = tid; i < Lp * nq; i += 256) {
+    u32 p = i / nq, c = i % nq, v = 0;
+    for (u32 k = 0; k < slots; ++k) v += hist[(k * Lp + p) * stride + c];
+    if (v) { atomicAdd(&gq[(p + 1) * nq + c], v); atomicAdd(&gq[c], v); }
+  }
+}
+
+/* ---- shared pieces of the per-record title kernels ------------------------------------------------------------ */
+struct TitleS {
+  FieldClass fc[MAXF];
+  u32 vals[MAXF][CH];
+  u32 pvals0[MAXF];
+};
+
+/* loads the field classes, parses every record's numeric token values into S.vals (and the record before
+ * the chunk into S.pvals0) so that deltas never need a second walk */
+__device__ __forceinline__ void title_prepare(const Dev &d, const SbClass &C, const u8 *b, TitleS &S, u32 r0, u32 nrec, u32 chunk) {
+  const u32 tid = threadIdx.x;
+  for (u32 i = tid; i < C.nf * (sizeof(FieldClass) / 4); i += CH) ((u32 *)S.fc)[i] = ((const u32 *)C.f)[i];
+  if (tid < nrec) {
+    u32 r = r0 + tid;
+    TitleCursor c; c.init(b, d.rstart[r], d.te[r]);
+    Tok t;
+    for (u32 f = 0; f < C.nf; ++f) { if (!c.next(t)) break; S.vals[f][tid] = t.v; }
+  }
+  if (tid == 0 && chunk > 0) {
+    TitleCursor c; c.init(b, d.rstart[r0 - 1], d.te[r0 - 1]);
+    Tok t;
+    for (u32 f = 0; f < C.nf; ++f) { if (!c.next(t)) break; S.pvals0[f] = t.v; }
+  }
+  __syncthreads();
+}
+
+struct PrevFromS {
+  const TitleS *S; u32 tid;
+  __device__ __forceinline__ i32 operator()(u32 f) const { return (i32)(tid > 0 ? S->vals[f][tid - 1] : S->pvals0[f]); }
+};
+
+/* ---- stat2: numeric / char histograms and 32-record block descriptors (tasks.cpp:64-93, 127-182) --------------- */
+__device__ __forceinline__ void warp_hist_add(u32 *hist, u32 idx, bool on) {
+  u32 key = on ? idx : 0xFFFFFFFFu;
+  u32 m = __match_any_sync(0xFFFFFFFFu, key);
+  if (on && (u32)(__ffs(m) - 1) == (threadIdx.x & 31)) atomicAdd(hist + idx, (u32)__popc(m));
+}
+
+__global__ void __launch_bounds__(CH) k_stat2(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ TitleS S;
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const SbClass &C = d.cls[s];
+  if (C.status || chunk * CH >= C.R) return;
+  if (C.nnc == 0) { /* every field constant: all block flags are irrelevant */ return; }
+  const SbPlan P = d.plans[s];
+  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
+  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  title_prepare(d, C, b, S, r0, nrec, chunk);
+  const bool active = tid < nrec;
+  const u32 r = r0 + (active ? tid : 0);
+  const u32 nf = C.nf;
+  TitleCursor cur; cur.init(b, d.rstart[r], d.te[r]);
+  u32 flags = 0;
+  /* number of records of this warp's block */
+  const u32 wbase = tid & ~31u;
+  for (u32 f = 0; f < nf; ++f) {
+    Tok t; t.start = t.end = 0; t.v = 0; t.num = false;
+    if (active) cur.next(t);
+    const FieldClass &F = S.fc[f];
+    if (F.kind == K_CONST) continue;
+    bool pred = true;
+    if (F.kind == K_STR) {
+      u32 len = t.end - t.start;
+      u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
+      if (active) {
+        pred = len == len_lo;
+        for (u32 j = 0; pred && j < len; ++j) pred = b[t.start + j] == b[st_lo + j];
+        const u16 *sm = (const u16 *)(arena + F.slotmap_off);
+        for (u32 j = 0; j < len; ++j)
+          if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
+            u32 tab = sm[j < 128 ? j : 128];
+            atomicAdd(arena + td[tab].freq_off + b[t.start + j], 1u);
+          }
+      }
+    } else {
+      i32 v = (i32)S.vals[f][tid];
+      i32 pv = (i32)(tid > 0 ? S.vals[f][tid - 1] : S.pvals0[f]);
+      i32 dl = wsub(v, pv);
+      bool hasd = active && r > P.first_rec;
+      if (F.is_delta) {
+        /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
+        i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
+        if (nrec - wbase < 2) bd = 0;
+        pred = !active || lane < 2 || dl == bd;
+        bool all = __all_sync(0xFFFFFFFFu, pred);
+        pred = all && bd == F.min_d;
+        if (F.has_table) warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(dl, F.base), hasd);
+      } else {
+        i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
+        pred = !active || v == v_lo;
+        pred = __all_sync(0xFFFFFFFFu, pred);
+        if (F.has_table) {
+          warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(v, F.base), active);
+          if (active && r == P.first_rec) atomicAdd(arena + td[F.tab].freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
+        }
+      }
+    }
+    if (F.kind == K_STR) pred = __all_sync(0xFFFFFFFFu, pred);
+    if (pred) flags |= 1u << f;
+  }
+  if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (chunk * CH + wbase) / 32] = flags;
+}
+
+/* ---- Huffman build: one warp per table ------------------------------------------------------------------------- */
+struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+
+__global__ void __launch_bounds__(128) k_huff(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  HuffScratch *HS = (HuffScratch *)dyn_smem;
+  const u32 s = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SbClass &C = d.cls[s];
+  if (C.status) return;
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  TableDesc *td = (TableDesc *)(arena + C.tabdesc_off);
+  for (u32 t = blockIdx.x * 4 + w; t < C.ntab; t += gridDim.x * 4) {
+    TableDesc D = td[t];
+    u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS[w], lane, 32u, WarpSync());
+    if (lane == 0) td[t].tree_len = blob;
+    __syncwarp();
+  }
+}
+
+/* ---- lengths ----------------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(CH) k_lengths(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ TitleS S;
+  __shared__ u8 codes[512];
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const SbClass &C = d.cls[s];
+  if (C.status || chunk * CH >= C.R) return;
+  const SbPlan P = d.plans[s];
+  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
+  for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
+  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  title_prepare(d, C, b, S, r0, nrec, chunk);
+  const bool active = tid < nrec;
+  const u32 r = r0 + (active ? tid : 0);
+  const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
+  u32 tbits = 0;
+  if (active) {
+    const u32 kx = d.kx[r];
+    const bool xfer = kx >> 15;
+    CountSink q; q.init();
+    quality_record(b, te + 1, L, se + 3, xfer, codes, (const u64 *)(arena + td[C.tq0].cl_off), C.nq, q);
+    d.qoff[r] = (u32)q.bits;
+    if (C.plain) d.doff[r] = 2 * (kx & 0x7FFFu);
+    else {
+      CountSink dn; dn.init();
+      dna_record(b, te + 1, L, xfer, false, codes + 256, (const u64 *)(arena + td[C.tdna].cl_off), dn);
+      d.doff[r] = (u32)dn.bits;
+    }
+    if (C.nnc) {
+      const u32 blk = (chunk * CH + tid) / 32;
+      CountSink t; t.init();
+      PrevFromS pv; pv.S = &S; pv.tid = tid;
+      title_record(b, d.rstart[r], te, C, S.fc, arena, arena[C.flagbits_off + blk], lane == 0, pv, t);
+      tbits = (u32)t.bits;
+    }
+  }
+  u32 sum = __reduce_add_sync(0xFFFFFFFFu, tbits);
+  const u32 wbase = tid & ~31u;
+  if (lane == 0 && wbase < nrec) arena[C.blkoff_off + (chunk * CH + wbase) / 32] = (C.nnc + sum + 7) / 8;
+}
+
+/* ---- layout: headers, scans, section sizes ------------------------------------------------------------------------ */
+/* in-place exclusive scan of a[0..n) by one 256-thread CTA; returns the total (64-bit) */
+__device__ u64 cta_scan_inplace(u32 *a, u32 n, u32 *ws, bool wide_check, i32 *overflow) {
+  u64 carry = 0;
+  for (u32 base = 0; base < n; base += 256) {
+    u32 i = base + threadIdx.x;
+    u32 v = i < n ? a[i] : 0u, tot;
+    u32 ex = block_excl_scan_256(v, ws, tot);
+    u64 o = carry + ex;
+    if (wide_check && i < n && o > 0xFFFFFFFFull) *overflow = 1;
+    if (i < n) a[i] = (u32)o;
+    carry += tot;
+  }
+  return carry;
+}
+
+__global__ void __launch_bounds__(256) k_layout(Dev d) {
+  __shared__ u32 ws[8];
+  __shared__ i32 ovf, okh;
+  const u32 s = blockIdx.x, tid = threadIdx.x;
+  SbClass &C = d.cls[s];
+  if (C.status) return;
+  const SbPlan P = d.plans[s];
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  if (tid == 0) { ovf = 0; okh = layout_headers(d.in, C, arena) ? 1 : 0; }
+  __syncthreads();
+  if (!okh) { if (tid == 0) C.status = E_UNSUPPORTED; return; }
+  /* copy the tree blobs to their place in the staged headers, one warp per table */
+  {
+    const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
+    u8 *stage = (u8 *)(arena + C.stage_off);
+    for (u32 t = tid >> 5; t < C.ntab; t += 8) {
+      const u8 *src = (const u8 *)(arena + td[t].tree_off);
+      u8 *dst = stage + td[t].dst;
+      for (u32 i = tid & 31; i < td[t].tree_len; i += 32) dst[i] = src[i];
+    }
+  }
+  u64 qb = cta_scan_inplace(d.qoff + P.first_rec, C.R, ws, true, &ovf);
+  u64 db = cta_scan_inplace(d.doff + P.first_rec, C.R, ws, true, &ovf);
+  u64 tb = C.nnc ? cta_scan_inplace(arena + C.blkoff_off, C.nblk, ws, true, &ovf) : 0;
+  __syncthreads();
+  if (tid == 0) {
+    if (ovf || tb > 0x7FFFFFFFull || qb > 0x3FFFFFFFFull || db > 0x3FFFFFFFFull) { C.status = E_CAPACITY; return; }
+    finish_layout(C, (u32)tb, qb, db);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_outscan(Dev d) {
+  if (threadIdx.x != 0) return;
+  u32 S = d.hdr->S;
+  u64 off = 0;
+  for (u32 s = 0; s < S; ++s) {
+    SbClass &C = d.cls[s];
+    SbOut o;
+    o.status = C.status; o.out_off = off; o.out_len = C.status ? 0u : C.payload_len;
+    o.sec_len[0] = C.info_len; o.sec_len[1] = C.title_len; o.sec_len[2] = C.qual_len; o.sec_len[3] = C.dna_len;
+    if (!C.status && off + C.payload_len > d.out_cap) { C.status = E_CAPACITY; o.status = E_CAPACITY; o.out_len = 0; }
+    C.out_off = off;
+    d.sbout[s] = o;
+    off += (o.out_len + 15u) & ~15u;
+  }
+  d.hdr->total_out = off;
+}
+
+__global__ void __launch_bounds__(256) k_zero_out(Dev d) {
+  u64 n16 = (d.hdr->total_out + 15) / 16;
+  uint4 z = make_uint4(0, 0, 0, 0);
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n16; i += (u64)gridDim.x * 256) ((uint4 *)d.out)[i] = z;
+}
+
+/* ---- emit ------------------------------------------------------------------------------------------------------------ */
+/* `base` is 4-byte aligned */
+__device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
+  if (v) atomicOr((u32 *)(base + (pos & ~3u)), (u32)v << (8 * (pos & 3u)));
+}
+__global__ void __launch_bounds__(CH) k_emit(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ TitleS S;
+  __shared__ u8 codes[512];
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const SbClass &C = d.cls[s];
+  if (C.status || chunk * CH >= C.R) return;
+  const SbPlan P = d.plans[s];
+  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
+  u8 *out = d.out + C.out_off;
+  u32 *outw = (u32 *)d.out;
+  const u64 obase = C.out_off; /* byte offset of the payload inside d.out (16-byte aligned) */
+  for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
+  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  title_prepare(d, C, b, S, r0, nrec, chunk);
+  const u32 o_title = C.info_len, o_qual = o_title + C.title_len, o_dna = o_qual + C.qual_len;
+  if (chunk == 0) {
+    /* fixed part of the info stream (phyNGSC.cpp:719-730) and the three staged headers.  Bytes are OR-ed
+     * into the zeroed payload word-atomically because a header may end inside a word whose other bytes
+     * belong to a bit stream written by another thread. */
+    if (tid == 0) {
+      u8 fx[INFO_FIXED];
+      ByteWriter w; w.p = fx; w.n = 0;
+      w.word(C.R); w.word(C.max_qlen); w.word(C.max_slen);
+      w.byte((u8)C.nsym); w.byte(0); w.byte((u8)C.nq); w.word(C.flags);
+      for (u32 i = 0; i < INFO_FIXED; ++i) or_byte(out, i, fx[i]);
+    }
+    const u8 *stage = (const u8 *)(arena + C.stage_off);
+    for (u32 i = tid; i < C.thdr_len; i += CH) or_byte(out, o_title + i, stage[i]);
+    for (u32 i = tid; i < C.qhdr_len; i += CH) or_byte(out, o_qual + i, stage[C.thdr_cap + i]);
+    for (u32 i = tid; i < C.dhdr_len; i += CH) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
+  }
+  const bool active = tid < nrec;
+  const u32 r = r0 + (active ? tid : 0);
+  const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
+  const u32 i_sb = chunk * CH + tid; /* record index inside the subblock */
+  u32 tbits = 0;
+  const u32 blk = i_sb / 32;
+  const u32 flags = (active && C.nnc) ? arena[C.flagbits_off + blk] : 0u;
+  PrevFromS pv; pv.S = &S; pv.tid = tid;
+  if (active) {
+    const u32 kx = d.kx[r];
+    const bool xfer = kx >> 15;
+    { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
+      OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * C.nb_len);
+      k.put(L, C.nb_len); k.finish();
+    }
+    {
+      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + d.qoff[r]);
+      quality_record(b, te + 1, L, se + 3, xfer, codes, (const u64 *)(arena + td[C.tq0].cl_off), C.nq, q);
+      q.finish();
+    }
+    {
+      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + d.doff[r]);
+      dna_record(b, te + 1, L, xfer, C.plain != 0, codes + 256, C.plain ? (const u64 *)nullptr : (const u64 *)(arena + td[C.tdna].cl_off), dn);
+      dn.finish();
+    }
+    if (C.nnc) {
+      CountSink t; t.init();
+      title_record(b, d.rstart[r], te, C, S.fc, arena, flags, lane == 0, pv, t);
+      tbits = (u32)t.bits;
+    }
+  }
+  if (C.nnc) {
+    /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509) */
+    u32 x = tbits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
+    const u32 before = x - tbits;
+    if (active) {
+      OrSink t; t.init(outw, (obase + o_title + C.thdr_len + arena[C.blkoff_off + blk]) * 8 + (lane == 0 ? 0u : C.nnc + before));
+      if (lane == 0) {
+        u32 v = 0;
+        for (u32 f = 0; f < C.nf; ++f) if (S.fc[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
+        t.put(v, C.nnc);
+      }
+      title_record(b, d.rstart[r], te, C, S.fc, arena, flags, lane == 0, pv, t);
+      t.finish();
+    }
+  }
+}
+
+}  // namespace phy

@@ -1,0 +1,109 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-minted goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gpu_cases
+from phyngsc_b200 import api, container, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx(oracle):
+    c = api.Context(0, max_batch_bytes=64 << 20, max_subblocks=256)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", gpu_cases.CASES, ids=[c[0] for c in gpu_cases.CASES])
+def test_payloads_bit_exact_against_oracle(case, ctx):
+    probs = gpu_cases.run_case(ctx, case)
+    assert not probs, "\n".join(probs[:20])
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(GOLD, "manifest.json"))), ids=lambda c: c["file"])
+def test_payloads_bit_exact_against_reference_goldens(case, ctx):
+    data = synth.fastq(case["shape"], case["seed"], target_bytes=case["target_bytes"])
+    ng = container.read_ngsc(os.path.join(GOLD, case["file"]))
+    for r in range(case["np"]):
+        start, _ = api.region_slice(data.size, case["np"], r)
+        descs, out, res = ctx.compress_region(data[start:], api.region_params(data.size, case["np"], r))
+        assert api.payloads(descs, out) == ng["per_rank_subblocks"][r]
+        assert res.wr_overlap == ng["footer"]["overlaps"][r]
+
+
+def test_multi_batch_equals_single_batch(oracle):
+    data = synth.fastq("100bp", 41, target_bytes=6_000_000)
+    prm = api.region_params(data.size, 1, 0, window_bytes=512 * 1024)
+    big = api.Context(0, max_batch_bytes=32 << 20, max_subblocks=64)
+    small = api.Context(0, max_batch_bytes=(3 << 20) // 2, max_subblocks=64)
+    try:
+        d1, o1, r1 = big.compress_region(data, prm)
+        d2, o2, r2 = small.compress_region(data, prm)
+        assert r1.n_batches == 1 and r2.n_batches > 2
+        assert api.payloads(d1, o1) == api.payloads(d2, o2)
+        assert [(d.win_off, d.win_len, d.n_records) for d in d1] == [(d.win_off, d.win_len, d.n_records) for d in d2]
+        assert api.payloads(d1, o1) == oracle.compress_rank(data, 1, 0, window_bytes=512 * 1024)["subblocks"]
+    finally:
+        big.close(); small.close()
+
+
+def test_resident_legs_match_region_call(ctx):
+    data = synth.fastq("36bp", 42, target_bytes=3_000_000)
+    prm = api.region_params(data.size, 1, 0, window_bytes=1 << 20)
+    d1, o1, _ = ctx.compress_region(data, prm)
+    ctx.upload(data)
+    d2, res = ctx.compress_resident(data.size, prm)
+    o2 = np.empty(res.out_used, np.uint8)
+    assert ctx.download(o2) == res.out_used
+    assert api.payloads(d1, o1) == api.payloads(d2, o2)
+    assert res.kernel_launches >= 10 and res.kernel_ms > 0
+
+
+def test_malformed_inputs_are_errors(ctx):
+    good = synth.fastq("36bp", 43, target_bytes=200_000)
+    prm = lambda a: api.region_params(a.size, 1, 0)  # noqa: E731
+    # line 3 is not '+'
+    bad = good.copy()
+    plus = int(np.flatnonzero(bad == ord("+"))[5])
+    bad[plus] = ord("-")
+    with pytest.raises(api.PhyError) as e:
+        ctx.compress_region(bad, prm(bad))
+    assert e.value.code == -1
+    # a title with one separator more than record 0
+    txt = good.tobytes().split(b"\n")
+    txt[4 * 7] = txt[4 * 7].replace(b"/2", b"/2/3")
+    bad = np.frombuffer(b"\n".join(txt), np.uint8)
+    with pytest.raises(api.PhyError) as e:
+        ctx.compress_region(bad, prm(bad))
+    assert e.value.code == -2
+    # quality shorter than the sequence
+    txt = good.tobytes().split(b"\n")
+    txt[4 * 3 + 3] = txt[4 * 3 + 3][:-2]
+    bad = np.frombuffer(b"\n".join(txt), np.uint8)
+    with pytest.raises(api.PhyError) as e:
+        ctx.compress_region(bad, prm(bad))
+    assert e.value.code == -1
+    # the ctx still works afterwards
+    d, o, _ = ctx.compress_region(good, prm(good))
+    assert len(d) == 1 and d[0].status == 0
+
+
+def test_roundtrip_properties_at_full_window_size(ctx):
+    """Size-independent checks on a 64 MB input: every desc chains to the next, record counts add up,
+    the info stream's header words agree with the descriptor."""
+    data = synth.fastq("150bp_paired", 44, target_bytes=64_000_000)
+    d, out, res = ctx.compress_region(data, api.region_params(data.size, 1, 0))
+    assert res.bytes_in == data.size and sum(x.bytes_consumed for x in d) == data.size
+    pos = 0
+    for x in d:
+        assert x.win_off == pos and x.status == 0
+        pos += x.bytes_consumed
+        p = out[x.out_off:x.out_off + 19].tobytes()
+        assert int.from_bytes(p[0:4], "big") == x.n_records and int.from_bytes(p[4:8], "big") == 150
+        assert x.out_len == sum(x.sec_len)
+    assert sum(x.n_records for x in d) == int((data == 10).sum()) // 4
