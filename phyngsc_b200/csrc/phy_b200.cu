@@ -25,7 +25,7 @@ struct phy_ctx {
   u64 max_batch = 0; u32 max_sb = 0; u32 maxrec = 0; u32 arena_words = 0; u64 out_cap = 0; u32 slack = 0;
   u32 max_tiles = 0;
   /* device buffers */
-  u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr;
+  u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr;
   u32 *tile_cnt = nullptr, *tile_off = nullptr;
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
@@ -86,7 +86,7 @@ extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state};
@@ -121,6 +121,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaMalloc(&ctx->kx, (size_t)(ctx->maxrec + 4) * 2));
   CK(cudaMalloc(&ctx->qoff, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->doff, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->toff, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->plan_state, sizeof(PlanState)));
@@ -135,8 +136,8 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaHostAlloc(&ctx->h_plans, sizeof(SbPlan) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_sbout, sizeof(SbOut) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_state, sizeof(PlanState), cudaHostAllocDefault));
-  CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
-  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
+  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
   CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
   CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_SMEM));
@@ -173,7 +174,7 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   memset(&d, 0, sizeof d);
   d.in = ctx->in; d.len = len; d.start_pos = start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
-  d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff;
+  d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff;
   d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
@@ -184,7 +185,20 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   ctx->last_S = 0;
   if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
   int pi = 0;
-#define PMARK() do { if (ctx->profile) cudaEventRecord(ctx->pev[pi++], st); } while (0)
+  static const bool dbg_sync = getenv("PHY_DEBUG_SYNC") != nullptr; /* fault isolation: synchronise after every launch */
+#define PMARK()                                                                                                   \
+  do {                                                                                                            \
+    if (ctx->profile) cudaEventRecord(ctx->pev[pi], st);                                                          \
+    if (dbg_sync) {                                                                                               \
+      cudaError_t e_ = cudaStreamSynchronize(st);                                                                 \
+      if (e_ == cudaSuccess) e_ = cudaGetLastError();                                                             \
+      if (e_ != cudaSuccess) {                                                                                    \
+        ctx->err = std::string("after stage ") + (pi ? KERNEL_NAMES[pi - 1] : "start") + ": " + cudaGetErrorString(e_); \
+        return PHY_ERR_CUDA;                                                                                      \
+      }                                                                                                           \
+    }                                                                                                             \
+    ++pi;                                                                                                         \
+  } while (0)
   PMARK();
   k_nl_count<<<d.ntiles, 256, 0, st>>>(d); PMARK();
   k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
@@ -205,14 +219,16 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   if (span < 8192) span = 8192;
   if (span > SPAN_MAX) span = SPAN_MAX;
   d.span_bytes = span;
+  d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
+  const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
   dim3 gc(H.max_chunks, S), gq(H.max_qchunks, S);
   PMARK();
-  k_stat1<<<gc, CH, span, st>>>(d); PMARK();
+  k_stat1<<<gc, CH, span_v, st>>>(d); PMARK();
   k_classify<<<S, 32, 0, st>>>(d); PMARK();
   k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d); PMARK();
   k_qhist<<<gq, 256, QH_SMEM, st>>>(d); PMARK();
-  k_stat2<<<gc, CH, span, st>>>(d); PMARK();
+  k_stat2<<<gc, CH, span_v, st>>>(d); PMARK();
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
   k_lengths<<<gc, CH, span, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
@@ -438,6 +454,7 @@ extern "C" int64_t phy_debug_read(phy_ctx *ctx, const char *name, uint64_t offse
   struct { const char *n; const void *p; u64 size; } tab[] = {
       {"te", ctx->te, (u64)ctx->maxrec * 4}, {"se", ctx->se, (u64)ctx->maxrec * 4}, {"rstart", ctx->rstart, (u64)ctx->maxrec * 4},
       {"kx", ctx->kx, (u64)ctx->maxrec * 2}, {"qoff", ctx->qoff, (u64)ctx->maxrec * 4}, {"doff", ctx->doff, (u64)ctx->maxrec * 4},
+      {"toff", ctx->toff, (u64)ctx->maxrec * 4},
       {"plans", ctx->plans, sizeof(SbPlan) * ctx->max_sb}, {"acc", ctx->acc, sizeof(SbAcc) * ctx->max_sb},
       {"cls", ctx->cls, sizeof(SbClass) * ctx->max_sb}, {"arena", ctx->arena, (u64)ctx->arena_words * 4 * ctx->max_sb},
       {"hdr", ctx->hdr, sizeof(BatchHdr)}, {"sbout", ctx->sbout, sizeof(SbOut) * ctx->max_sb}, {"out", ctx->out, ctx->out_cap}};

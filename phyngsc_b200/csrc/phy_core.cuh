@@ -34,6 +34,7 @@ constexpr int CHARPOS = 129;   /* per-position char tables 0..127 + the shared o
 constexpr int NUMH = 512;      /* numeric Huffman table only if the range is <= 512          */
 constexpr int MAX_READ = 32767;/* kept-count + transfer flag packed in 16 bits               */
 constexpr u32 NOTAB = 0xFFFFu;
+constexpr u32 CHUNK_RECORDS = 128; /* records per GPU work item; offsets inside the streams are kept per chunk + local */
 
 enum { K_CONST = 0, K_NUM = 1, K_STR = 2 };
 
@@ -107,13 +108,16 @@ struct OrSink {
   u64 acc;    /* pending bits, right-aligned            */
   u32 fill;   /* number of pending bits incl. the leading pad of the first word */
   bool shared_first;
-  PHY_HD void init(u32 *words, u64 bitpos) {
+  bool live;  /* false: walk without storing (lanes that only keep a warp converged) */
+  PHY_HD void init(u32 *words, u64 bitpos, bool live_ = true) {
     w = words + (bitpos >> 5);
     fill = (u32)(bitpos & 31);
     acc = 0;
     shared_first = fill != 0;
+    live = live_;
   }
   PHY_HD void flush_word(u32 word, bool shared) {
+    if (!live) return;
     u32 v = bswap32(word);
 #if defined(__CUDA_ARCH__)
     if (shared) atomicOr(w, v); else *w = v;
@@ -203,7 +207,9 @@ struct SbClass {
   u32 ts0, te0;                /* title line of record 0 (batch-relative positions)                   */
   /* arena layout (word offsets unless stated) */
   u32 ntab, tabdesc_off, tq0, tdna, qstat_off, zero_begin, zero_end;
-  u32 nblk, flagbits_off, blkoff_off;
+  u32 nblk, flagbits_off;
+  u32 blkloc_off;              /* per 32-record title block: byte offset inside its chunk */
+  u32 nchunk, chunk_off;       /* per 128-record chunk: [3][nchunk] totals -> bases of quality bits, dna bits, title bytes */
   u32 stage_off;               /* header staging: title | quality | dna header bytes                  */
   u32 thdr_cap, qhdr_cap, dhdr_cap;
   u32 arena_used;
@@ -431,7 +437,9 @@ PHY_HDN void classify_subblock(const u8 *b, const SbAcc &A, u32 R, u32 ts0, u32 
   for (u32 f = 0; f < nf; ++f) if (C.f[f].kind == K_STR) C.f[f].slotmap_off = al.take((CHARPOS + 1) / 2 + 1);
   C.nblk = (R + 31) / 32;
   C.flagbits_off = al.take(C.nblk);
-  C.blkoff_off = al.take(C.nblk + 1);
+  C.blkloc_off = al.take(C.nblk);
+  C.nchunk = (R + CHUNK_RECORDS - 1) / CHUNK_RECORDS;
+  C.chunk_off = al.take(3 * C.nchunk);
   if (al.used & 1) al.take(1); /* 8-byte alignment for the code tables */
   u32 cl_off = al.used;
   u64 cl_words = 2ull * ((u64)(C.max_qlen + 1) * nq + (C.plain ? 0 : nsym) + (u64)ntab_chr * 256);
@@ -574,9 +582,10 @@ PHY_HD void dna_record(const u8 *b, u32 ss, u32 L, bool xfer, bool plain, const 
 }
 
 /* Title tokens of one record (tasks.cpp:427-506).  `flags` has bit f set when field f's block flag is
- * 1; `first` = first record of its 32-record block; prev(f) yields the previous record's numeric value
- * of field f (only called for delta-coded fields of non-first records); tables are reached through
- * `arena` (table directory + slot maps). */
+ * 1; `first` = first record of its 32-record block; prev(f, v) yields the previous record's numeric value
+ * of field f given this record's value v -- it is called for EVERY numeric field of EVERY record, in field
+ * order, so that on the GPU it can be a warp shuffle (lane = record of the block; all 32 lanes walk
+ * together); tables are reached through `arena` (table directory + slot maps). */
 template <class Sink, class Prev>
 PHY_HD void title_record(const u8 *b, u32 ts, u32 te, const SbClass &C, const FieldClass *FC, const u32 *arena, u32 flags,
                          bool first, Prev prev, Sink &s) {
@@ -590,10 +599,14 @@ PHY_HD void title_record(const u8 *b, u32 ts, u32 te, const SbClass &C, const Fi
     bool flag = (flags >> f) & 1u;
     if (F.kind == K_NUM) {
       i32 v = (i32)t.v;
+      i32 pv = prev(f, v);
       if (first) s.put((u32)wsub(v, F.min_v), F.bits_val);
       else if (!flag) {
-        u32 x = F.is_delta ? (u32)wsub(wsub(v, prev(f)), F.min_d) : (u32)wsub(v, F.min_v);
-        if (F.has_table) { u64 e = ((const u64 *)(arena + td[F.tab].cl_off))[x]; s.put((u32)e, (u32)(e >> 32)); }
+        u32 x = F.is_delta ? (u32)wsub(wsub(v, pv), F.min_d) : (u32)wsub(v, F.min_v);
+        if (F.has_table) { /* x < diff for real records; lanes that only shadow a record may see anything */
+          u64 e = ((const u64 *)(arena + td[F.tab].cl_off))[x < F.diff ? x : 0u];
+          s.put((u32)e, (u32)(e >> 32));
+        }
         else s.put(x, F.bits_num);
       }
       continue;
@@ -623,10 +636,11 @@ struct ByteWriter {
  * assigns each tree blob its destination (TableDesc::dst = byte offset inside the staging area; the
  * blobs themselves are copied afterwards, possibly in parallel, by copy_tree_blobs).  Returns false when
  * a table failed to build (tree_len == 0). */
-PHY_HDN bool layout_headers(const u8 *b, SbClass &C, u32 *arena) {
-  TableDesc *td = (TableDesc *)(arena + C.tabdesc_off);
+/* tlen[t] = blob length of table t (in), tdst[t] = its byte offset inside the staging area (out); the
+ * caller moves them from / to the table directory (the GPU keeps them in shared memory meanwhile). */
+PHY_HDN bool layout_headers(const u8 *b, SbClass &C, u32 *arena, const u32 *tlen, u32 *tdst) {
   u8 *stage = (u8 *)(arena + C.stage_off);
-  for (u32 i = 0; i < C.ntab; ++i) if (td[i].tree_len == 0) return false;
+  for (u32 i = 0; i < C.ntab; ++i) if (tlen[i] == 0) return false;
   ByteWriter w; w.p = stage; w.n = 0;
   w.word(C.nf); /* tasks.cpp:302 */
   for (u32 f = 0; f < C.nf; ++f) {
@@ -638,7 +652,7 @@ PHY_HDN bool layout_headers(const u8 *b, SbClass &C, u32 *arena) {
     w.byte(F.kind == K_NUM ? 1 : 0);
     if (F.kind == K_NUM) {
       w.word((u32)F.min_v); w.word((u32)F.max_v); w.word((u32)F.min_d); w.word((u32)F.max_d);
-      if (F.has_table) { td[F.tab].dst = w.n; w.n += td[F.tab].tree_len; }
+      if (F.has_table) { tdst[F.tab] = w.n; w.n += tlen[F.tab]; }
       continue;
     }
     w.byte(F.is_len_const);
@@ -654,7 +668,7 @@ PHY_HDN bool layout_headers(const u8 *b, SbClass &C, u32 *arena) {
     for (u32 j = 0; j < (u32)CHARPOS; ++j) {
       u32 tid = sm[j];
       if (tid == NOTAB) continue;
-      td[tid].dst = w.n; w.n += td[tid].tree_len;
+      tdst[tid] = w.n; w.n += tlen[tid];
     }
   }
   C.thdr_len = w.n;
@@ -663,13 +677,13 @@ PHY_HDN bool layout_headers(const u8 *b, SbClass &C, u32 *arena) {
   u32 qb = C.thdr_cap;
   w.n = qb;
   for (u32 i = 0; i < C.nq; ++i) w.byte(C.quals[i]);
-  for (u32 p = 0; p <= C.max_qlen; ++p) { td[C.tq0 + p].dst = w.n; w.n += td[C.tq0 + p].tree_len; }
+  for (u32 p = 0; p <= C.max_qlen; ++p) { tdst[C.tq0 + p] = w.n; w.n += tlen[C.tq0 + p]; }
   C.qhdr_len = w.n - qb;
   /* dna header: symbols then the table when not plain (tasks.cpp:519-542) */
   u32 db = C.thdr_cap + C.qhdr_cap;
   w.n = db;
   for (u32 i = 0; i < C.nsym; ++i) w.byte(C.symbols[i]);
-  if (!C.plain) { td[C.tdna].dst = w.n; w.n += td[C.tdna].tree_len; }
+  if (!C.plain) { tdst[C.tdna] = w.n; w.n += tlen[C.tdna]; }
   C.dhdr_len = w.n - db;
   return C.qhdr_len <= C.qhdr_cap && C.dhdr_len <= C.dhdr_cap;
 }

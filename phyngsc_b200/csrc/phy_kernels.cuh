@@ -5,7 +5,8 @@
  *   in[len + slack]            the FASTQ bytes, batch-relative positions are uint32
  *   te[r], se[r], rstart[r]    record table: newline ending the title line / the sequence line, first byte
  *   kx[r]                      kept DNA length | transfer flag << 15          (phyNGSC.cpp:549-588)
- *   qoff[r], doff[r]           bit offset of the record inside the quality / DNA body
+ *   qoff[r], doff[r], toff[r]  bit offset of the record inside its 128-record chunk of the quality / DNA body,
+ *                              and inside its 32-record title block
  *   plans[s], acc[s], cls[s]   per-subblock window, reduced statistics, coding decisions (phy_core.cuh)
  *   arena[s][ARENA_WORDS]      per-subblock histograms, Huffman tables, tree blobs, header staging
  *   out[]                      payloads info|title|quality|dna, 16-byte aligned per subblock
@@ -42,7 +43,8 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   i32 status;          /* batch-level error (capacity ...)                                      */
   u64 total_out;       /* bytes of output used                                                  */
   u64 next_pos;        /* region-relative position where the next window starts                 */
-  u32 max_qchunks, pad;
+  u32 max_qchunks;
+  u32 max_nf;          /* max over subblocks of the separator count of the first title        */
 };
 
 struct SbOut {         /* device -> host, one per subblock */
@@ -53,7 +55,7 @@ struct Dev {
   const u8 *in; u32 len;      /* batch bytes                                                   */
   u32 start_pos;              /* first record start inside the batch                           */
   u32 *te, *se, *rstart; u32 maxrec;
-  u16 *kx; u32 *qoff, *doff;
+  u16 *kx; u32 *qoff, *doff, *toff;
   u32 *tile_cnt, *tile_off; u32 ntiles;
   PlanState *plan_state; SbPlan *plans; u32 max_sb;
   BatchHdr *hdr;
@@ -62,6 +64,7 @@ struct Dev {
   u8 *out; u64 out_cap;
   i64 batch_base, region_len; i32 batch_is_final; u32 slack;
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
+  u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
 };
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -84,7 +87,8 @@ __device__ __forceinline__ u32 nl_count64(const u8 *in, u32 p, u32 lo, u32 hi) {
   return n;
 }
 
-__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warp_sums /*[8]*/, u32 &total) {
+template <int NW>
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *warp_sums /*[NW]*/, u32 &total) {
   u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   u32 x = v;
 #pragma unroll
@@ -93,11 +97,12 @@ __device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warp_sums /*[8]*/
   __syncthreads();
   u32 base = 0, tot = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { u32 s = warp_sums[k]; if ((u32)k < w) base += s; tot += s; }
+  for (int k = 0; k < NW; ++k) { u32 s = warp_sums[k]; if ((u32)k < w) base += s; tot += s; }
   total = tot;
   __syncthreads();
   return base + x - v;
 }
+__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warp_sums /*[8]*/, u32 &total) { return block_excl_scan<8>(v, warp_sums, total); }
 
 /* (a) record splitter, pass 1: newline count per 16 KiB tile */
 __global__ void __launch_bounds__(256) k_nl_count(Dev d) {
@@ -132,7 +137,12 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   for (u32 i = b; i < e; ++i) { d.tile_off[i] = run; run += d.tile_cnt[i]; }
 }
 
-/* (a) record splitter, pass 2: line l = 4r+k ends at the l-th newline; k=0 title, 1 sequence, 3 quality */
+/* (a) record splitter, pass 2: line l = 4r+k ends at the l-th newline; k=0 title, 1 sequence, 3 quality.
+ * Each thread owns 64 bytes; newline bytes are found with a SIMD byte compare and visited by bit scan. */
+__device__ __forceinline__ void nl_put(const Dev &d, u32 l, u32 pos) {
+  u32 r = l >> 2, k = l & 3;
+  if (k == 0) d.te[r] = pos; else if (k == 1) d.se[r] = pos; else if (k == 3) d.rstart[r + 1] = pos + 1;
+}
 __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   __shared__ u32 ws[8];
   if (d.hdr->status) return;
@@ -142,12 +152,21 @@ __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   u32 tot;
   u32 l = d.tile_off[t] + block_excl_scan_256(n, ws, tot);
   if (!n) return;
-  u32 lo = max(p, d.start_pos), hi = min(p + 64, d.len);
-  for (u32 i = lo; i < hi; ++i) {
-    if (d.in[i] != '\n') continue;
-    u32 r = l >> 2, k = l & 3;
-    if (k == 0) d.te[r] = i; else if (k == 1) d.se[r] = i; else if (k == 3) d.rstart[r + 1] = i + 1;
-    ++l;
+  if (p >= d.start_pos && p + 64 <= d.len) {
+    const uint4 *q = (const uint4 *)(d.in + p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 v = __ldg(q + k);
+      u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        u32 m = __vcmpeq4(w[j], 0x0A0A0A0Au) & 0x01010101u;
+        while (m) { u32 bit = __ffs(m) - 1; nl_put(d, l++, p + k * 16 + j * 4 + (bit >> 3)); m &= m - 1; }
+      }
+    }
+  } else {
+    u32 lo = max(p, d.start_pos), hi = min(p + 64, d.len);
+    for (u32 i = lo; i < hi; ++i) if (d.in[i] == '\n') nl_put(d, l++, i);
   }
 }
 
@@ -211,6 +230,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     P.warnings = capped ? 1u : 0u;
     P.bytes_consumed = (u64)((i64)d.rstart[last + 1] - ws);
     if (lane == 0) d.plans[S] = P;
+    __syncwarp();
     u32 nch = (P.n_records + CH - 1) / CH;
     chunk_base += nch;
     max_chunks = max(max_chunks, nch);
@@ -225,7 +245,15 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     st.done = st.bytes_read >= st.region;
     st.n_subblocks_total++;
   }
+  /* separator count of every subblock's first title (sizes the per-field shared-memory tables) */
+  u32 mnf = 0;
+  for (u32 s = lane; s < S; s += 32) {
+    u32 fr = d.plans[s].first_rec;
+    mnf = max(mnf, count_seps(d.in, d.rstart[fr], d.te[fr]));
+  }
+  mnf = __reduce_max_sync(0xFFFFFFFFu, mnf);
   if (lane == 0) {
+    H->max_nf = mnf;
     H->S = S; H->max_chunks = max_chunks; H->max_rec_bytes = max_rec_bytes; H->max_qchunks = max_qchunks;
     H->next_pos = (u64)st.bytes_read;
     if (st.status) H->status = st.status;
@@ -246,11 +274,8 @@ __device__ __forceinline__ const u8 *stage_span(const u8 *in, u32 lo, u32 hi, u8
   return smem - alo;
 }
 
-/* per-CTA copy of what the per-record code needs from SbClass */
-struct ClsS {
-  u32 nf, nnc, nq, plain, R, nb_len;
-  u32 tabdesc_off, flagbits_off, blkoff_off, tq0, tdna;
-};
+/* Dynamic shared memory of the per-record kernels: [span_bytes: staged records][vals: nf x CH numeric values] */
+__device__ __forceinline__ u32 *vals_area(uint4 *dyn, u32 span_bytes) { return (u32 *)((u8 *)dyn + span_bytes); }
 
 /* ---- stat1 ---------------------------------------------------------------------------------------------- */
 struct Stat1S {
@@ -263,7 +288,6 @@ struct Stat1S {
   u32 nf, ts0, te0;
   u32 off0[MAXF], len0[MAXF];
   u32 pvals0[MAXF];
-  u32 vals[MAXF][CH];
   u8 r0[R0_MAX];
 };
 
@@ -274,9 +298,10 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   const SbPlan P = d.plans[s];
   if (P.status || chunk * CH >= P.n_records) return;
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
-  for (u32 i = tid; i < sizeof(Stat1S) / 4 - R0_MAX / 4 - MAXF * CH; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
+  for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
   const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  u32 *vals = vals_area(dyn_smem, d.span_bytes); /* vals[f * CH + tid] */
   __syncthreads();
   /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
   const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       Tok t; u32 nf = 0;
       while (c.next(t)) { if (nf < (u32)MAXF) { S.off0[nf] = t.start; S.len0[nf] = t.end - t.start; } ++nf; }
       S.nf = nf;
-      if (nf == 0 || nf > (u32)MAXF) S.err = E_UNSUPPORTED;
+      if (nf == 0 || nf > (u32)MAXF || nf > d.max_nf) S.err = E_UNSUPPORTED;
     }
   }
   __syncthreads();
@@ -310,22 +335,37 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       if ((c0 >= '0' && c0 <= '3') || (c1 >= '0' && c1 <= '3')) err = E_COLORSPACE;
     }
   }
-  /* sequence / quality */
+  /* sequence / quality (phyNGSC.cpp:549-619): one pass; records with ambiguity codes take a second one */
   u32 kept = 0, acgt0 = 0, acgt1 = 0, acgt2 = 0, acgt3 = 0, myL = 0;
   if (active && !err) {
-    SeqStat st;
     u64 qm = 0; /* quality bytes 33..96 seen by this thread */
-    seqqual_stat(b, te + 1, L, qs, st,
-                 [&](u8 c) { atomicAdd(&S.dna[c], 1u); },
-                 [&](u8 q) {
-                   u32 k = (u32)q - 33u;
-                   if (k < 64u) qm |= 1ull << k;
-                   else if (!((S.qp[q >> 5] >> (q & 31)) & 1u)) atomicOr(&S.qp[q >> 5], 1u << (q & 31));
-                 });
-    if (st.err) err = E_UNSUPPORTED;
-    kept = st.kept; myL = L;
-    acgt0 = st.acgt[0]; acgt1 = st.acgt[1]; acgt2 = st.acgt[2]; acgt3 = st.acgt[3];
-    d.kx[r] = (u16)(st.kept | (st.xfer << 15));
+    auto seen = [&](u8 q) {
+      u32 k = (u32)q - 33u;
+      if (k < 64u) qm |= 1ull << k;
+      else if (!((S.qp[q >> 5] >> (q & 31)) & 1u)) atomicOr(&S.qp[q >> 5], 1u << (q & 31));
+    };
+    bool ok = true, nul = false;
+    u32 namb = 0;
+    const u8 *sp = b + te + 1, *qp = b + qs;
+    for (u32 j = 0; j < L; ++j) {
+      u8 c = sp[j], q = qp[j];
+      nul = nul || c == 0 || q == 0;
+      if (c == 'A') ++acgt0; else if (c == 'C') ++acgt1; else if (c == 'G') ++acgt2; else if (c == 'T') ++acgt3;
+      else { ++namb; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; continue; }
+      seen(q);
+    }
+    const u32 xfer = (namb && ok) ? 1u : 0u;
+    if (namb) {
+      for (u32 j = 0; j < L; ++j) {
+        u8 c = sp[j], q = qp[j];
+        if (is_acgt(c)) continue;
+        if (xfer) seen(xfer_qual(amb_code(c), q));
+        else { atomicAdd(&S.dna[c], 1u); seen(q); }
+      }
+    }
+    if (nul) err = E_UNSUPPORTED;
+    kept = xfer ? L - namb : L; myL = L;
+    d.kx[r] = (u16)(kept | (xfer << 15));
     /* bits 33..63 -> word 1 bits 1..31; 64..95 -> word 2; 96 -> word 3 bit 0 */
     u32 w1 = (u32)(qm << 1), w2 = (u32)(qm >> 31), w3 = (u32)(qm >> 63);
     if (w1 & ~S.qp[1]) atomicOr(&S.qp[1], w1);
@@ -344,22 +384,23 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms);
     }
   }
-  /* title: field count, then per-field reductions (tasks.cpp:22-223 as closed forms) */
-  if (active && !err && seed_ok && count_seps(b, ts, te) != nf) err = E_FIELDS;
-  const bool ok = active && !err && seed_ok;
+  /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way */
+  const bool walk = active && !err && seed_ok;
+  bool fields_ok = true;
   TitleCursor cur; cur.init(b, ts, te);
   for (u32 f = 0; f < nf && seed_ok; ++f) {
     Tok t; t.start = t.end = 0; t.v = 0; t.num = true;
     u32 len = 0;
+    bool ok = walk && fields_ok;
+    if (ok && !cur.next(t)) { fields_ok = false; ok = false; t.start = t.end = 0; t.v = 0; t.num = true; }
     if (ok) {
-      cur.next(t);
       len = t.end - t.start;
       const u32 len0 = S.len0[f], m = len < len0 ? len : len0;
-      const u8 *d0 = S.r0 + S.off0[f];
+      const u8 *d0 = S.r0 + S.off0[f], *dp = b + t.start;
       for (u32 p = 0; p < m; ++p)
-        if (b[t.start + p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
+        if (dp[p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
     }
-    S.vals[f][tid] = t.v;
+    vals[f * CH + tid] = t.v;
     u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
     u32 mx = __reduce_max_sync(0xFFFFFFFFu, ok ? len : 0u);
     u32 nn = __ballot_sync(0xFFFFFFFFu, ok && !t.num);
@@ -372,6 +413,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       atomicMax(&S.facc[f][3], kmax); atomicMax(&S.facc[f][4], kinv);
     }
   }
+  if (walk && (!fields_ok || cur.pos <= cur.lim)) err = E_FIELDS; /* fewer or more separators than record 0 */
   /* the record before this chunk, for the first delta */
   if (tid == 0 && chunk > 0 && seed_ok) {
     u32 pts = d.rstart[r0 - 1], pte = d.te[r0 - 1];
@@ -381,9 +423,9 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   }
   __syncthreads();
   for (u32 f = 0; f < nf && seed_ok; ++f) {
-    const bool hasd = ok && r > P.first_rec;
-    u32 pv = tid > 0 ? S.vals[f][tid - 1] : S.pvals0[f];
-    u32 kd = key_of((i32)(S.vals[f][tid] - pv));
+    const bool hasd = walk && r > P.first_rec;
+    u32 pv = tid > 0 ? vals[f * CH + tid - 1] : S.pvals0[f];
+    u32 kd = key_of((i32)(vals[f * CH + tid] - pv));
     u32 kmax = __reduce_max_sync(0xFFFFFFFFu, hasd ? kd : 0u);
     u32 kinv = __reduce_max_sync(0xFFFFFFFFu, hasd ? ~kd : 0u);
     if (lane == 0) { atomicMax(&S.facc[f][5], kmax); atomicMax(&S.facc[f][6], kinv); }
@@ -504,34 +546,14 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
 }
 
 /* ---- shared pieces of the per-record title kernels ------------------------------------------------------------ */
-struct TitleS {
-  FieldClass fc[MAXF];
-  u32 vals[MAXF][CH];
-  u32 pvals0[MAXF];
-};
-
-/* loads the field classes, parses every record's numeric token values into S.vals (and the record before
- * the chunk into S.pvals0) so that deltas never need a second walk */
-__device__ __forceinline__ void title_prepare(const Dev &d, const SbClass &C, const u8 *b, TitleS &S, u32 r0, u32 nrec, u32 chunk) {
-  const u32 tid = threadIdx.x;
-  for (u32 i = tid; i < C.nf * (sizeof(FieldClass) / 4); i += CH) ((u32 *)S.fc)[i] = ((const u32 *)C.f)[i];
-  if (tid < nrec) {
-    u32 r = r0 + tid;
-    TitleCursor c; c.init(b, d.rstart[r], d.te[r]);
-    Tok t;
-    for (u32 f = 0; f < C.nf; ++f) { if (!c.next(t)) break; S.vals[f][tid] = t.v; }
-  }
-  if (tid == 0 && chunk > 0) {
-    TitleCursor c; c.init(b, d.rstart[r0 - 1], d.te[r0 - 1]);
-    Tok t;
-    for (u32 f = 0; f < C.nf; ++f) { if (!c.next(t)) break; S.pvals0[f] = t.v; }
-  }
-  __syncthreads();
+__device__ __forceinline__ void load_field_classes(const SbClass &C, FieldClass *fc) {
+  for (u32 i = threadIdx.x; i < C.nf * (sizeof(FieldClass) / 4); i += blockDim.x) ((u32 *)fc)[i] = ((const u32 *)C.f)[i];
 }
 
-struct PrevFromS {
-  const TitleS *S; u32 tid;
-  __device__ __forceinline__ i32 operator()(u32 f) const { return (i32)(tid > 0 ? S->vals[f][tid - 1] : S->pvals0[f]); }
+/* previous record's numeric value = the neighbouring lane's (lane = record of the 32-record block).  Lane 0
+ * receives garbage, which is never used: the first record of a block is coded raw (tasks.cpp:455-458). */
+struct PrevShfl {
+  __device__ __forceinline__ i32 operator()(u32, i32 v) const { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
 };
 
 /* ---- stat2: numeric / char histograms and 32-record block descriptors (tasks.cpp:64-93, 127-182) --------------- */
@@ -543,68 +565,79 @@ __device__ __forceinline__ void warp_hist_add(u32 *hist, u32 idx, bool on) {
 
 __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ TitleS S;
+  __shared__ FieldClass fc[MAXF];
+  __shared__ u32 pvals0[MAXF];
   const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const SbClass &C = d.cls[s];
   if (C.status || chunk * CH >= C.R) return;
-  if (C.nnc == 0) { /* every field constant: all block flags are irrelevant */ return; }
+  if (C.nnc == 0) return; /* every field constant: no histogram, no block flag is ever read */
   const SbPlan P = d.plans[s];
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  title_prepare(d, C, b, S, r0, nrec, chunk);
+  u32 *vals = vals_area(dyn_smem, d.span_bytes);
+  load_field_classes(C, fc);
+  __syncthreads();
   const bool active = tid < nrec;
   const u32 r = r0 + (active ? tid : 0);
   const u32 nf = C.nf;
-  TitleCursor cur; cur.init(b, d.rstart[r], d.te[r]);
-  u32 flags = 0;
-  /* number of records of this warp's block */
   const u32 wbase = tid & ~31u;
+  u32 flags = 0;
+  /* one walk: string fields are finished here, numeric values are parked in shared memory */
+  TitleCursor cur; cur.init(b, d.rstart[r], d.te[r]);
   for (u32 f = 0; f < nf; ++f) {
     Tok t; t.start = t.end = 0; t.v = 0; t.num = false;
     if (active) cur.next(t);
-    const FieldClass &F = S.fc[f];
+    const FieldClass &F = fc[f];
     if (F.kind == K_CONST) continue;
+    if (F.kind == K_NUM) { vals[f * CH + tid] = t.v; continue; }
+    u32 len = t.end - t.start;
+    u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
     bool pred = true;
-    if (F.kind == K_STR) {
-      u32 len = t.end - t.start;
-      u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
-      if (active) {
-        pred = len == len_lo;
-        for (u32 j = 0; pred && j < len; ++j) pred = b[t.start + j] == b[st_lo + j];
-        const u16 *sm = (const u16 *)(arena + F.slotmap_off);
-        for (u32 j = 0; j < len; ++j)
-          if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
-            u32 tab = sm[j < 128 ? j : 128];
-            atomicAdd(arena + td[tab].freq_off + b[t.start + j], 1u);
-          }
-      }
-    } else {
-      i32 v = (i32)S.vals[f][tid];
-      i32 pv = (i32)(tid > 0 ? S.vals[f][tid - 1] : S.pvals0[f]);
-      i32 dl = wsub(v, pv);
-      bool hasd = active && r > P.first_rec;
-      if (F.is_delta) {
-        /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
-        i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
-        if (nrec - wbase < 2) bd = 0;
-        pred = !active || lane < 2 || dl == bd;
-        bool all = __all_sync(0xFFFFFFFFu, pred);
-        pred = all && bd == F.min_d;
-        if (F.has_table) warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(dl, F.base), hasd);
-      } else {
-        i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
-        pred = !active || v == v_lo;
-        pred = __all_sync(0xFFFFFFFFu, pred);
-        if (F.has_table) {
-          warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(v, F.base), active);
-          if (active && r == P.first_rec) atomicAdd(arena + td[F.tab].freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
+    if (active) {
+      pred = len == len_lo;
+      const u8 *a = b + t.start, *a0 = b + st_lo;
+      for (u32 j = 0; pred && j < len; ++j) pred = a[j] == a0[j];
+      const u16 *sm = (const u16 *)(arena + F.slotmap_off);
+      for (u32 j = 0; j < len; ++j)
+        if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
+          u32 tab = sm[j < 128 ? j : 128];
+          atomicAdd(arena + td[tab].freq_off + a[j], 1u);
         }
+    }
+    if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
+  }
+  if (tid == 0 && chunk > 0) {
+    TitleCursor c; c.init(b, d.rstart[r0 - 1], d.te[r0 - 1]);
+    Tok t;
+    for (u32 f = 0; f < nf; ++f) { if (!c.next(t)) break; pvals0[f] = t.v; }
+  }
+  __syncthreads();
+  for (u32 f = 0; f < nf; ++f) {
+    const FieldClass &F = fc[f];
+    if (F.kind != K_NUM) continue;
+    i32 v = (i32)vals[f * CH + tid];
+    i32 pv = (i32)(tid > 0 ? vals[f * CH + tid - 1] : pvals0[f]);
+    i32 dl = wsub(v, pv);
+    bool hasd = active && r > P.first_rec;
+    bool pred;
+    if (F.is_delta) {
+      /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
+      i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
+      if (nrec - wbase < 2) bd = 0;
+      pred = !active || lane < 2 || dl == bd;
+      pred = __all_sync(0xFFFFFFFFu, pred) && bd == F.min_d;
+      if (F.has_table) warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(dl, F.base), hasd);
+    } else {
+      i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
+      pred = __all_sync(0xFFFFFFFFu, !active || v == v_lo);
+      if (F.has_table) {
+        warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(v, F.base), active);
+        if (active && r == P.first_rec) atomicAdd(arena + td[F.tab].freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
       }
     }
-    if (F.kind == K_STR) pred = __all_sync(0xFFFFFFFFu, pred);
     if (pred) flags |= 1u << f;
   }
   if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (chunk * CH + wbase) / 32] = flags;
@@ -630,11 +663,15 @@ __global__ void __launch_bounds__(128) k_huff(Dev d) {
 }
 
 /* ---- lengths ----------------------------------------------------------------------------------------------------- */
+/* Bit length of every record in the three bodies.  Offsets are kept two-level: local to the 128-record chunk
+ * (qoff/doff/toff per record, title block offsets per 32-record block) plus one total per chunk that k_layout
+ * turns into chunk bases with a short scan. */
 __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ TitleS S;
+  __shared__ FieldClass fc[MAXF];
   __shared__ u8 codes[512];
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  __shared__ u32 ws[4];
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
   if (C.status || chunk * CH >= C.R) return;
   const SbPlan P = d.plans[s];
@@ -642,81 +679,103 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
-  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  title_prepare(d, C, b, S, r0, nrec, chunk);
+  load_field_classes(C, fc);
+  __syncthreads();
   const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : 0);
+  const u32 r = r0 + (active ? tid : nrec - 1); /* idle lanes shadow the chunk's last record so that warps stay converged */
   const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
-  u32 tbits = 0;
+  u32 qbits = 0, dbits = 0;
   if (active) {
     const u32 kx = d.kx[r];
     const bool xfer = kx >> 15;
     CountSink q; q.init();
     quality_record(b, te + 1, L, se + 3, xfer, codes, (const u64 *)(arena + td[C.tq0].cl_off), C.nq, q);
-    d.qoff[r] = (u32)q.bits;
-    if (C.plain) d.doff[r] = 2 * (kx & 0x7FFFu);
+    qbits = (u32)q.bits;
+    if (C.plain) dbits = 2 * (kx & 0x7FFFu);
     else {
       CountSink dn; dn.init();
       dna_record(b, te + 1, L, xfer, false, codes + 256, (const u64 *)(arena + td[C.tdna].cl_off), dn);
-      d.doff[r] = (u32)dn.bits;
-    }
-    if (C.nnc) {
-      const u32 blk = (chunk * CH + tid) / 32;
-      CountSink t; t.init();
-      PrevFromS pv; pv.S = &S; pv.tid = tid;
-      title_record(b, d.rstart[r], te, C, S.fc, arena, arena[C.flagbits_off + blk], lane == 0, pv, t);
-      tbits = (u32)t.bits;
+      dbits = (u32)dn.bits;
     }
   }
-  u32 sum = __reduce_add_sync(0xFFFFFFFFu, tbits);
-  const u32 wbase = tid & ~31u;
-  if (lane == 0 && wbase < nrec) arena[C.blkoff_off + (chunk * CH + wbase) / 32] = (C.nnc + sum + 7) / 8;
+  u32 qtot, dtot;
+  u32 qloc = block_excl_scan<4>(qbits, ws, qtot);
+  u32 dloc = block_excl_scan<4>(dbits, ws, dtot);
+  if (active) { d.qoff[r] = qloc; d.doff[r] = dloc; }
+  u32 blk_bytes = 0;
+  if (C.nnc) {
+    __syncwarp();
+    CountSink t; t.init();
+    title_record(b, d.rstart[r], te, C, fc, arena, arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32], lane == 0, PrevShfl(), t);
+    u32 tb = active ? (u32)t.bits : 0u, x = tb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
+    if (active) d.toff[r] = x - tb; /* bits of the block's earlier records (the flag bits come on top) */
+    u32 sum = __shfl_sync(0xFFFFFFFFu, x, 31);
+    if ((tid & ~31u) < nrec) blk_bytes = (C.nnc + sum + 7) / 8;
+  }
+  /* title block offsets local to the chunk */
+  u32 ttot;
+  u32 tloc = block_excl_scan<4>(lane == 0 ? blk_bytes : 0u, ws, ttot);
+  if (lane == 0 && (tid & ~31u) < nrec) arena[C.blkloc_off + chunk * (CH / 32) + w] = tloc;
+  if (tid == 0) {
+    arena[C.chunk_off + chunk] = qtot;
+    arena[C.chunk_off + C.nchunk + chunk] = dtot;
+    arena[C.chunk_off + 2 * C.nchunk + chunk] = ttot;
+  }
 }
 
 /* ---- layout: headers, scans, section sizes ------------------------------------------------------------------------ */
 /* in-place exclusive scan of a[0..n) by one 256-thread CTA; returns the total (64-bit) */
-__device__ u64 cta_scan_inplace(u32 *a, u32 n, u32 *ws, bool wide_check, i32 *overflow) {
+__device__ u64 cta_scan_inplace(u32 *a, u32 n, u32 *ws, i32 *overflow) {
   u64 carry = 0;
   for (u32 base = 0; base < n; base += 256) {
     u32 i = base + threadIdx.x;
     u32 v = i < n ? a[i] : 0u, tot;
     u32 ex = block_excl_scan_256(v, ws, tot);
     u64 o = carry + ex;
-    if (wide_check && i < n && o > 0xFFFFFFFFull) *overflow = 1;
+    if (i < n && o > 0xFFFFFFFFull) *overflow = 1;
     if (i < n) a[i] = (u32)o;
     carry += tot;
   }
   return carry;
 }
 
+constexpr u32 LAYOUT_TABS = 2048; /* table lengths / destinations kept in shared memory while the headers are laid out */
+
 __global__ void __launch_bounds__(256) k_layout(Dev d) {
   __shared__ u32 ws[8];
   __shared__ i32 ovf, okh;
+  __shared__ u32 tlen[LAYOUT_TABS], tdst[LAYOUT_TABS];
   const u32 s = blockIdx.x, tid = threadIdx.x;
   SbClass &C = d.cls[s];
   if (C.status) return;
-  const SbPlan P = d.plans[s];
   u32 *arena = d.arena + (size_t)s * d.arena_words;
-  if (tid == 0) { ovf = 0; okh = layout_headers(d.in, C, arena) ? 1 : 0; }
+  TableDesc *td = (TableDesc *)(arena + C.tabdesc_off);
+  if (C.ntab > LAYOUT_TABS) { if (tid == 0) C.status = E_CAPACITY; return; }
+  for (u32 t = tid; t < C.ntab; t += 256) { tlen[t] = td[t].tree_len; tdst[t] = 0; }
+  if (tid == 0) ovf = 0;
+  __syncthreads();
+  if (tid == 0) okh = layout_headers(d.in, C, arena, tlen, tdst) ? 1 : 0;
   __syncthreads();
   if (!okh) { if (tid == 0) C.status = E_UNSUPPORTED; return; }
   /* copy the tree blobs to their place in the staged headers, one warp per table */
   {
-    const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
     u8 *stage = (u8 *)(arena + C.stage_off);
     for (u32 t = tid >> 5; t < C.ntab; t += 8) {
       const u8 *src = (const u8 *)(arena + td[t].tree_off);
-      u8 *dst = stage + td[t].dst;
-      for (u32 i = tid & 31; i < td[t].tree_len; i += 32) dst[i] = src[i];
+      u8 *dst = stage + tdst[t];
+      for (u32 i = tid & 31; i < tlen[t]; i += 32) dst[i] = src[i];
     }
   }
-  u64 qb = cta_scan_inplace(d.qoff + P.first_rec, C.R, ws, true, &ovf);
-  u64 db = cta_scan_inplace(d.doff + P.first_rec, C.R, ws, true, &ovf);
-  u64 tb = C.nnc ? cta_scan_inplace(arena + C.blkoff_off, C.nblk, ws, true, &ovf) : 0;
+  u64 qb = cta_scan_inplace(arena + C.chunk_off, C.nchunk, ws, &ovf);
+  u64 db = cta_scan_inplace(arena + C.chunk_off + C.nchunk, C.nchunk, ws, &ovf);
+  u64 tb = C.nnc ? cta_scan_inplace(arena + C.chunk_off + 2 * C.nchunk, C.nchunk, ws, &ovf) : 0;
   __syncthreads();
   if (tid == 0) {
-    if (ovf || tb > 0x7FFFFFFFull || qb > 0x3FFFFFFFFull || db > 0x3FFFFFFFFull) { C.status = E_CAPACITY; return; }
+    if (ovf || tb > 0x7FFFFFFFull) { C.status = E_CAPACITY; return; }
     finish_layout(C, (u32)tb, qb, db);
   }
 }
@@ -749,11 +808,12 @@ __global__ void __launch_bounds__(256) k_zero_out(Dev d) {
 __device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
   if (v) atomicOr((u32 *)(base + (pos & ~3u)), (u32)v << (8 * (pos & 3u)));
 }
+
 __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ TitleS S;
+  __shared__ FieldClass fc[MAXF];
   __shared__ u8 codes[512];
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
   if (C.status || chunk * CH >= C.R) return;
   const SbPlan P = d.plans[s];
@@ -764,9 +824,10 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   u32 *outw = (u32 *)d.out;
   const u64 obase = C.out_off; /* byte offset of the payload inside d.out (16-byte aligned) */
   for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
-  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  title_prepare(d, C, b, S, r0, nrec, chunk);
+  load_field_classes(C, fc);
+  __syncthreads();
   const u32 o_title = C.info_len, o_qual = o_title + C.title_len, o_dna = o_qual + C.qual_len;
   if (chunk == 0) {
     /* fixed part of the info stream (phyNGSC.cpp:719-730) and the three staged headers.  Bytes are OR-ed
@@ -774,9 +835,9 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
      * belong to a bit stream written by another thread. */
     if (tid == 0) {
       u8 fx[INFO_FIXED];
-      ByteWriter w; w.p = fx; w.n = 0;
-      w.word(C.R); w.word(C.max_qlen); w.word(C.max_slen);
-      w.byte((u8)C.nsym); w.byte(0); w.byte((u8)C.nq); w.word(C.flags);
+      ByteWriter bw; bw.p = fx; bw.n = 0;
+      bw.word(C.R); bw.word(C.max_qlen); bw.word(C.max_slen);
+      bw.byte((u8)C.nsym); bw.byte(0); bw.byte((u8)C.nq); bw.word(C.flags);
       for (u32 i = 0; i < INFO_FIXED; ++i) or_byte(out, i, fx[i]);
     }
     const u8 *stage = (const u8 *)(arena + C.stage_off);
@@ -785,13 +846,9 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
     for (u32 i = tid; i < C.dhdr_len; i += CH) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
   }
   const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : 0);
+  const u32 i_sb = chunk * CH + (active ? tid : nrec - 1); /* record index inside the subblock (idle lanes shadow the last) */
+  const u32 r = P.first_rec + i_sb;
   const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
-  const u32 i_sb = chunk * CH + tid; /* record index inside the subblock */
-  u32 tbits = 0;
-  const u32 blk = i_sb / 32;
-  const u32 flags = (active && C.nnc) ? arena[C.flagbits_off + blk] : 0u;
-  PrevFromS pv; pv.S = &S; pv.tid = tid;
   if (active) {
     const u32 kx = d.kx[r];
     const bool xfer = kx >> 15;
@@ -800,37 +857,29 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
       k.put(L, C.nb_len); k.finish();
     }
     {
-      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + d.qoff[r]);
+      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + arena[C.chunk_off + chunk] + d.qoff[r]);
       quality_record(b, te + 1, L, se + 3, xfer, codes, (const u64 *)(arena + td[C.tq0].cl_off), C.nq, q);
       q.finish();
     }
     {
-      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + d.doff[r]);
+      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + arena[C.chunk_off + C.nchunk + chunk] + d.doff[r]);
       dna_record(b, te + 1, L, xfer, C.plain != 0, codes + 256, C.plain ? (const u64 *)nullptr : (const u64 *)(arena + td[C.tdna].cl_off), dn);
       dn.finish();
     }
-    if (C.nnc) {
-      CountSink t; t.init();
-      title_record(b, d.rstart[r], te, C, S.fc, arena, flags, lane == 0, pv, t);
-      tbits = (u32)t.bits;
-    }
   }
   if (C.nnc) {
-    /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509) */
-    u32 x = tbits;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
-    const u32 before = x - tbits;
-    if (active) {
-      OrSink t; t.init(outw, (obase + o_title + C.thdr_len + arena[C.blkoff_off + blk]) * 8 + (lane == 0 ? 0u : C.nnc + before));
-      if (lane == 0) {
-        u32 v = 0;
-        for (u32 f = 0; f < C.nf; ++f) if (S.fc[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
-        t.put(v, C.nnc);
-      }
-      title_record(b, d.rstart[r], te, C, S.fc, arena, flags, lane == 0, pv, t);
-      t.finish();
+    /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509); all 32 lanes walk together */
+    __syncwarp();
+    const u32 flags = arena[C.flagbits_off + i_sb / 32];
+    const u64 blk_byte = obase + o_title + C.thdr_len + arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w];
+    OrSink t; t.init(outw, blk_byte * 8 + (lane == 0 ? 0u : C.nnc + d.toff[r]), active);
+    if (lane == 0) {
+      u32 v = 0;
+      for (u32 f = 0; f < C.nf; ++f) if (fc[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
+      t.put(v, C.nnc);
     }
+    title_record(b, d.rstart[r], te, C, fc, arena, flags, lane == 0, PrevShfl(), t);
+    t.finish();
   }
 }
 

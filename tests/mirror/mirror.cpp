@@ -79,7 +79,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
   SbClass *C = (SbClass *)calloc(1, sizeof(SbClass));
   classify_subblock(b, *A, R, rstart[0], te[0], arena, AW, *C);
   int rc = C->status;
-  std::vector<u32> qoff(R + 1), doff(R + 1);
+  std::vector<u32> qoff(R + 1), doff(R + 1), blkoff((R + 31) / 32 + 1);
   if (!rc) {
     TableDesc *td = (TableDesc *)(arena + C->tabdesc_off);
     for (u32 i = C->zero_begin; i < C->zero_end; ++i) arena[i] = 0;
@@ -133,7 +133,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
       td[i].tree_len = huff_table(arena + td[i].freq_off, td[i].n, (u64 *)(arena + td[i].cl_off), (u8 *)(arena + td[i].tree_off), *HS, 0u, 1u, NoSync());
     delete HS;
     // lengths
-    auto prev_of = [&](u32 r) { return [&, r](u32 f) { return (i32)vals[(size_t)(r - 1) * nf + f]; }; };
+    auto prev_of = [&](u32 r) { return [&, r](u32 f, i32) { return r ? (i32)vals[(size_t)(r - 1) * nf + f] : 0; }; };
     for (u32 r = 0; r < R; ++r) {
       u32 L = se[r] - te[r] - 1; bool xf = kx[r] >> 15;
       CountSink q; q.init();
@@ -150,16 +150,19 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
         title_record(b, rstart[r], te[r], *C, C->f, arena, arena[C->flagbits_off + lo / 32], r == lo, prev_of(r), ts);
         bits += ts.bits;
       }
-      arena[C->blkoff_off + lo / 32] = (u32)((bits + 7) / 8);
+      blkoff[lo / 32] = (u32)((bits + 7) / 8);
     }
     // layout
-    if (!layout_headers(b, *C, arena)) rc = E_UNSUPPORTED;
+    std::vector<u32> tlen(C->ntab), tdst(C->ntab);
+    for (u32 i = 0; i < C->ntab; ++i) tlen[i] = td[i].tree_len;
+    if (!layout_headers(b, *C, arena, tlen.data(), tdst.data())) rc = E_UNSUPPORTED;
+    for (u32 i = 0; i < C->ntab; ++i) td[i].dst = tdst[i];
     if (!rc) {
       u8 *stage = (u8 *)(arena + C->stage_off);
       for (u32 i = 0; i < C->ntab; ++i) memcpy(stage + td[i].dst, (u8 *)(arena + td[i].tree_off), td[i].tree_len);
       u64 qb = 0, db = 0, tb = 0;
       for (u32 r = 0; r < R; ++r) { u32 v = qoff[r]; qoff[r] = (u32)qb; qb += v; v = doff[r]; doff[r] = (u32)db; db += v; }
-      for (u32 k = 0; k < C->nblk && C->nnc; ++k) { u32 v = arena[C->blkoff_off + k]; arena[C->blkoff_off + k] = (u32)tb; tb += v; }
+      for (u32 k = 0; k < C->nblk && C->nnc; ++k) { u32 v = blkoff[k]; blkoff[k] = (u32)tb; tb += v; }
       finish_layout(*C, (u32)tb, qb, db);
       if (C->payload_len > out_cap) rc = E_CAPACITY;
     }
@@ -183,7 +186,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
       }
       for (u32 lo = 0; lo < R && C->nnc; lo += 32) {
         u32 hi = lo + 32 < R ? lo + 32 : R, flags = arena[C->flagbits_off + lo / 32];
-        OrSink ts; ts.init(outw, (u64)(o_title + C->thdr_len + arena[C->blkoff_off + lo / 32]) * 8);
+        OrSink ts; ts.init(outw, (u64)(o_title + C->thdr_len + blkoff[lo / 32]) * 8);
         u32 v = 0;
         for (u32 f = 0; f < nf; ++f) if (C->f[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
         ts.put(v, C->nnc);
