@@ -136,6 +136,11 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaHostAlloc(&ctx->h_plans, sizeof(SbPlan) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_sbout, sizeof(SbOut) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_state, sizeof(PlanState), cudaHostAllocDefault));
+  {
+    u8 lut[256];
+    fill_char_lut(lut);
+    CK(cudaMemcpyToSymbol(g_char_lut, lut, sizeof lut));
+  }
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
@@ -203,8 +208,9 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   k_nl_count<<<d.ntiles, 256, 0, st>>>(d); PMARK();
   k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
   k_nl_emit<<<d.ntiles, 256, 0, st>>>(d); PMARK();
-  k_plan<<<1, 32, 0, st>>>(d); PMARK();
-  ctx->launches += 4;
+  k_plan<<<1, 32, 0, st>>>(d);
+  k_spanmax<<<ctx->max_sb, 256, 0, st>>>(d); PMARK();
+  ctx->launches += 5;
   CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_state, ctx->plan_state, sizeof(PlanState), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_plans, ctx->plans, sizeof(SbPlan) * ctx->max_sb, cudaMemcpyDeviceToHost, st));
@@ -214,10 +220,8 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   const u32 S = H.S;
   ctx->last_S = S;
   if (S == 0) return PHY_OK;
-  u32 span = (u32)((u64)(CH + 1) * H.max_rec_bytes * 9 / 8) + 256;
-  span = (span + 1023) & ~1023u;
-  if (span < 8192) span = 8192;
-  if (span > SPAN_MAX) span = SPAN_MAX;
+  u32 span = (H.max_span + 16 + 1023) & ~1023u; /* exact: every 128-record span of the batch fits (k_spanmax) */
+  if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */

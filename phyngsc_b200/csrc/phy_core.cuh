@@ -151,26 +151,33 @@ PHY_HD u32 count_seps(const u8 *b, u32 ts, u32 te) {
   return n;
 }
 
+/* character classes for the tokeniser: bit 0 = separator, bit 1 = decimal digit */
+PHY_HD void fill_char_lut(u8 *lut) {
+  for (u32 c = 0; c < 256; ++c) lut[c] = (u8)((is_sep((u8)c) ? 1u : 0u) | ((c >= '0' && c <= '9') ? 2u : 0u));
+}
+
 /* Walks the separators of one title line [ts, te] (te = its '\n').  next() yields the token before the
- * next separator together with utils::is_num / utils::to_num of it (utils.h:107-125). */
+ * next separator together with utils::is_num / utils::to_num of it (utils.h:107-125); skip(len) steps over
+ * a token whose length is already known (constant fields). */
 struct TitleCursor {
-  const u8 *b; u32 pos, lim;
-  PHY_HD void init(const u8 *base, u32 ts, u32 te) { b = base; pos = ts; lim = te; }
+  const u8 *b; const u8 *lut; u32 pos, lim;
+  PHY_HD void init(const u8 *base, u32 ts, u32 te, const u8 *char_lut) { b = base; pos = ts; lim = te; lut = char_lut; }
+  PHY_HD void skip(u32 len) { pos += len + 1; }
   PHY_HD bool next(Tok &t) {
     if (pos > lim) return false;
     u32 i = pos, v = 0;
-    bool alld = true;
+    u32 alld = 2;
     u8 c0 = b[i];
     for (;; ++i) {
       u8 c = b[i];
-      if (is_sep(c)) break;
-      u32 d = (u32)c - '0';
-      alld = alld && d < 10u;
-      v = v * 10u + d;
+      u32 fl = lut[c];
+      if (fl & 1u) break;
+      alld &= fl;
+      v = v * 10u + ((u32)c - '0');
     }
     u32 len = i - pos;
     t.start = pos; t.end = i; t.v = v;
-    t.num = alld && len >= 1 && (len == 1 || c0 != '0');
+    t.num = alld != 0 && len >= 1 && (len == 1 || c0 != '0');
     pos = i + 1;
     return true;
   }
@@ -345,7 +352,7 @@ struct ArenaAlloc {
   PHY_HD u32 take(u32 words) { u32 o = used; used += words; if (used > cap) over = true; return o; }
 };
 
-PHY_HDN void classify_subblock(const u8 *b, const SbAcc &A, u32 R, u32 ts0, u32 te0, u32 *arena, u32 arena_words, SbClass &C) {
+PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R, u32 ts0, u32 te0, u32 *arena, u32 arena_words, SbClass &C) {
   C.status = A.status; C.R = R; C.ts0 = ts0; C.te0 = te0;
   if (C.status) return;
   /* DNA symbols / quality alphabet ascending, phyNGSC.cpp:669-686 */
@@ -370,7 +377,7 @@ PHY_HDN void classify_subblock(const u8 *b, const SbAcc &A, u32 R, u32 ts0, u32 
   C.qstat_off = al.take((C.max_qlen + 1) * nq);
 
   /* title fields, seeded from record 0 (phyNGSC.cpp:345-379) */
-  TitleCursor cur; cur.init(b, ts0, te0);
+  TitleCursor cur; cur.init(b, ts0, te0, lut);
   Tok t; u32 nf = 0;
   while (cur.next(t)) {
     if (nf < (u32)MAXF) { C.f[nf].off0 = t.start - ts0; C.f[nf].len0 = t.end - t.start; C.f[nf].sep = b[t.end]; }
@@ -424,7 +431,6 @@ PHY_HDN void classify_subblock(const u8 *b, const SbAcc &A, u32 R, u32 ts0, u32 
   }
   C.nnc = nnc;
   /* numeric + char histograms */
-  for (u32 f = 0; f < nf; ++f) if (C.f[f].kind == K_NUM && C.f[f].has_table) C.f[f].base = C.f[f].base; /* (offsets assigned below) */
   u32 numhist_off[MAXF];
   for (u32 f = 0; f < nf; ++f) numhist_off[f] = (C.f[f].kind == K_NUM && C.f[f].has_table) ? al.take(C.f[f].diff) : 0;
   u32 chrhist_off = al.take(ntab_chr * 256);
@@ -587,15 +593,15 @@ PHY_HD void dna_record(const u8 *b, u32 ss, u32 L, bool xfer, bool plain, const 
  * order, so that on the GPU it can be a warp shuffle (lane = record of the block; all 32 lanes walk
  * together); tables are reached through `arena` (table directory + slot maps). */
 template <class Sink, class Prev>
-PHY_HD void title_record(const u8 *b, u32 ts, u32 te, const SbClass &C, const FieldClass *FC, const u32 *arena, u32 flags,
+PHY_HD void title_record(const u8 *b, const u8 *lut, u32 ts, u32 te, const SbClass &C, const FieldClass *FC, const u32 *arena, u32 flags,
                          bool first, Prev prev, Sink &s) {
-  TitleCursor cur; cur.init(b, ts, te);
+  TitleCursor cur; cur.init(b, ts, te, lut);
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   Tok t;
   for (u32 f = 0; f < C.nf; ++f) {
-    if (!cur.next(t)) break;
     const FieldClass &F = FC[f];
-    if (F.kind == K_CONST) continue;
+    if (F.kind == K_CONST) { cur.skip(F.len0); continue; } /* every record carries record 0's token here */
+    if (!cur.next(t)) break;
     bool flag = (flags >> f) & 1u;
     if (F.kind == K_NUM) {
       i32 v = (i32)t.v;

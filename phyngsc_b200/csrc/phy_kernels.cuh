@@ -39,7 +39,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 NL, NR;          /* newlines found, complete records                                      */
   u32 S;               /* subblocks planned in this batch                                       */
   u32 max_chunks;      /* max over subblocks of ceil(n_records / CH)                            */
-  u32 max_rec_bytes;   /* max over subblocks of ceil(bytes / records)                           */
+  u32 max_span;        /* widest 128-record span (16-byte aligned start, one record of halo)     */
   i32 status;          /* batch-level error (capacity ...)                                      */
   u64 total_out;       /* bytes of output used                                                  */
   u64 next_pos;        /* region-relative position where the next window starts                 */
@@ -66,6 +66,12 @@ struct Dev {
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
 };
+
+/* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
+__device__ u8 g_char_lut[256];
+__device__ __forceinline__ void load_lut(u8 *lut) {
+  for (u32 i = threadIdx.x; i < 64; i += blockDim.x) ((u32 *)lut)[i] = ((const u32 *)g_char_lut)[i];
+}
 
 /* ---------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ u32 nl_count16(uint4 v) {
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
     u32 run = 0;
     for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; }
     d.hdr->NL = run; d.hdr->NR = run / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_rec_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (run / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
   u32 lane = threadIdx.x;
   if (H->status || st.done || st.status) { if (lane == 0) { H->S = 0; H->next_pos = (u64)st.bytes_read; } return; }
   const u32 NR = H->NR, NL = H->NL;
-  u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0, max_rec_bytes = 0, max_qchunks = 0;
+  u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0, max_qchunks = 0;
   i64 avg = 128;
   while (!st.done && S < d.max_sb) {
     i64 ws = st.bytes_read - d.batch_base; /* batch-relative window start */
@@ -236,7 +242,6 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     max_chunks = max(max_chunks, nch);
     max_qchunks = max(max_qchunks, (P.n_records + QCH - 1) / QCH);
     avg = max((i64)16, (i64)(P.bytes_consumed / P.n_records));
-    max_rec_bytes = max(max_rec_bytes, (u32)((P.bytes_consumed + P.n_records - 1) / P.n_records));
     ++S; F = last + 1;
     /* phyNGSC.cpp:745-755 */
     st.bytes_read += (i64)P.bytes_consumed;
@@ -245,30 +250,40 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     st.done = st.bytes_read >= st.region;
     st.n_subblocks_total++;
   }
-  /* separator count of every subblock's first title (sizes the per-field shared-memory tables) */
-  u32 mnf = 0;
-  for (u32 s = lane; s < S; s += 32) {
-    u32 fr = d.plans[s].first_rec;
-    mnf = max(mnf, count_seps(d.in, d.rstart[fr], d.te[fr]));
-  }
-  mnf = __reduce_max_sync(0xFFFFFFFFu, mnf);
   if (lane == 0) {
-    H->max_nf = mnf;
-    H->S = S; H->max_chunks = max_chunks; H->max_rec_bytes = max_rec_bytes; H->max_qchunks = max_qchunks;
+    H->S = S; H->max_chunks = max_chunks; H->max_qchunks = max_qchunks;
     H->next_pos = (u64)st.bytes_read;
     if (st.status) H->status = st.status;
     *d.plan_state = st;
   }
 }
 
+/* Exact shared-memory needs of the per-record kernels: the widest 128-record span (plus the record before
+ * it) and the largest field count over all subblocks of the batch. */
+__global__ void __launch_bounds__(256) k_spanmax(Dev d) {
+  const u32 s = blockIdx.x;
+  if (s >= d.hdr->S) return; /* launched for the context's capacity: the host learns S only afterwards */
+  const SbPlan P = d.plans[s];
+  if (P.status) return;
+  u32 mx = 0;
+  for (u32 c = threadIdx.x; c * CH < P.n_records; c += 256) {
+    u32 r0 = P.first_rec + c * CH, nrec = min((u32)CH, P.n_records - c * CH);
+    u32 lo = d.rstart[r0 - (c > 0 ? 1 : 0)] & ~15u;
+    mx = max(mx, d.rstart[r0 + nrec] - lo);
+  }
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&d.hdr->max_span, mx);
+  if (threadIdx.x == 0) atomicMax(&d.hdr->max_nf, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
+}
+
 /* ---- record spans in shared memory ------------------------------------------------------------------- */
 /* Copies bytes [lo, hi) of the batch (16-byte granules) into shared memory and returns a pointer p with
- * p[pos] valid for batch positions pos in [lo, hi); falls back to the global buffer when the span does
- * not fit.  All threads of the CTA must call it. */
+ * p[pos] valid for batch positions pos in [lo, hi), or nullptr when the span does not fit (records far
+ * beyond the reference's 500-byte domain).  All threads of the CTA must call it. */
 __device__ __forceinline__ const u8 *stage_span(const u8 *in, u32 lo, u32 hi, u8 *smem, u32 smem_bytes) {
   u32 alo = lo & ~15u;
   u32 n = hi - alo;
-  if (n > smem_bytes) return in;
+  if (n > smem_bytes) return nullptr;
   for (u32 i = threadIdx.x * 16; i < n; i += blockDim.x * 16) *(uint4 *)(smem + i) = __ldg((const uint4 *)(in + alo + i));
   __syncthreads();
   return smem - alo;
@@ -300,7 +315,10 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
   for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
   const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  __shared__ u8 lut[256];
+  load_lut(lut);
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  if (!b) { if (tid == 0) atomicMin(&d.acc[s].status, (i32)E_UNSUPPORTED); return; }
   u32 *vals = vals_area(dyn_smem, d.span_bytes); /* vals[f * CH + tid] */
   __syncthreads();
   /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
@@ -312,7 +330,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     S.ts0 = ts0; S.te0 = te0;
     if (!r0_ok) S.err = E_UNSUPPORTED;
     else {
-      TitleCursor c; c.init(S.r0, 0, te0 - ts0);
+      TitleCursor c; c.init(S.r0, 0, te0 - ts0, lut);
       Tok t; u32 nf = 0;
       while (c.next(t)) { if (nf < (u32)MAXF) { S.off0[nf] = t.start; S.len0[nf] = t.end - t.start; } ++nf; }
       S.nf = nf;
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way */
   const bool walk = active && !err && seed_ok;
   bool fields_ok = true;
-  TitleCursor cur; cur.init(b, ts, te);
+  TitleCursor cur; cur.init(b, ts, te, lut);
   for (u32 f = 0; f < nf && seed_ok; ++f) {
     Tok t; t.start = t.end = 0; t.v = 0; t.num = true;
     u32 len = 0;
@@ -417,7 +435,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   /* the record before this chunk, for the first delta */
   if (tid == 0 && chunk > 0 && seed_ok) {
     u32 pts = d.rstart[r0 - 1], pte = d.te[r0 - 1];
-    TitleCursor pc; pc.init(b, pts, pte);
+    TitleCursor pc; pc.init(b, pts, pte, lut);
     Tok t;
     for (u32 f = 0; f < nf; ++f) { if (!pc.next(t)) break; S.pvals0[f] = t.v; }
   }
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(32) k_classify(Dev d) {
   SbClass &C = d.cls[s];
   if (P.status) { C.status = P.status; C.R = P.n_records; C.payload_len = 0; return; }
   u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
-  classify_subblock(d.in, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
+  classify_subblock(d.in, g_char_lut, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
   C.payload_len = 0;
 }
 
@@ -517,13 +535,22 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
     const u32 slot = tid / Lp, p = tid % Lp;
     if (slot < slots) {
       u32 *row = hist + (slot * Lp + p) * stride;
-      for (u32 i = slot; i < nrec; i += slots) {
-        u32 L = m_len[i];
-        if (p < L) {
-          u32 qs = m_qs[i];
-          u8 q = d.in[qs + p];
-          if (m_x[i]) { u32 a = amb_code(d.in[qs - 3 - L + p]); if (a > 1) q = xfer_qual(a, q); }
-          row[qcode[q]]++;
+      /* four records in flight per thread so that the byte loads overlap */
+      for (u32 i0 = slot; i0 < nrec; i0 += 4 * slots) {
+        u8 q[4]; bool on[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          u32 i = i0 + k * slots;
+          on[k] = i < nrec && p < m_len[i];
+          q[k] = on[k] ? __ldg(d.in + m_qs[i] + p) : (u8)0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!on[k]) continue;
+          u32 i = i0 + k * slots;
+          u8 qq = q[k];
+          if (m_x[i]) { u32 a = amb_code(d.in[m_qs[i] - 3 - m_len[i] + p]); if (a > 1) qq = xfer_qual(a, qq); }
+          row[qcode[qq]]++;
         }
       }
     }
@@ -576,7 +603,10 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  __shared__ u8 lut[256];
+  load_lut(lut);
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  if (!b) return; /* cannot happen: stat1 staged the same span */
   u32 *vals = vals_area(dyn_smem, d.span_bytes);
   load_field_classes(C, fc);
   __syncthreads();
@@ -586,12 +616,12 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   const u32 wbase = tid & ~31u;
   u32 flags = 0;
   /* one walk: string fields are finished here, numeric values are parked in shared memory */
-  TitleCursor cur; cur.init(b, d.rstart[r], d.te[r]);
+  TitleCursor cur; cur.init(b, d.rstart[r], d.te[r], lut);
   for (u32 f = 0; f < nf; ++f) {
+    const FieldClass &F = fc[f];
+    if (F.kind == K_CONST) { cur.skip(F.len0); continue; }
     Tok t; t.start = t.end = 0; t.v = 0; t.num = false;
     if (active) cur.next(t);
-    const FieldClass &F = fc[f];
-    if (F.kind == K_CONST) continue;
     if (F.kind == K_NUM) { vals[f * CH + tid] = t.v; continue; }
     u32 len = t.end - t.start;
     u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
@@ -610,7 +640,7 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
     if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
   }
   if (tid == 0 && chunk > 0) {
-    TitleCursor c; c.init(b, d.rstart[r0 - 1], d.te[r0 - 1]);
+    TitleCursor c; c.init(b, d.rstart[r0 - 1], d.te[r0 - 1], lut);
     Tok t;
     for (u32 f = 0; f < nf; ++f) { if (!c.next(t)) break; pvals0[f] = t.v; }
   }
@@ -680,7 +710,10 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
+  __shared__ u8 lut[256];
+  load_lut(lut);
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_field_classes(C, fc);
   __syncthreads();
   const bool active = tid < nrec;
@@ -708,7 +741,7 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   if (C.nnc) {
     __syncwarp();
     CountSink t; t.init();
-    title_record(b, d.rstart[r], te, C, fc, arena, arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32], lane == 0, PrevShfl(), t);
+    title_record(b, lut, d.rstart[r], te, C, fc, arena, arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32], lane == 0, PrevShfl(), t);
     u32 tb = active ? (u32)t.bits : 0u, x = tb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
@@ -825,7 +858,10 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   const u64 obase = C.out_off; /* byte offset of the payload inside d.out (16-byte aligned) */
   for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
+  __shared__ u8 lut[256];
+  load_lut(lut);
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_field_classes(C, fc);
   __syncthreads();
   const u32 o_title = C.info_len, o_qual = o_title + C.title_len, o_dna = o_qual + C.qual_len;
@@ -878,7 +914,7 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
       for (u32 f = 0; f < C.nf; ++f) if (fc[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
       t.put(v, C.nnc);
     }
-    title_record(b, d.rstart[r], te, C, fc, arena, flags, lane == 0, PrevShfl(), t);
+    title_record(b, lut, d.rstart[r], te, C, fc, arena, flags, lane == 0, PrevShfl(), t);
     t.finish();
   }
 }

@@ -42,10 +42,12 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
   }
   u32 R = (u32)te.size();
   if (!R) return E_MALFORMED;
+  u8 lut[256];
+  fill_char_lut(lut);
   std::vector<u16> kx(R);
   SbAcc *A = (SbAcc *)calloc(1, sizeof(SbAcc));
   // stat1
-  TitleCursor c0; c0.init(b, rstart[0], te[0]);
+  TitleCursor c0; c0.init(b, rstart[0], te[0], lut);
   Tok t; u32 nf = 0; u32 off0[MAXF], len0[MAXF];
   while (c0.next(t)) { if (nf < (u32)MAXF) { off0[nf] = t.start - rstart[0]; len0[nf] = t.end - t.start; } ++nf; }
   if (nf == 0 || nf > (u32)MAXF) return E_UNSUPPORTED;
@@ -60,7 +62,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
     kx[r] = (u16)(st.kept | (st.xfer << 15));
     amax(A->max_qlen, L); amax(A->max_slen, st.kept);
     if (count_seps(b, rstart[r], te[r]) != nf) return E_FIELDS;
-    TitleCursor cur; cur.init(b, rstart[r], te[r]);
+    TitleCursor cur; cur.init(b, rstart[r], te[r], lut);
     for (u32 f = 0; f < nf; ++f) {
       cur.next(t);
       u32 len = t.end - t.start;
@@ -77,7 +79,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
   const u32 AW = (8u << 20) / 4;
   u32 *arena = (u32 *)calloc(AW, 4);
   SbClass *C = (SbClass *)calloc(1, sizeof(SbClass));
-  classify_subblock(b, *A, R, rstart[0], te[0], arena, AW, *C);
+  classify_subblock(b, lut, *A, R, rstart[0], te[0], arena, AW, *C);
   int rc = C->status;
   std::vector<u32> qoff(R + 1), doff(R + 1), blkoff((R + 31) / 32 + 1);
   if (!rc) {
@@ -103,7 +105,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
         i32 bd = 0;
         u32 st_lo = 0, len_lo = 0;
         for (u32 r = lo; r < hi; ++r) {
-          TitleCursor cur; cur.init(b, rstart[r], te[r]);
+          TitleCursor cur; cur.init(b, rstart[r], te[r], lut);
           for (u32 k = 0; k <= f; ++k) cur.next(t);
           u32 len = t.end - t.start;
           i32 v = (i32)t.v, pv = r ? (i32)vals[(size_t)(r - 1) * nf + f] : 0;
@@ -147,7 +149,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
       u32 hi = lo + 32 < R ? lo + 32 : R; u64 bits = C->nnc;
       for (u32 r = lo; r < hi; ++r) {
         CountSink ts; ts.init();
-        title_record(b, rstart[r], te[r], *C, C->f, arena, arena[C->flagbits_off + lo / 32], r == lo, prev_of(r), ts);
+        title_record(b, lut, rstart[r], te[r], *C, C->f, arena, arena[C->flagbits_off + lo / 32], r == lo, prev_of(r), ts);
         bits += ts.bits;
       }
       blkoff[lo / 32] = (u32)((bits + 7) / 8);
@@ -190,7 +192,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
         u32 v = 0;
         for (u32 f = 0; f < nf; ++f) if (C->f[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
         ts.put(v, C->nnc);
-        for (u32 r = lo; r < hi; ++r) title_record(b, rstart[r], te[r], *C, C->f, arena, flags, r == lo, prev_of(r), ts);
+        for (u32 r = lo; r < hi; ++r) title_record(b, lut, rstart[r], te[r], *C, C->f, arena, flags, r == lo, prev_of(r), ts);
         ts.finish();
       }
       sec_len[0] = C->info_len; sec_len[1] = C->title_len; sec_len[2] = C->qual_len; sec_len[3] = C->dna_len;
