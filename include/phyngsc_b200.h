@@ -79,6 +79,7 @@ typedef struct {
  * (< 4 GiB: positions inside a batch are 32-bit); max_subblocks bounds the windows per batch.
  * 0 picks defaults (1 GiB + 16 MiB / 192). */
 int phy_ctx_create(phy_ctx **out, int cuda_device, uint64_t max_batch_bytes, uint32_t max_subblocks);
+int phy_device_count(void); /* CUDA devices visible to the process (0 when there is none) */
 void phy_ctx_destroy(phy_ctx *ctx);
 
 /* Replaces phyNGSC.cpp:168-840 for a whole working region: partition sync (:131-156), window chaining

@@ -31,7 +31,7 @@ class RegionResult(C.Structure):
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
 
 
-EXPORTS = ["phy_ctx_create", "phy_ctx_destroy", "phy_compress_region", "phy_upload", "phy_compress_resident", "phy_download",
+EXPORTS = ["phy_device_count", "phy_ctx_create", "phy_ctx_destroy", "phy_compress_region", "phy_upload", "phy_compress_resident", "phy_download",
            "phy_find_first_record", "phy_device_input", "phy_device_output", "phy_host_alloc", "phy_host_free",
            "phy_make_block_header", "phy_make_footer", "phy_debug_read", "phy_profile", "phy_profile_read", "phy_strerror", "phy_last_error", "phy_abi_version"]
 
@@ -54,6 +54,7 @@ def lib():
         L.phy_ctx_create.restype = C.c_int
         L.phy_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint64, C.c_uint32]
         L.phy_ctx_destroy.argtypes = [C.c_void_p]
+        L.phy_device_count.restype = C.c_int
         L.phy_compress_region.restype = C.c_int
         L.phy_compress_region.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(RegionParams), C.c_void_p, C.c_uint64,
                                           C.POINTER(SubblockDesc), C.POINTER(C.c_uint32), C.POINTER(RegionResult)]

@@ -60,6 +60,12 @@ static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "pla
 
 extern "C" int phy_abi_version(void) { return PHY_ABI_VERSION; }
 
+extern "C" int phy_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 extern "C" const char *phy_strerror(int code) {
   switch (code) {
     case PHY_OK: return "ok";

@@ -1,0 +1,222 @@
+/*
+ * phyNGSC_b200 -- drop-in host driver: `mpiexec -np N ./phyNGSC_b200 in.fastq out.ngsc threads`
+ * (same CLI as the reference, phyNGSC.cpp:61-71).  One MPI rank drives one B200 through the C ABI
+ * (include/phyngsc_b200.h); this file is plain C++/MPI and contains no compression arithmetic.
+ *
+ * What stays exactly as in the reference:
+ *   - working regions: region = size / np, rank r owns [r*region, r*region + region + 499]  (phyNGSC.cpp:113-124)
+ *   - subblock membership / window chaining (done inside the library, bit-exact with :254-331, :744-755)
+ *   - 8 MiB blocks with the bit-packed header, subblocks split across blocks (LSBS / FSBS), stale BESO  (:842-928)
+ *   - footer layout (tasks.cpp:1104-1176)
+ * What changes, as the north star asks: blocks are not appended through the shared file pointer in
+ * completion order (:875, non-deterministic); an MPI_Exscan of the ranks' compressed sizes fixes every
+ * rank's file offset and the blocks are written with MPI_File_write_at, rank by rank.  The footer's block
+ * order list states that order, so the file is a valid .ngsc and every block (keyed by WRID) is byte-identical
+ * to the reference's.
+ *
+ * Differences kept on purpose: np = 1 is accepted (the reference refuses np < 2, :91-97; WRID then takes 0 bits);
+ * `threads` only selects the per-thread record cap of :51 for threads = 1 semantics (the GPU path has no thread count).
+ * Built against a real <mpi.h> when mpicxx exists, otherwise against host/mpi_shim/mpi.h (PHY_SHIM_NP=<n> ./phyNGSC_b200 ...).
+ */
+#include <mpi.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "phyngsc_b200.h"
+
+static const uint64_t READ_BUFFER_SIZE = 1u << 23;  /* defs.h:20 */
+static const uint64_t WRITE_BUFFER_SIZE = 1u << 23; /* defs.h:21 */
+static const uint32_t OVERLAP = 500;                /* phyNGSC.cpp:48 */
+static const uint64_t READ_SLACK = 64 * 1024;       /* bytes read past p_wr_end: records longer than the overlap */
+
+static int ceil_log2(uint64_t x) { int b = 0; while ((1ull << b) < x) ++b; return b; }
+static int bitlen(uint64_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
+
+static void die(int rank, int code, const char *msg, const char *detail) {
+  fprintf(stderr, "[E] rank %d: %s%s%s\n", rank, msg, detail ? ": " : "", detail ? detail : "");
+  MPI_Abort(MPI_COMM_WORLD, code);
+  exit(code);
+}
+
+/* Block assembly of one rank, phyNGSC.cpp:842-928: appends the finished blocks to `file_bytes`. */
+struct BlockAssembler {
+  int wrid, bewr;
+  std::vector<uint8_t> wbuf;   /* payload bytes of the block being filled */
+  std::vector<uint32_t> sbol;
+  int beso = 0, bcss = 0;
+  std::vector<uint8_t> file_bytes;
+  uint32_t n_blocks = 0, last_block_size = 0;
+
+  BlockAssembler(int rank, int np) : wrid(rank), bewr(ceil_log2((uint64_t)np)) { wbuf.reserve(WRITE_BUFFER_SIZE); }
+
+  uint64_t header_size() const { return ((uint64_t)bewr + 18 + (uint64_t)beso * sbol.size() + 7 + 7) / 8; } /* structures.h:323-333 */
+
+  bool flush_block() {
+    uint8_t hdr[4096];
+    uint64_t hs = header_size();
+    uint32_t hl = phy_make_block_header(wrid, bewr, (int)hs, beso, bcss, sbol.data(), (uint32_t)sbol.size(), hdr, sizeof hdr);
+    if (hl == 0 || hl != hs) return false;
+    file_bytes.insert(file_bytes.end(), hdr, hdr + hl);
+    file_bytes.insert(file_bytes.end(), wbuf.begin(), wbuf.end());
+    last_block_size = (uint32_t)(hl + wbuf.size());
+    ++n_blocks;
+    return true;
+  }
+
+  bool add_subblock(const uint8_t *p, uint32_t n) {
+    sbol.push_back(n);
+    uint32_t mx = 0;
+    for (uint32_t v : sbol) if (v > mx) mx = v;
+    beso = bitlen(mx); /* evaluated with the subblock's full size even if it is split below (:843-846) */
+    uint64_t hs = header_size();
+    if (wbuf.size() + n + hs > WRITE_BUFFER_SIZE) {
+      bcss |= 1; /* LSBS: the last subblock continues in the next block */
+      uint64_t fill = WRITE_BUFFER_SIZE - (wbuf.size() + hs);
+      sbol.back() = (uint32_t)fill;
+      wbuf.insert(wbuf.end(), p, p + fill);
+      if (!flush_block()) return false;
+      wbuf.assign(p + fill, p + n);
+      bcss |= 2; bcss &= ~1; /* FSBS stays set for all later blocks of the rank (:893-894) */
+      sbol.clear(); sbol.push_back((uint32_t)(n - fill));
+    } else {
+      wbuf.insert(wbuf.end(), p, p + n);
+    }
+    return true;
+  }
+
+  bool finish() { /* :910-928 */
+    if (wbuf.empty()) { last_block_size = 0; return true; }
+    return flush_block();
+  }
+};
+
+int main(int argc, char **argv) {
+  int provided = 0, rank = 0, np = 1;
+  MPI_Init_thread(&argc, &argv, MPI_THREAD_FUNNELED, &provided);
+  MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+  MPI_Comm_size(MPI_COMM_WORLD, &np);
+  if (argc != 4) {
+    if (rank == 0) printf("[E] usage: mpiexec -np <N> %s <in.fastq> <out.ngsc> <threads>\n", argv[0]);
+    MPI_Finalize();
+    return 1;
+  }
+  const int threads = atoi(argv[3]);
+  if (threads < 1) {
+    if (rank == 0) printf("[E] the number of threads must be at least 1\n");
+    MPI_Finalize();
+    return 1;
+  }
+  MPI_File fin, fout;
+  if (MPI_File_open(MPI_COMM_WORLD, argv[1], MPI_MODE_RDONLY, MPI_INFO_NULL, &fin) != MPI_SUCCESS) {
+    if (rank == 0) printf("[E] cannot open %s\n", argv[1]);
+    MPI_Finalize();
+    return 2;
+  }
+  if (rank == 0) remove(argv[2]); /* the reference does not truncate an existing output */
+  MPI_Barrier(MPI_COMM_WORLD);
+  if (MPI_File_open(MPI_COMM_WORLD, argv[2], MPI_MODE_CREATE | MPI_MODE_RDWR, MPI_INFO_NULL, &fout) != MPI_SUCCESS) {
+    if (rank == 0) printf("[E] cannot create %s\n", argv[2]);
+    MPI_Finalize();
+    return 2;
+  }
+  if (rank == 0) printf("[I] INFO: phyNGSC_b200, %d rank(s), one GPU each\n", np);
+  const double t0 = MPI_Wtime();
+
+  MPI_Offset fsize = 0;
+  MPI_File_get_size(fin, &fsize);
+  const uint64_t size = (uint64_t)fsize, region = size / (uint64_t)np, start = (uint64_t)rank * region;
+  uint64_t end = rank == np - 1 ? size : start + region + OVERLAP + READ_SLACK;
+  if (end > size) end = size;
+  const uint64_t region_len = end - start;
+
+  uint8_t *in = (uint8_t *)phy_host_alloc(region_len + 64);
+  uint64_t out_cap = region_len / 2 + (1u << 20);
+  uint8_t *out = (uint8_t *)phy_host_alloc(out_cap);
+  if (!in || !out) die(rank, 3, "cannot allocate pinned host buffers", nullptr);
+  for (uint64_t o = 0; o < region_len; o += 1u << 30) { /* MPI counts are ints */
+    uint64_t n = region_len - o < (1u << 30) ? region_len - o : (1u << 30);
+    MPI_File_read_at(fin, (MPI_Offset)(start + o), in + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
+  }
+  const double t_read = MPI_Wtime();
+
+  const int ndev = phy_device_count();
+  if (ndev < 1) die(rank, 3, "no CUDA device (this build has no CPU path)", nullptr);
+  const char *lr = getenv("LOCAL_RANK");
+  const int dev = (lr ? atoi(lr) : rank) % ndev; /* one rank per GPU; ranks wrap when there are fewer GPUs */
+  uint64_t batch = region_len + (1u << 20) < (3ull << 30) ? region_len + (1u << 20) : (1ull << 30) + (16u << 20);
+  phy_ctx *ctx = nullptr;
+  int rc = phy_ctx_create(&ctx, dev, batch, (uint32_t)(batch / (READ_BUFFER_SIZE / 2)) + 16);
+  if (rc) die(rank, 3, "cannot create the GPU context", phy_strerror(rc));
+
+  phy_region_params prm;
+  prm.file_size = size; prm.np = np; prm.rank = rank; prm.window_bytes = READ_BUFFER_SIZE; prm.overlap = OVERLAP;
+  prm.record_cap = 100000u / (uint32_t)threads; /* records_per_th, phyNGSC.cpp:51,82 */
+  std::vector<phy_subblock_desc> descs((size_t)(region_len / (READ_BUFFER_SIZE / 2)) + 64);
+  uint32_t nd_ = (uint32_t)descs.size();
+  phy_region_result res;
+  rc = phy_compress_region(ctx, in, region_len, &prm, out, out_cap, descs.data(), &nd_, &res);
+  if (rc) die(rank, 4, phy_strerror(rc), phy_last_error(ctx));
+  const double t_comp = MPI_Wtime();
+  for (uint32_t i = 0; i < nd_; ++i)
+    if (descs[i].warnings & 1u) printf("[!] WARNING: rank %d subblock %u hit the record cap\n", rank, i);
+
+  BlockAssembler ba(rank, np);
+  for (uint32_t i = 0; i < nd_; ++i)
+    if (!ba.add_subblock(out + descs[i].out_off, descs[i].out_len)) die(rank, 4, "block header does not fit", nullptr);
+  if (!ba.finish()) die(rank, 4, "block header does not fit", nullptr);
+
+  /* file offsets: exclusive scan of the ranks' compressed sizes (the only cross-rank exchange on the data path) */
+  long long mine = (long long)ba.file_bytes.size(), off = 0;
+  MPI_Exscan(&mine, &off, 1, MPI_LONG_LONG, MPI_SUM, MPI_COMM_WORLD);
+  if (rank == 0) off = 0;
+  for (uint64_t o = 0; o < (uint64_t)mine; o += 1u << 30) {
+    uint64_t n = (uint64_t)mine - o < (1u << 30) ? (uint64_t)mine - o : (1u << 30);
+    MPI_File_write_at(fout, (MPI_Offset)((uint64_t)off + o), ba.file_bytes.data() + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
+  }
+
+  /* footer: gather {n_blocks, n_subblocks, wr_overlap, last_block_size, bytes} on rank 0 (phyNGSC.cpp:930-1057) */
+  long long info[5] = {(long long)ba.n_blocks, (long long)nd_, (long long)res.wr_overlap, (long long)ba.last_block_size, mine};
+  std::vector<long long> all((size_t)np * 5);
+  MPI_Gather(info, 5, MPI_LONG_LONG, all.data(), 5, MPI_LONG_LONG, 0, MPI_COMM_WORLD);
+  if (rank == 0) {
+    std::vector<int32_t> overlaps(np), order;
+    std::vector<uint32_t> lbs(np);
+    uint64_t nblk = 0, nsb = 0, total = 0;
+    for (int r = 0; r < np; ++r) {
+      overlaps[r] = (int32_t)all[5 * r + 2]; lbs[r] = (uint32_t)all[5 * r + 3];
+      for (long long k = 0; k < all[5 * r]; ++k) order.push_back(r);
+      nblk += (uint64_t)all[5 * r]; nsb += (uint64_t)all[5 * r + 1]; total += (uint64_t)all[5 * r + 4];
+    }
+    std::vector<uint8_t> foot(64 + 4 * (order.size() + 2 * (size_t)np));
+    bool any_ov = false;
+    for (int r = 1; r < np; ++r) any_ov = any_ov || overlaps[r] > 0;
+    if (!any_ov) overlaps[0] = 1; /* every rank starts on a record: the reference evaluates log2(0) here; keep the width field at 1 */
+    int32_t fl = phy_make_footer(np, size, (uint32_t)nblk, (uint32_t)nsb, overlaps.data(), order.data(), lbs.data(), foot.data(), (uint32_t)foot.size());
+    if (fl < 0) die(rank, 4, "cannot build the footer", phy_strerror(fl));
+    MPI_File_write_at(fout, (MPI_Offset)total, foot.data(), fl, MPI_CHAR, MPI_STATUS_IGNORE);
+  }
+  const double t1 = MPI_Wtime();
+
+  /* the reference's per-rank table (phyNGSC.cpp:1060-1066) plus where the time went */
+  for (int r = 0; r < np; ++r) {
+    MPI_Barrier(MPI_COMM_WORLD);
+    if (r == rank) {
+      if (rank == 0) printf("RANK\tCOMP_TIME\tN_BLOCK\tN_SUBBLOCKS\n");
+      printf("%d\t%f\t%u\t%u\n", rank, t1 - t0, ba.n_blocks, nd_);
+      printf("[I] rank %d: read %.3fs, gpu path %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), assemble+write %.3fs, %llu -> %lld bytes\n",
+             rank, t_read - t0, t_comp - t_read, res.h2d_ms, res.kernel_ms, res.d2h_ms, res.kernel_launches, t1 - t_comp,
+             (unsigned long long)res.bytes_in, mine);
+      fflush(stdout);
+    }
+  }
+  MPI_Barrier(MPI_COMM_WORLD);
+  phy_ctx_destroy(ctx);
+  phy_host_free(in); phy_host_free(out);
+  MPI_File_close(&fin); MPI_File_close(&fout);
+  MPI_Finalize();
+  return 0;
+}
