@@ -192,6 +192,7 @@ def main():
     import torch
     import torch.distributed as dist
     from phyngsc_b200 import api
+    from phyngsc_b200 import dist as pdist
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device -- the product path has no CPU fallback", file=sys.stderr)
         return 2
@@ -252,10 +253,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(a.steps):
         d2, o2, r2 = ctx.compress_region(data, prm, out=pin_out.array)
-        if world > 1:  # exclusive scan of compressed sizes -> file offsets (MPI_Exscan in the host driver)
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([r2.bytes_out], dtype=torch.int64, device="cuda"))
-            _offset = int(sum(int(s.item()) for s in sizes[:rank]))
+        _offset, _total = pdist.exscan_bytes(r2.bytes_out, device="cuda")  # file offsets (MPI_Exscan in the host driver)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / a.steps)
     clocks = sampler.summary(t_region0, time.perf_counter())
