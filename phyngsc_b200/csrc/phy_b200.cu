@@ -29,6 +29,12 @@ struct phy_ctx {
   u32 *tile_cnt = nullptr, *tile_off = nullptr;
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
+  /* second input / output buffers and copy streams of the pipelined region call (allocated on first use) */
+  u8 *in2 = nullptr, *out2 = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h0[2] = {nullptr, nullptr}, ev_d0[2] = {nullptr, nullptr};
+  u8 *h_nl = nullptr;
   /* pinned host mirrors */
   BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; SbOut *h_sbout = nullptr; PlanState *h_state = nullptr;
   u32 launches = 0;
@@ -93,10 +99,16 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
-                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out};
+                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2};
   for (void *p : dev) if (p) cudaFree(p);
-  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state};
+  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl};
   for (void *p : host) if (p) cudaFreeHost(p);
+  for (int i = 0; i < 2; ++i) {
+    cudaEvent_t evs[] = {ctx->ev_in[i], ctx->ev_c[i], ctx->ev_out[i], ctx->ev_h0[i], ctx->ev_d0[i]};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+  }
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->pev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -149,9 +161,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   }
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
+  CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_SMEM));
   CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
   CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
-  CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_SMEM));
   CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
   return PHY_OK;
 }
@@ -180,16 +192,16 @@ extern "C" int64_t phy_find_first_record(const uint8_t *b, uint64_t lim) {
 
 /* Runs every kernel over the batch that is resident in ctx->in[0..len).  `start_pos` = first record of the
  * next window inside the batch.  On return h_hdr / h_plans / h_sbout describe the batch. */
-static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
+static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
   Dev d;
   memset(&d, 0, sizeof d);
-  d.in = ctx->in; d.len = len; d.start_pos = start_pos;
+  d.in = in; d.len = len; d.start_pos = start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
   d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff;
   d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
-  d.out = ctx->out; d.out_cap = ctx->out_cap;
+  d.out = out; d.out_cap = ctx->out_cap;
   d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
   d.span_bytes = 0;
   cudaStream_t st = ctx->stream;
@@ -232,12 +244,13 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
-  dim3 gc(H.max_chunks, S), gq(H.max_qchunks, S);
+  dim3 gc(H.max_chunks, S);
   PMARK();
   k_stat1<<<gc, CH, span_v, st>>>(d); PMARK();
   k_classify<<<S, 32, 0, st>>>(d); PMARK();
-  k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d); PMARK();
-  k_qhist<<<gq, 256, QH_SMEM, st>>>(d); PMARK();
+  k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d);
+  k_dnacount<<<dim3(16, S), 256, 0, st>>>(d); PMARK();
+  k_qhist<<<dim3(H.max_qchunks, S), 256, QH_SMEM, st>>>(d); PMARK();
   k_stat2<<<gc, CH, span_v, st>>>(d); PMARK();
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
   k_lengths<<<gc, CH, span, st>>>(d); PMARK();
@@ -245,7 +258,7 @@ static int run_batch(phy_ctx *ctx, u32 len, u32 start_pos, i64 batch_base, i64 r
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
   k_emit<<<gc, CH, span, st>>>(d); PMARK();
-  ctx->launches += 11;
+  ctx->launches += 12;
   CK(cudaGetLastError());
   if (ctx->profile) {
     CK(cudaStreamSynchronize(st));
@@ -337,7 +350,7 @@ extern "C" int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const ph
   ctx->launches = 0;
   CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  rc = run_batch(ctx, (u32)len, first, 0, (i64)len, true);
+  rc = run_batch(ctx, ctx->in, ctx->out, (u32)len, first, 0, (i64)len, true);
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -370,6 +383,28 @@ extern "C" int phy_download(phy_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64
   return PHY_OK;
 }
 
+/* second buffers, copy streams and events of the pipelined region call */
+static int pipeline_init(phy_ctx *ctx) {
+  if (ctx->s_in) return PHY_OK;
+  CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreate(&ctx->ev_in[i]));
+    CK(cudaEventCreateWithFlags(&ctx->ev_c[i], cudaEventDisableTiming));
+    CK(cudaEventCreate(&ctx->ev_out[i]));
+    CK(cudaEventCreate(&ctx->ev_h0[i]));
+    CK(cudaEventCreate(&ctx->ev_d0[i]));
+  }
+  CK(cudaHostAlloc(&ctx->h_nl, 64, cudaHostAllocDefault));
+  memset(ctx->h_nl, 0, 64);
+  ctx->h_nl[0] = '\n';
+  return PHY_OK;
+}
+
+/* Pipelined over batches: while batch b is compressed, batch b+1 streams host -> device on a second stream and
+ * the payloads of batch b-1 stream device -> host on a third (double-buffered input and output).  The start of
+ * batch b+1 does not depend on batch b's result: it is placed one window + slack before the end of batch b, which
+ * is never past the point where the window chain stops in batch b. */
 extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
                                    uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
                                    phy_region_result *result) {
@@ -384,27 +419,70 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
   cudaStream_t s = ctx->stream;
   CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));
+  const bool multi = region_len > ctx->max_batch;
+  if (multi) {
+    rc = pipeline_init(ctx);
+    if (rc) return rc;
+    if (!ctx->in2) { CK(cudaMalloc(&ctx->in2, ctx->max_batch + 4096)); CK(cudaMemset(ctx->in2, 0, ctx->max_batch + 4096)); }
+    if (!ctx->out2) CK(cudaMalloc(&ctx->out2, ctx->out_cap + 64));
+  } else {
+    rc = pipeline_init(ctx);
+    if (rc) return rc;
+  }
+  u8 *inb[2] = {ctx->in, multi ? ctx->in2 : ctx->in}, *outb[2] = {ctx->out, multi ? ctx->out2 : ctx->out};
+  const u64 back = (u64)params->window_bytes + ctx->slack; /* how far before a batch's end the next one starts */
+  if (multi && ctx->max_batch < 2 * back + 4096) { ctx->err = "max_batch_bytes is too small for the window size"; return PHY_ERR_CAPACITY; }
   const u32 cap_descs = *inout_n_descs;
   u32 nd = 0, nb = 0;
-  u64 out_used = 0, base = 0, next_pos = 0; /* base: region-relative start of the batch; next_pos: chain position */
+  u64 out_used = 0, next_pos = 0;
   float k_ms = 0, h2d_ms = 0, d2h_ms = 0;
   int worst = 0;
-  bool done = false;
-  while (!done) {
-    u64 blen = region_len - base;
+  const bool patch_nl = st.is_last && region[region_len - 1] != '\n';
+
+  /* enqueue the upload of the batch that starts at `base` into buffer `slot` (stream s_in) */
+  auto upload = [&](u64 base, int slot, u64 &blen, bool &final, u64 &len) -> int {
+    blen = region_len - base;
     if (blen > ctx->max_batch) blen = ctx->max_batch;
-    const bool final = base + blen == region_len;
-    CK(cudaEventRecord(ctx->ev[0], s));
-    CK(cudaMemcpyAsync(ctx->in, region + base, blen, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->in + blen, 0, 64, s));
-    u64 len = blen;
-    rc = patch_trailing_newline(ctx, len, st.is_last, final, region[region_len - 1]);
-    if (rc) return rc;
+    final = base + blen == region_len;
+    len = blen;
+    CK(cudaEventRecord(ctx->ev_h0[slot], ctx->s_in));
+    CK(cudaMemcpyAsync(inb[slot], region + base, blen, cudaMemcpyHostToDevice, ctx->s_in));
+    if (final && patch_nl) { /* virtual trailing newline, see patch_trailing_newline */
+      CK(cudaMemcpyAsync(inb[slot] + blen, ctx->h_nl, 64, cudaMemcpyHostToDevice, ctx->s_in));
+      len += 1;
+    } else {
+      CK(cudaMemsetAsync(inb[slot] + blen, 0, 64, ctx->s_in));
+    }
+    CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    return PHY_OK;
+  };
+
+  u64 base = 0, blen = 0, len = 0;
+  bool final = false;
+  rc = upload(0, 0, blen, final, len);
+  if (rc) return rc;
+  bool done = false;
+  bool have_d2h[2] = {false, false};
+  while (!done) {
+    const int cur = (int)(nb & 1), nxt = cur ^ 1;
+    /* speculative upload of the next batch */
+    u64 nbase = 0, nblen = 0, nlen = 0;
+    bool nfinal = false, have_next = false;
+    if (!final) {
+      nbase = (base + blen - back) & ~(u64)255;
+      CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_c[nxt], 0)); /* batch b-1 has finished reading that buffer */
+      rc = upload(nbase, nxt, nblen, nfinal, nlen);
+      if (rc) return rc;
+      have_next = true;
+    }
+    CK(cudaStreamWaitEvent(s, ctx->ev_in[cur], 0));
+    if (have_d2h[cur]) CK(cudaStreamWaitEvent(s, ctx->ev_out[cur], 0)); /* payloads of batch b-2 have left that buffer */
     CK(cudaEventRecord(ctx->ev[1], s));
-    u32 start_pos = (u32)(next_pos - base) + (nb == 0 ? first : 0u);
-    rc = run_batch(ctx, (u32)len, start_pos, (i64)base, (i64)region_len, final);
+    const u32 start_pos = (u32)(next_pos - base) + (nb == 0 ? first : 0u);
+    rc = run_batch(ctx, inb[cur], outb[cur], (u32)len, start_pos, (i64)base, (i64)region_len, final);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], s));
+    CK(cudaEventRecord(ctx->ev_c[cur], s));
     CK(cudaStreamSynchronize(s));
     const u32 S = ctx->last_S;
     const PlanState hs = *ctx->h_state;
@@ -413,22 +491,38 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
     if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
     const u64 tot = S ? ctx->h_hdr->total_out : 0;
     if (out_used + tot > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
-    CK(cudaEventRecord(ctx->ev[3], s));
-    if (tot) CK(cudaMemcpyAsync(out + out_used, ctx->out, tot, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(ctx->ev[4], s));
-    CK(cudaStreamSynchronize(s));
+    if (have_d2h[cur]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[cur], ctx->ev_out[cur])); d2h_ms += t; have_d2h[cur] = false; }
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_c[cur], 0));
+    CK(cudaEventRecord(ctx->ev_d0[cur], ctx->s_out));
+    if (tot) CK(cudaMemcpyAsync(out + out_used, outb[cur], tot, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaEventRecord(ctx->ev_out[cur], ctx->s_out));
+    have_d2h[cur] = true;
     fill_descs(ctx, S, out_used, descs + nd);
     float t;
-    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1])); h2d_ms += t;
     CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); k_ms += t;
-    CK(cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4])); d2h_ms += t;
     nd += S; out_used += tot; ++nb;
     done = hs.done != 0;
     next_pos = (u64)hs.bytes_read;
     if (!done) {
       if (final) { ctx->err = "region exhausted before the working region was covered"; return PHY_ERR_MALFORMED; }
-      base = next_pos & ~(u64)255;
+      if (!have_next || next_pos < nbase) {
+        /* the chain stopped early (subblock capacity): the speculative upload starts too late, redo it */
+        CK(cudaStreamSynchronize(ctx->s_in));
+        nbase = next_pos & ~(u64)255;
+        rc = upload(nbase, nxt, nblen, nfinal, nlen);
+        if (rc) return rc;
+      }
+      base = nbase; blen = nblen; len = nlen; final = nfinal;
     }
+  }
+  CK(cudaStreamSynchronize(ctx->s_in));
+  CK(cudaStreamSynchronize(ctx->s_out));
+  for (int i = 0; i < 2; ++i)
+    if (have_d2h[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[i], ctx->ev_out[i])); d2h_ms += t; }
+  { /* upload time: not separable per batch once copies overlap; report bytes / measured copy windows of the last two */
+    float t = 0;
+    for (int i = 0; i < 2 && i < (int)nb; ++i) if (cudaEventElapsedTime(&t, ctx->ev_h0[i], ctx->ev_in[i]) == cudaSuccess) h2d_ms += t;
+    if (nb > 2) h2d_ms = h2d_ms / 2 * nb; /* extrapolated from the last two batches */
   }
   *inout_n_descs = nd;
   if (result) {

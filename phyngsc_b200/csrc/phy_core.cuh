@@ -79,7 +79,13 @@ PHY_HD i32 wsub(i32 a, i32 b) { return (i32)((u32)a - (u32)b); }
 /* order-preserving map int32 -> uint32 so that signed min/max become unsigned atomicMax on zeroed memory */
 PHY_HD u32 key_of(i32 v) { return (u32)v ^ 0x80000000u; }
 PHY_HD i32 val_of(u32 k) { return (i32)(k ^ 0x80000000u); }
-PHY_HD u32 bswap32(u32 x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); }
+PHY_HD u32 bswap32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, 0, 0x0123);
+#else
+  return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24);
+#endif
+}
 PHY_HD u32 align_up(u32 x, u32 a) { return (x + a - 1) / a * a; }
 
 /* bits needed for a leaf id in the serialised tree (huffman.cpp:96-98) */
@@ -104,11 +110,11 @@ struct CountSink {
 };
 
 struct OrSink {
-  u32 *w;     /* word pointer of the next word to flush */
-  u64 acc;    /* pending bits, right-aligned            */
-  u32 fill;   /* number of pending bits incl. the leading pad of the first word */
+  u32 *w;     /* word pointer of the next word to flush                                    */
+  u64 acc;    /* pending bits, left-aligned: the next stream bit is bit 63                 */
+  u32 fill;   /* number of pending bits incl. the leading pad of the first word (< 32)     */
   bool shared_first;
-  bool live;  /* false: walk without storing (lanes that only keep a warp converged) */
+  bool live;  /* false: walk without storing (lanes that only keep a warp converged)       */
   PHY_HD void init(u32 *words, u64 bitpos, bool live_ = true) {
     w = words + (bitpos >> 5);
     fill = (u32)(bitpos & 31);
@@ -117,28 +123,29 @@ struct OrSink {
     live = live_;
   }
   PHY_HD void flush_word(u32 word, bool shared) {
-    if (!live) return;
-    u32 v = bswap32(word);
+    if (live) {
+      u32 v = bswap32(word);
 #if defined(__CUDA_ARCH__)
-    if (shared) atomicOr(w, v); else *w = v;
+      if (shared) atomicOr(w, v); else *w = v;
 #else
-    (void)shared; *w |= v;
+      (void)shared; *w |= v;
 #endif
+    }
     ++w;
   }
   PHY_HD void put(u32 v, u32 n) { /* n <= 32, v < 2^n */
     if (n == 0) return;
-    acc = (acc << n) | v;
+    acc |= (u64)v << (64 - fill - n); /* shift in [1, 63] */
     fill += n;
     if (fill >= 32) {
-      fill -= 32;
-      flush_word((u32)(acc >> fill), shared_first);
+      flush_word((u32)(acc >> 32), shared_first);
       shared_first = false;
-      acc &= ((u64)1 << fill) - 1;
+      acc <<= 32;
+      fill -= 32;
     }
   }
   PHY_HD void finish() {
-    if (fill) { flush_word((u32)(acc << (32 - fill)), true); fill = 0; acc = 0; }
+    if (fill) { flush_word((u32)(acc >> 32), true); fill = 0; acc = 0; }
   }
 };
 
@@ -192,7 +199,7 @@ struct SbAcc {
   i32 status; u32 warnings;
   u32 max_qlen, max_slen;
   u32 qpresent[8];
-  u32 dna_occ[256];
+  u32 dna_occ[256];  /* non-zero = symbol occurs in the (compacted) DNA; exact counts are taken later, only if needed */
   FieldAcc f[MAXF];
 };
 
@@ -213,7 +220,8 @@ struct SbClass {
   u32 max_qlen, max_slen, nsym, nq, plain, flags, nb_len;
   u32 ts0, te0;                /* title line of record 0 (batch-relative positions)                   */
   /* arena layout (word offsets unless stated) */
-  u32 ntab, tabdesc_off, tq0, tdna, qstat_off, zero_begin, zero_end;
+  u32 ntab, tabdesc_off, tq0, tdna, qstat_off, dnastat_off, zero_begin, zero_end;
+  u32 qpk_off, qpk_bad;        /* quality tables packed to 16 bits (len << 12 | code); qpk_bad != 0 when a code is longer than 12 bits */
   u32 nblk, flagbits_off;
   u32 blkloc_off;              /* per 32-record title block: byte offset inside its chunk */
   u32 nchunk, chunk_off;       /* per 128-record chunk: [3][nchunk] totals -> bases of quality bits, dna bits, title bytes */
@@ -434,8 +442,11 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   u32 numhist_off[MAXF];
   for (u32 f = 0; f < nf; ++f) numhist_off[f] = (C.f[f].kind == K_NUM && C.f[f].has_table) ? al.take(C.f[f].diff) : 0;
   u32 chrhist_off = al.take(ntab_chr * 256);
+  u32 dnastat_off = al.take(nsym); /* exact symbol counts, only filled (by a later pass) when the DNA is Huffman coded */
+  C.dnastat_off = dnastat_off;
   C.zero_end = al.used;
-  u32 dnastat_off = al.take(nsym);
+  C.qpk_off = al.take(((C.max_qlen + 1) * nq + 1) / 2);
+  C.qpk_bad = 0;
   /* table directory: quality (max_qlen+1), dna (0/1), numeric, char */
   u32 ntab = (C.max_qlen + 1) + (C.plain ? 0 : 1) + ntab_num + ntab_chr;
   C.ntab = ntab;
@@ -493,7 +504,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   }
   C.tdna = NOTAB;
   if (!C.plain) {
-    for (u32 i = 0; i < nsym; ++i) arena[dnastat_off + i] = A.dna_occ[C.symbols[i]]; /* tasks.cpp:233-236 */
+    /* sym_stats (tasks.cpp:233-236) are counted into arena[dnastat_off + sym_code] after the zeroing pass */
     C.tdna = tid;
     td[tid].n = nsym; td[tid].freq_off = dnastat_off; td[tid].cl_off = cl_off; td[tid].tree_off = tree_off;
     td[tid].tree_len = 0; td[tid].dst = 0;
@@ -563,27 +574,57 @@ PHY_HD void seqqual_stat(const u8 *b, u32 ss, u32 L, u32 qs, SeqStat &o, Other o
 }
 
 /* ---- per-record stream walkers ----------------------------------------------------------------- */
+/* Quality table lookups: (table, symbol code) -> (code, len).  QFull reads the 64-bit entries the Huffman stage
+ * wrote; QPacked reads a 16-bit copy (len << 12 | code, valid when no code is longer than 12 bits) that the GPU
+ * kernels keep in shared memory. */
+struct QFull {
+  const u64 *cl; u32 nq;
+  PHY_HD void get(u32 table, u32 c, u32 &code, u32 &len) const { u64 e = cl[table * nq + c]; code = (u32)e; len = (u32)(e >> 32); }
+};
+struct QPacked {
+  const u16 *pk; u32 nq;
+  PHY_HD void get(u32 table, u32 c, u32 &code, u32 &len) const { u32 e = pk[table * nq + c]; code = e & 0xFFFu; len = e >> 12; }
+};
+PHY_HD bool qpack_entry(u64 e, u16 &out) {
+  u32 len = (u32)(e >> 32), code = (u32)e;
+  if (len > 12) { out = 0; return false; }
+  out = (u16)((len << 12) | code);
+  return true;
+}
+
 /* Quality codes of one record: position k uses table k+1 (tasks.cpp:609-619). */
-template <class Sink>
-PHY_HD void quality_record(const u8 *b, u32 ss, u32 L, u32 qs, bool xfer, const u8 *qua_code, const u64 *qcl, u32 nq, Sink &s) {
-  const u64 *row = qcl + nq; /* table 1 */
-  for (u32 j = 0; j < L; ++j, row += nq) {
-    u8 q = b[qs + j];
-    if (xfer) { u32 a = amb_code(b[ss + j]); if (a > 1) q = xfer_qual(a, q); }
-    u64 e = row[qua_code[q]];
-    s.put((u32)e, (u32)(e >> 32));
+template <class Sink, class Q>
+PHY_HD void quality_record(const u8 *b, u32 ss, u32 L, u32 qs, bool xfer, const u8 *qua_code, const Q &tab, Sink &s) {
+  const u8 *qp = b + qs, *sp = b + ss;
+  for (u32 j = 0; j < L; ++j) {
+    u8 q = qp[j];
+    if (xfer) { u32 a = amb_code(sp[j]); if (a > 1) q = xfer_qual(a, q); }
+    u32 code, len;
+    tab.get(j + 1, qua_code[q], code, len);
+    s.put(code, len);
   }
 }
 
-/* DNA codes of one record (tasks.cpp:544-557): 2 bits per kept base or its Huffman code. */
+/* DNA codes of one record (tasks.cpp:544-557): 2 bits per kept base (sixteen at a time) or its Huffman code. */
 template <class Sink>
 PHY_HD void dna_record(const u8 *b, u32 ss, u32 L, bool xfer, bool plain, const u8 *sym_code, const u64 *dcl, Sink &s) {
+  const u8 *sp = b + ss;
+  if (plain) {
+    u32 w = 0, cnt = 0;
+    for (u32 j = 0; j < L; ++j) {
+      u8 c = sp[j];
+      if (xfer && !is_acgt(c)) continue; /* transferred codes are > 1 by construction */
+      w = (w << 2) | sym_code[c];
+      if (++cnt == 16) { s.put(w, 32); w = 0; cnt = 0; }
+    }
+    s.put(w, 2 * cnt);
+    return;
+  }
   for (u32 j = 0; j < L; ++j) {
-    u8 c = b[ss + j];
-    if (xfer && !is_acgt(c)) continue; /* transferred codes are > 1 by construction */
-    u32 k = sym_code[c];
-    if (plain) s.put(k, 2);
-    else { u64 e = dcl[k]; s.put((u32)e, (u32)(e >> 32)); }
+    u8 c = sp[j];
+    if (xfer && !is_acgt(c)) continue;
+    u64 e = dcl[sym_code[c]];
+    s.put((u32)e, (u32)(e >> 32));
   }
 }
 

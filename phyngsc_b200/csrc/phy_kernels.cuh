@@ -25,6 +25,7 @@
  */
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include "phy_core.cuh"
 
 namespace phy {
@@ -45,6 +46,8 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u64 next_pos;        /* region-relative position where the next window starts                 */
   u32 max_qchunks;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
+  u32 max_qh_words;    /* max over subblocks of max_qlen * (n_qualities | 1): one private histogram copy */
+  u32 pad;
 };
 
 struct SbOut {         /* device -> host, one per subblock */
@@ -65,6 +68,7 @@ struct Dev {
   i64 batch_base, region_len; i32 batch_is_final; u32 slack;
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
+  u32 qh_bytes;               /* shared memory for the private quality-histogram copies         */
 };
 
 /* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
     u32 run = 0;
     for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; }
     d.hdr->NL = run; d.hdr->NR = run / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_qh_words = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (run / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -303,6 +307,7 @@ struct Stat1S {
   u32 nf, ts0, te0;
   u32 off0[MAXF], len0[MAXF];
   u32 pvals0[MAXF];
+  u8 qflag[256];  /* quality byte seen (after ambiguity transfer) */
   u8 r0[R0_MAX];
 };
 
@@ -315,8 +320,9 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
   for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
   const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
-  __shared__ u8 lut[256];
+  __shared__ u8 lut[256], dlut[256];
   load_lut(lut);
+  for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'G' ? 4 : i == 'T' ? 8 : 0);
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) { if (tid == 0) atomicMin(&d.acc[s].status, (i32)E_UNSUPPORTED); return; }
   u32 *vals = vals_area(dyn_smem, d.span_bytes); /* vals[f * CH + tid] */
@@ -353,52 +359,41 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       if ((c0 >= '0' && c0 <= '3') || (c1 >= '0' && c1 <= '3')) err = E_COLORSPACE;
     }
   }
-  /* sequence / quality (phyNGSC.cpp:549-619): one pass; records with ambiguity codes take a second one */
-  u32 kept = 0, acgt0 = 0, acgt1 = 0, acgt2 = 0, acgt3 = 0, myL = 0;
+  /* sequence / quality (phyNGSC.cpp:549-619): one pass; records with ambiguity codes take a second one.
+   * Only the PRESENCE of A/C/G/T is recorded here (that decides plain 2-bit coding); exact symbol counts are
+   * taken by k_dnacount in the rare Huffman-DNA case. */
+  u32 kept = 0, pres = 0, myL = 0;
   if (active && !err) {
-    u64 qm = 0; /* quality bytes 33..96 seen by this thread */
-    auto seen = [&](u8 q) {
-      u32 k = (u32)q - 33u;
-      if (k < 64u) qm |= 1ull << k;
-      else if (!((S.qp[q >> 5] >> (q & 31)) & 1u)) atomicOr(&S.qp[q >> 5], 1u << (q & 31));
-    };
     bool ok = true, nul = false;
     u32 namb = 0;
     const u8 *sp = b + te + 1, *qp = b + qs;
     for (u32 j = 0; j < L; ++j) {
       u8 c = sp[j], q = qp[j];
-      nul = nul || c == 0 || q == 0;
-      if (c == 'A') ++acgt0; else if (c == 'C') ++acgt1; else if (c == 'G') ++acgt2; else if (c == 'T') ++acgt3;
-      else { ++namb; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; continue; }
-      seen(q);
+      u32 f = dlut[c];
+      if (f) { pres |= f; S.qflag[q] = 1; }
+      else { ++namb; nul = nul || c == 0; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; }
     }
     const u32 xfer = (namb && ok) ? 1u : 0u;
     if (namb) {
       for (u32 j = 0; j < L; ++j) {
         u8 c = sp[j], q = qp[j];
-        if (is_acgt(c)) continue;
-        if (xfer) seen(xfer_qual(amb_code(c), q));
-        else { atomicAdd(&S.dna[c], 1u); seen(q); }
+        if (dlut[c]) continue;
+        if (xfer) S.qflag[xfer_qual(amb_code(c), q)] = 1;
+        else { atomicAdd(&S.dna[c], 1u); S.qflag[q] = 1; }
       }
     }
     if (nul) err = E_UNSUPPORTED;
     kept = xfer ? L - namb : L; myL = L;
     d.kx[r] = (u16)(kept | (xfer << 15));
-    /* bits 33..63 -> word 1 bits 1..31; 64..95 -> word 2; 96 -> word 3 bit 0 */
-    u32 w1 = (u32)(qm << 1), w2 = (u32)(qm >> 31), w3 = (u32)(qm >> 63);
-    if (w1 & ~S.qp[1]) atomicOr(&S.qp[1], w1);
-    if (w2 & ~S.qp[2]) atomicOr(&S.qp[2], w2);
-    if (w3 & ~S.qp[3]) atomicOr(&S.qp[3], w3);
   }
   {
-    u32 a0 = __reduce_add_sync(0xFFFFFFFFu, acgt0), a1 = __reduce_add_sync(0xFFFFFFFFu, acgt1);
-    u32 a2 = __reduce_add_sync(0xFFFFFFFFu, acgt2), a3 = __reduce_add_sync(0xFFFFFFFFu, acgt3);
+    u32 pr = __reduce_or_sync(0xFFFFFFFFu, pres);
     u32 mq = __reduce_max_sync(0xFFFFFFFFu, myL), ms = __reduce_max_sync(0xFFFFFFFFu, kept);
     if (lane == 0) {
-      if (a0) atomicAdd(&S.dna['A'], a0);
-      if (a1) atomicAdd(&S.dna['C'], a1);
-      if (a2) atomicAdd(&S.dna['G'], a2);
-      if (a3) atomicAdd(&S.dna['T'], a3);
+      if (pr & 1u) S.dna['A'] = 1;
+      if (pr & 2u) S.dna['C'] = 1;
+      if (pr & 4u) S.dna['G'] = 1;
+      if (pr & 8u) S.dna['T'] = 1;
       atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms);
     }
   }
@@ -456,7 +451,12 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     if (S.err) atomicMin(&A->status, S.err);
     atomicMax(&A->max_qlen, S.maxq); atomicMax(&A->max_slen, S.maxs);
   }
-  if (tid < 8 && S.qp[tid]) atomicOr(&A->qpresent[tid], S.qp[tid]);
+  if (tid < 8) {
+    u32 m = 0;
+    for (u32 k = 0; k < 32; ++k) m |= S.qflag[tid * 32 + k] ? 1u << k : 0u;
+    if (tid == 0 && (m & 1u)) atomicMin(&A->status, (i32)E_UNSUPPORTED); /* NUL quality byte */
+    if (m) atomicOr(&A->qpresent[tid], m);
+  }
   for (u32 i = tid; i < 256; i += CH) if (S.dna[i]) atomicAdd(&A->dna_occ[i], S.dna[i]);
   if (seed_ok)
     for (u32 i = tid; i < nf * 8; i += CH) {
@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(32) k_classify(Dev d) {
   u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
   classify_subblock(d.in, g_char_lut, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
   C.payload_len = 0;
+  if (!C.status) atomicMax(&d.hdr->max_qh_words, C.max_qlen * (C.nq | 1u));
 }
 
 __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
@@ -489,6 +490,30 @@ __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
   if (C.status) return;
   u32 *a = d.arena + (size_t)s * d.arena_words;
   for (u32 i = C.zero_begin + blockIdx.x * 256 + threadIdx.x; i < C.zero_end; i += gridDim.x * 256) a[i] = 0;
+}
+
+/* Exact DNA symbol counts (sym_stats, tasks.cpp:233-236), needed only when more than four symbols force
+ * Huffman-coded DNA; plain subblocks leave immediately. */
+__global__ void __launch_bounds__(256) k_dnacount(Dev d) {
+  __shared__ u32 h[256];
+  const u32 s = blockIdx.y;
+  const SbClass &C = d.cls[s];
+  if (C.status || C.plain) return;
+  const SbPlan P = d.plans[s];
+  for (u32 i = threadIdx.x; i < 256; i += 256) h[i] = 0;
+  __syncthreads();
+  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < C.R; i += gridDim.x * 256) {
+    u32 r = P.first_rec + i, te = d.te[r], se = d.se[r];
+    bool xfer = d.kx[r] >> 15;
+    for (u32 j = te + 1; j < se; ++j) {
+      u8 c = d.in[j];
+      if (xfer && !is_acgt(c)) continue;
+      atomicAdd(&h[C.sym_code[c]], 1u);
+    }
+  }
+  __syncthreads();
+  u32 *dst = d.arena + (size_t)s * d.arena_words + C.dnastat_off;
+  for (u32 i = threadIdx.x; i < C.nsym; i += 256) if (h[i]) atomicAdd(dst + i, h[i]);
 }
 
 /* ---- per-position quality histogram (tasks.cpp:260-286) ----------------------------------------------------- */
@@ -588,6 +613,15 @@ __device__ __forceinline__ void warp_hist_add(u32 *hist, u32 idx, bool on) {
   u32 key = on ? idx : 0xFFFFFFFFu;
   u32 m = __match_any_sync(0xFFFFFFFFu, key);
   if (on && (u32)(__ffs(m) - 1) == (threadIdx.x & 31)) atomicAdd(hist + idx, (u32)__popc(m));
+}
+
+/* Issues the asynchronous copy (cp.async, 16 bytes per request) of batch bytes [lo, hi) into `smem`; the caller
+ * commits / waits.  Returns false when the span does not fit. */
+__device__ __forceinline__ bool span_issue(const u8 *in, u32 lo, u32 hi, u8 *smem, u32 smem_bytes) {
+  u32 alo = lo & ~15u, n = hi - alo;
+  if (n > smem_bytes) return false;
+  for (u32 i = threadIdx.x * 16; i < n; i += blockDim.x * 16) __pipeline_memcpy_async(smem + i, in + alo + i, 16);
+  return true;
 }
 
 __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
@@ -724,7 +758,7 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
     const u32 kx = d.kx[r];
     const bool xfer = kx >> 15;
     CountSink q; q.init();
-    quality_record(b, te + 1, L, se + 3, xfer, codes, (const u64 *)(arena + td[C.tq0].cl_off), C.nq, q);
+    { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq; quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
     qbits = (u32)q.bits;
     if (C.plain) dbits = 2 * (kx & 0x7FFFu);
     else {
@@ -894,7 +928,7 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
     }
     {
       OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + arena[C.chunk_off + chunk] + d.qoff[r]);
-      quality_record(b, te + 1, L, se + 3, xfer, codes, (const u64 *)(arena + td[C.tq0].cl_off), C.nq, q);
+      { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq; quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
       q.finish();
     }
     {

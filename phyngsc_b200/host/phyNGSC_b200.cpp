@@ -147,7 +147,8 @@ int main(int argc, char **argv) {
   if (ndev < 1) die(rank, 3, "no CUDA device (this build has no CPU path)", nullptr);
   const char *lr = getenv("LOCAL_RANK");
   const int dev = (lr ? atoi(lr) : rank) % ndev; /* one rank per GPU; ranks wrap when there are fewer GPUs */
-  uint64_t batch = region_len + (1u << 20) < (3ull << 30) ? region_len + (1u << 20) : (1ull << 30) + (16u << 20);
+  /* regions beyond 320 MiB are processed in 256 MiB batches so that upload, kernels and download overlap */
+  uint64_t batch = region_len <= (320ull << 20) ? region_len + (1u << 20) : (256ull << 20);
   phy_ctx *ctx = nullptr;
   int rc = phy_ctx_create(&ctx, dev, batch, (uint32_t)(batch / (READ_BUFFER_SIZE / 2)) + 16);
   if (rc) die(rank, 3, "cannot create the GPU context", phy_strerror(rc));

@@ -85,6 +85,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
   if (!rc) {
     TableDesc *td = (TableDesc *)(arena + C->tabdesc_off);
     for (u32 i = C->zero_begin; i < C->zero_end; ++i) arena[i] = 0;
+    if (!C->plain) for (u32 i = 0; i < C->nsym; ++i) arena[C->dnastat_off + i] = A->dna_occ[C->symbols[i]];
     // qhist
     u32 *gq = arena + C->qstat_off;
     for (u32 r = 0; r < R; ++r) {
@@ -139,7 +140,8 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
     for (u32 r = 0; r < R; ++r) {
       u32 L = se[r] - te[r] - 1; bool xf = kx[r] >> 15;
       CountSink q; q.init();
-      quality_record(b, te[r] + 1, L, se[r] + 3, xf, C->qua_code, (const u64 *)(arena + td[C->tq0].cl_off), C->nq, q);
+      QFull qt; qt.cl = (const u64 *)(arena + td[C->tq0].cl_off); qt.nq = C->nq;
+      quality_record(b, te[r] + 1, L, se[r] + 3, xf, C->qua_code, qt, q);
       qoff[r] = (u32)q.bits;
       CountSink dn; dn.init();
       dna_record(b, te[r] + 1, L, xf, C->plain != 0, C->sym_code, C->plain ? (const u64 *)0 : (const u64 *)(arena + td[C->tdna].cl_off), dn);
@@ -168,6 +170,10 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
       finish_layout(*C, (u32)tb, qb, db);
       if (C->payload_len > out_cap) rc = E_CAPACITY;
     }
+    // the 16-bit packed copy of the quality tables the GPU keeps in shared memory
+    std::vector<u16> pk((size_t)(C->max_qlen + 1) * C->nq);
+    bool use_packed = true;
+    for (size_t i = 0; i < pk.size(); ++i) use_packed = qpack_entry(((const u64 *)(arena + td[C->tq0].cl_off))[i], pk[i]) && use_packed;
     if (!rc) {
       memset(out, 0, (C->payload_len + 7) & ~3u);
       u32 *outw = (u32 *)out;
@@ -182,7 +188,9 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
         u32 L = se[r] - te[r] - 1; bool xf = kx[r] >> 15;
         OrSink k; k.init(outw, (u64)INFO_FIXED * 8 + (u64)r * C->nb_len); k.put(L, C->nb_len); k.finish();
         OrSink q; q.init(outw, (u64)(o_qual + C->qhdr_len) * 8 + qoff[r]);
-        quality_record(b, te[r] + 1, L, se[r] + 3, xf, C->qua_code, (const u64 *)(arena + td[C->tq0].cl_off), C->nq, q); q.finish();
+        if (use_packed) { QPacked qp; qp.pk = pk.data(); qp.nq = C->nq; quality_record(b, te[r] + 1, L, se[r] + 3, xf, C->qua_code, qp, q); }
+        else { QFull qt; qt.cl = (const u64 *)(arena + td[C->tq0].cl_off); qt.nq = C->nq; quality_record(b, te[r] + 1, L, se[r] + 3, xf, C->qua_code, qt, q); }
+        q.finish();
         OrSink dn; dn.init(outw, (u64)(o_dna + C->dhdr_len) * 8 + doff[r]);
         dna_record(b, te[r] + 1, L, xf, C->plain != 0, C->sym_code, C->plain ? (const u64 *)0 : (const u64 *)(arena + td[C->tdna].cl_off), dn); dn.finish();
       }
