@@ -25,7 +25,7 @@ struct phy_ctx {
   u64 max_batch = 0; u32 max_sb = 0; u32 maxrec = 0; u32 arena_words = 0; u64 out_cap = 0; u32 slack = 0;
   u32 max_tiles = 0;
   /* device buffers */
-  u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr;
+  u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr, *chunk_first = nullptr, *chunk_last = nullptr;
   u32 *tile_cnt = nullptr, *tile_off = nullptr;
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
@@ -98,7 +98,7 @@ extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl};
@@ -140,6 +140,11 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaMalloc(&ctx->qoff, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->doff, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->toff, (size_t)(ctx->maxrec + 4) * 4));
+  {
+    size_t rows = (size_t)ctx->maxrec / CH + ctx->max_sb + 2; /* every subblock rounds its chunk count up */
+    CK(cudaMalloc(&ctx->chunk_first, rows * MAXF * 4));
+    CK(cudaMalloc(&ctx->chunk_last, rows * MAXF * 4));
+  }
   CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->plan_state, sizeof(PlanState)));
@@ -197,13 +202,17 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   memset(&d, 0, sizeof d);
   d.in = in; d.len = len; d.start_pos = start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
-  d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff;
+  d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff; d.chunk_first = ctx->chunk_first; d.chunk_last = ctx->chunk_last;
   d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
   d.out = out; d.out_cap = ctx->out_cap;
   d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
   d.span_bytes = 0;
+  static const int tune_env = getenv("PHY_TUNE") ? atoi(getenv("PHY_TUNE")) : -1;
+  u32 tune = tune_env >= 0 ? (u32)tune_env : 0u;
+  static const u32 qh_smem = getenv("PHY_QH_KB") ? (u32)atoi(getenv("PHY_QH_KB")) * 1024u : QH_SMEM;
+  d.tune = tune; d.qh_bytes = qh_smem;
   cudaStream_t st = ctx->stream;
   ctx->last_S = 0;
   if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
@@ -242,23 +251,25 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
+  if (tune_env < 0 && H.max_span / CH > 200) d.tune |= 1u; /* records beyond ~200 B: stat2 reads its few title tokens directly */
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
   dim3 gc(H.max_chunks, S);
   PMARK();
-  k_stat1<<<gc, CH, span_v, st>>>(d); PMARK();
+  k_stat1<<<gc, CH, span_v, st>>>(d);
+  k_xdelta<<<S, 128, 0, st>>>(d); PMARK();
   k_classify<<<S, 32, 0, st>>>(d); PMARK();
   k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d);
   k_dnacount<<<dim3(16, S), 256, 0, st>>>(d); PMARK();
-  k_qhist<<<dim3(H.max_qchunks, S), 256, QH_SMEM, st>>>(d); PMARK();
-  k_stat2<<<gc, CH, span_v, st>>>(d); PMARK();
+  k_qhist<<<dim3(H.max_qchunks, S), 256, d.qh_bytes, st>>>(d); PMARK();
+  k_stat2<<<gc, CH, (d.tune & 1u) ? d.max_nf * CH * 4 : span_v, st>>>(d); PMARK();
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
   k_lengths<<<gc, CH, span, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
   k_emit<<<gc, CH, span, st>>>(d); PMARK();
-  ctx->launches += 12;
+  ctx->launches += 13;
   CK(cudaGetLastError());
   if (ctx->profile) {
     CK(cudaStreamSynchronize(st));

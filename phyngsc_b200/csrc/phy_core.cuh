@@ -220,7 +220,7 @@ struct SbClass {
   u32 max_qlen, max_slen, nsym, nq, plain, flags, nb_len;
   u32 ts0, te0;                /* title line of record 0 (batch-relative positions)                   */
   /* arena layout (word offsets unless stated) */
-  u32 ntab, tabdesc_off, tq0, tdna, qstat_off, dnastat_off, zero_begin, zero_end;
+  u32 ntab, tabdesc_off, tq0, tdna, tchr0, qstat_off, dnastat_off, zero_begin, zero_end;
   u32 qpk_off, qpk_bad;        /* quality tables packed to 16 bits (len << 12 | code); qpk_bad != 0 when a code is longer than 12 bits */
   u32 nblk, flagbits_off;
   u32 blkloc_off;              /* per 32-record title block: byte offset inside its chunk */
@@ -520,6 +520,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
     }
   }
   u32 slot = 0;
+  C.tchr0 = tid; /* char tables are numbered consecutively from here */
   for (u32 f = 0; f < nf; ++f) {
     FieldClass &F = C.f[f];
     if (F.kind != K_STR) continue;

@@ -33,7 +33,7 @@ namespace phy {
 constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
 constexpr int TILE = 16384;        /* bytes per newline-index tile                                         */
 constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
-constexpr u32 QH_SMEM = 64 * 1024; /* private histogram rows of one quality-histogram CTA                  */
+constexpr u32 QH_SMEM = 44 * 1024; /* private histogram rows of one quality-histogram CTA                  */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
@@ -59,6 +59,7 @@ struct Dev {
   u32 start_pos;              /* first record start inside the batch                           */
   u32 *te, *se, *rstart; u32 maxrec;
   u16 *kx; u32 *qoff, *doff, *toff;
+  u32 *chunk_first, *chunk_last; /* numeric token values of the first / last record of every 128-record chunk, [chunk][MAXF] */
   u32 *tile_cnt, *tile_off; u32 ntiles;
   PlanState *plan_state; SbPlan *plans; u32 max_sb;
   BatchHdr *hdr;
@@ -69,6 +70,7 @@ struct Dev {
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
   u32 qh_bytes;               /* shared memory for the private quality-histogram copies         */
+  u32 tune;                   /* experiment switches (PHY_TUNE): bit0 = stat2 reads titles straight from global memory */
 };
 
 /* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
   if (H->status || st.done || st.status) { if (lane == 0) { H->S = 0; H->next_pos = (u64)st.bytes_read; } return; }
   const u32 NR = H->NR, NL = H->NL;
   u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0, max_qchunks = 0;
-  i64 avg = 128;
+  i64 avg_n = 1, avg_b = 128;
   while (!st.done && S < d.max_sb) {
     i64 ws = st.bytes_read - d.batch_base; /* batch-relative window start */
     if (!d.batch_is_final && ws + st.rsize + (i64)d.slack > (i64)d.len) break;
@@ -226,26 +228,45 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     P.first_rec = F; P.n_records = 0; P.warnings = 0; P.status = 0; P.bytes_consumed = 0; P.chunk_base = chunk_base; P.pad = 0;
     if (F >= NR) { st.status = E_MALFORMED; break; }
     i64 target = ws + st.rsize - st.overlap, size_lim = ws + lim;
-    u32 last = F;
+    u32 last = F, rs_next = 0xFFFFFFFFu; /* rs_next: rstart[last + 1] when the probe already holds it */
     bool capped = false;
-    if (4ull * (F + 1) < NL && (i64)d.te[F + 1] < size_lim) {
-      i64 guess = (i64)F + (target - (ws + st.rec_start)) / avg;
-      u32 m = warp_lower_bound(d.rstart, F + 2, NR + 1, target, guess);
+    /* One round trip in the common case: the title newline of the second record, and a 32-wide probe of the
+     * record table around the interpolated position of the last record, are loaded together. */
+    const i64 guess = (i64)F + (target - (ws + st.rec_start)) * avg_n / avg_b; /* records-per-byte of the previous window */
+    u32 pbase;
+    { i64 gb = guess - 16; pbase = gb < (i64)F + 2 ? F + 2 : (u32)gb; }
+    const u32 pidx = pbase + lane;
+    const u32 te_f1 = 4ull * (F + 1) < NL ? d.te[F + 1] : 0xFFFFFFFFu;
+    const u32 prs = pidx <= NR ? d.rstart[pidx] : 0xFFFFFFFFu;
+    const u32 pte = pidx >= 1 && 4ull * (pidx - 1) < NL ? d.te[pidx - 1] : 0xFFFFFFFFu; /* title newline of record pidx-1 */
+    if ((i64)te_f1 < size_lim) {
+      u32 m;
+      u32 bal = __ballot_sync(0xFFFFFFFFu, (i64)prs >= target);
+      u32 k = bal ? __ffs(bal) - 1 : 32;
+      bool hit = bal != 0 && (k > 0 || pbase == F + 2) && pbase + k <= NR;
+      u32 te_last = 0xFFFFFFFFu;
+      if (hit) { m = pbase + k; te_last = __shfl_sync(0xFFFFFFFFu, pte, k); rs_next = __shfl_sync(0xFFFFFFFFu, prs, k); }
+      else m = warp_lower_bound(d.rstart, F + 2, NR + 1, target, guess);
       last = m - 1;
-      if (last > F + st.record_cap) { last = F + st.record_cap; capped = true; }
-      while (last > F && !(4ull * last < NL && (i64)d.te[last] < size_lim)) { --last; capped = false; }
+      if (last > F + st.record_cap) { last = F + st.record_cap; capped = true; te_last = 0xFFFFFFFFu; rs_next = 0xFFFFFFFFu; }
+      if (te_last == 0xFFFFFFFFu && 4ull * last < NL) te_last = d.te[last];
+      while (last > F && !(4ull * last < NL && (i64)te_last < size_lim)) {
+        --last; capped = false; rs_next = 0xFFFFFFFFu;
+        te_last = 4ull * last < NL ? d.te[last] : 0xFFFFFFFFu;
+      }
       if (last >= NR) { st.status = E_MALFORMED; break; }
     }
     P.n_records = last - F + 1;
     P.warnings = capped ? 1u : 0u;
-    P.bytes_consumed = (u64)((i64)d.rstart[last + 1] - ws);
+    if (rs_next == 0xFFFFFFFFu) rs_next = d.rstart[last + 1];
+    P.bytes_consumed = (u64)((i64)rs_next - ws);
     if (lane == 0) d.plans[S] = P;
     __syncwarp();
     u32 nch = (P.n_records + CH - 1) / CH;
     chunk_base += nch;
     max_chunks = max(max_chunks, nch);
     max_qchunks = max(max_qchunks, (P.n_records + QCH - 1) / QCH);
-    avg = max((i64)16, (i64)(P.bytes_consumed / P.n_records));
+    avg_n = (i64)P.n_records; avg_b = max((i64)1, (i64)P.bytes_consumed);
     ++S; F = last + 1;
     /* phyNGSC.cpp:745-755 */
     st.bytes_read += (i64)P.bytes_consumed;
@@ -272,7 +293,7 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
   u32 mx = 0;
   for (u32 c = threadIdx.x; c * CH < P.n_records; c += 256) {
     u32 r0 = P.first_rec + c * CH, nrec = min((u32)CH, P.n_records - c * CH);
-    u32 lo = d.rstart[r0 - (c > 0 ? 1 : 0)] & ~15u;
+    u32 lo = d.rstart[r0] & ~15u;
     mx = max(mx, d.rstart[r0 + nrec] - lo);
   }
   mx = __reduce_max_sync(0xFFFFFFFFu, mx);
@@ -319,7 +340,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   if (P.status || chunk * CH >= P.n_records) return;
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
   for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
-  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   __shared__ u8 lut[256], dlut[256];
   load_lut(lut);
   for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'G' ? 4 : i == 'T' ? 8 : 0);
@@ -427,17 +448,17 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     }
   }
   if (walk && (!fields_ok || cur.pos <= cur.lim)) err = E_FIELDS; /* fewer or more separators than record 0 */
-  /* the record before this chunk, for the first delta */
-  if (tid == 0 && chunk > 0 && seed_ok) {
-    u32 pts = d.rstart[r0 - 1], pte = d.te[r0 - 1];
-    TitleCursor pc; pc.init(b, pts, pte, lut);
-    Tok t;
-    for (u32 f = 0; f < nf; ++f) { if (!pc.next(t)) break; S.pvals0[f] = t.v; }
-  }
   __syncthreads();
+  /* deltas inside the chunk; the delta across the chunk boundary is folded in by k_xdelta from the values of
+   * the chunk's first / last record, so that no thread has to parse the neighbouring chunk's record */
+  if (seed_ok && tid < nf) {
+    const size_t row = ((size_t)P.chunk_base + chunk) * MAXF + tid;
+    d.chunk_first[row] = vals[tid * CH];
+    d.chunk_last[row] = vals[tid * CH + nrec - 1];
+  }
   for (u32 f = 0; f < nf && seed_ok; ++f) {
-    const bool hasd = walk && r > P.first_rec;
-    u32 pv = tid > 0 ? vals[f * CH + tid - 1] : S.pvals0[f];
+    const bool hasd = walk && tid > 0;
+    u32 pv = tid > 0 ? vals[f * CH + tid - 1] : 0u;
     u32 kd = key_of((i32)(vals[f * CH + tid] - pv));
     u32 kmax = __reduce_max_sync(0xFFFFFFFFu, hasd ? kd : 0u);
     u32 kinv = __reduce_max_sync(0xFFFFFFFFu, hasd ? ~kd : 0u);
@@ -469,6 +490,28 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       u32 f = i / MASKW, k = i % MASKW, v = S.mism[f][k];
       if (v) atomicOr(&A->f[f].mism[k], v);
     }
+}
+
+/* min / max of the numeric deltas that cross a chunk boundary (tasks.cpp:149-166 runs over all records) */
+__global__ void __launch_bounds__(128) k_xdelta(Dev d) {
+  __shared__ u32 mx[MAXF], mn[MAXF], nf_s;
+  const u32 s = blockIdx.x, tid = threadIdx.x;
+  const SbPlan P = d.plans[s];
+  SbAcc *A = d.acc + s;
+  if (P.status || A->status) return;
+  const u32 nchunk = (P.n_records + CH - 1) / CH;
+  if (tid < MAXF) { mx[tid] = 0; mn[tid] = 0; }
+  if (tid == 0) nf_s = min((u32)MAXF, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
+  __syncthreads();
+  const u32 nf = nf_s;
+  for (u32 i = tid; i < (nchunk - 1) * nf; i += 128) {
+    u32 c = 1 + i / nf, f = i % nf;
+    u32 a = d.chunk_first[((size_t)P.chunk_base + c) * MAXF + f], b = d.chunk_last[((size_t)P.chunk_base + c - 1) * MAXF + f];
+    u32 kd = key_of((i32)(a - b));
+    atomicMax(&mx[f], kd); atomicMax(&mn[f], ~kd);
+  }
+  __syncthreads();
+  if (tid < nf) { if (mx[tid]) atomicMax(&A->f[tid].kmax_d, mx[tid]); if (mn[tid]) atomicMax(&A->f[tid].kinvmin_d, mn[tid]); }
 }
 
 /* ---- classify + zero ------------------------------------------------------------------------------------- */
@@ -539,7 +582,7 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   }
   u32 *hist = (u32 *)dyn_smem;
   u32 slots = Lp <= 256 ? 256 / Lp : 1;
-  u32 fit = QH_SMEM / (Lp * stride * 4);
+  u32 fit = d.qh_bytes / (Lp * stride * 4);
   if (slots > fit) slots = fit;
   if (slots == 0) { /* rows do not fit in shared memory: count straight into the global table */
     __syncthreads();
@@ -624,6 +667,8 @@ __device__ __forceinline__ bool span_issue(const u8 *in, u32 lo, u32 hi, u8 *sme
   return true;
 }
 
+constexpr int CSLOTS = 8; /* per-position char tables whose histogram a CTA keeps in shared memory */
+
 __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ FieldClass fc[MAXF];
@@ -636,12 +681,19 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
-  const u32 lo = d.rstart[r0 - (chunk > 0 ? 1 : 0)], hi = d.rstart[r0 + nrec];
+  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   __shared__ u8 lut[256];
   load_lut(lut);
-  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
+  /* only the few non-constant tokens of each title are touched: with long records it is cheaper to read them
+   * straight from global memory (L1) than to stage whole records */
+  const bool direct = d.tune & 1u; /* chosen per batch by the host: long records -> direct, short records -> staged span */
+  const u8 *b = direct ? d.in : stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) return; /* cannot happen: stat1 staged the same span */
-  u32 *vals = vals_area(dyn_smem, d.span_bytes);
+  u32 *vals = direct ? (u32 *)dyn_smem : vals_area(dyn_smem, d.span_bytes);
+  /* char histograms of the first CSLOTS per-position tables are privatised in shared memory */
+  __shared__ u32 chist[CSLOTS * 256];
+  const u32 ncs = min(C.ntab - C.tchr0, (u32)CSLOTS);
+  for (u32 i = tid; i < ncs * 256; i += CH) chist[i] = 0;
   load_field_classes(C, fc);
   __syncthreads();
   const bool active = tid < nrec;
@@ -667,17 +719,18 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
       const u16 *sm = (const u16 *)(arena + F.slotmap_off);
       for (u32 j = 0; j < len; ++j)
         if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
-          u32 tab = sm[j < 128 ? j : 128];
-          atomicAdd(arena + td[tab].freq_off + a[j], 1u);
+          /* lanes of the warp that are at the same character of the same table add once, together */
+          u32 tab = sm[j < 128 ? j : 128], loc = tab - C.tchr0, ch = a[j];
+          u32 grp = __match_any_sync(__activemask(), (tab << 8) | ch);
+          if ((u32)(__ffs(grp) - 1) == lane) {
+            if (loc < ncs) atomicAdd(&chist[loc * 256 + ch], (u32)__popc(grp));
+            else atomicAdd(arena + td[tab].freq_off + ch, (u32)__popc(grp));
+          }
         }
     }
     if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
   }
-  if (tid == 0 && chunk > 0) {
-    TitleCursor c; c.init(b, d.rstart[r0 - 1], d.te[r0 - 1], lut);
-    Tok t;
-    for (u32 f = 0; f < nf; ++f) { if (!c.next(t)) break; pvals0[f] = t.v; }
-  }
+  if (tid < nf && chunk > 0) pvals0[tid] = d.chunk_last[((size_t)P.chunk_base + chunk - 1) * MAXF + tid]; /* record before the chunk */
   __syncthreads();
   for (u32 f = 0; f < nf; ++f) {
     const FieldClass &F = fc[f];
@@ -705,6 +758,11 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
     if (pred) flags |= 1u << f;
   }
   if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (chunk * CH + wbase) / 32] = flags;
+  __syncthreads();
+  for (u32 i = tid; i < ncs * 256; i += CH) {
+    u32 v = chist[i];
+    if (v) atomicAdd(arena + td[C.tchr0 + (i >> 8)].freq_off + (i & 255u), v);
+  }
 }
 
 /* ---- Huffman build: one warp per table ------------------------------------------------------------------------- */
