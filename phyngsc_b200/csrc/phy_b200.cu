@@ -251,7 +251,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
-  if (tune_env < 0 && H.max_span / CH > 200) d.tune |= 1u; /* records beyond ~200 B: stat2 reads its few title tokens directly */
+  if ((tune_env < 0 || (tune_env & 8)) && H.max_span / CH > 200) d.tune |= 1u; /* records beyond ~200 B: stat2 reads its few title tokens directly */
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
   dim3 gc(H.max_chunks, S);

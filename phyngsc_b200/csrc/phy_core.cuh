@@ -198,6 +198,7 @@ struct FieldAcc {
 struct SbAcc {
   i32 status; u32 warnings;
   u32 max_qlen, max_slen;
+  u32 inv_min_qlen, pad0; /* ~(shortest read) */
   u32 qpresent[8];
   u32 dna_occ[256];  /* non-zero = symbol occurs in the (compacted) DNA; exact counts are taken later, only if needed */
   FieldAcc f[MAXF];
@@ -218,6 +219,7 @@ struct TableDesc { u32 n, freq_off, cl_off, tree_off, tree_len, dst; };
 struct SbClass {
   i32 status; u32 R, nf, P, nnc;
   u32 max_qlen, max_slen, nsym, nq, plain, flags, nb_len;
+  u32 varlen;                  /* reads differ in length (picks the walker variant on the GPU; not part of the format) */
   u32 ts0, te0;                /* title line of record 0 (batch-relative positions)                   */
   /* arena layout (word offsets unless stated) */
   u32 ntab, tabdesc_off, tq0, tdna, tchr0, qstat_off, dnastat_off, zero_begin, zero_end;
@@ -375,6 +377,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   C.plain = nsym <= 4 ? 1u : 0u;                      /* tasks.cpp:239-256 (frequency test is dead code) */
   C.flags = 0x8u | 0x4u | 0x20u | 0x80u | (C.plain ? 0x2u : 0u); /* 0xAE / 0xAC */
   C.max_qlen = A.max_qlen; C.max_slen = A.max_slen;
+  C.varlen = (~A.inv_min_qlen != A.max_qlen) ? 1u : 0u;
   C.nb_len = bit_length_u32(C.max_qlen);
   if (C.nb_len > 32) { C.status = E_UNSUPPORTED; return; }
   C.info_len = INFO_FIXED + (u32)(((u64)R * C.nb_len + 7) / 8);
@@ -593,9 +596,44 @@ PHY_HD bool qpack_entry(u64 e, u16 &out) {
   return true;
 }
 
-/* Quality codes of one record: position k uses table k+1 (tasks.cpp:609-619). */
+/* Quality codes of one record: position k uses table k+1 (tasks.cpp:609-619).  The table entries of the next
+ * three positions are already in flight while one is appended (software pipeline of depth 3), because the
+ * lookup chain byte -> symbol code -> table entry is what a thread otherwise waits for. */
 template <class Sink, class Q>
 PHY_HD void quality_record(const u8 *b, u32 ss, u32 L, u32 qs, bool xfer, const u8 *qua_code, const Q &tab, Sink &s) {
+  const u8 *qp = b + qs, *sp = b + ss;
+  if (xfer) {
+    for (u32 j = 0; j < L; ++j) {
+      u8 q = qp[j];
+      u32 a = amb_code(sp[j]);
+      if (a > 1) q = xfer_qual(a, q);
+      u32 code, len;
+      tab.get(j + 1, qua_code[q], code, len);
+      s.put(code, len);
+    }
+    return;
+  }
+  u32 c0 = 0, l0 = 0, c1 = 0, l1 = 0, c2 = 0, l2 = 0;
+  if (0 < L) tab.get(1, qua_code[qp[0]], c0, l0);
+  if (1 < L) tab.get(2, qua_code[qp[1]], c1, l1);
+  if (2 < L) tab.get(3, qua_code[qp[2]], c2, l2);
+  u32 j = 0;
+  for (; j + 3 <= L; j += 3) {
+    u32 n0 = 0, m0 = 0, n1 = 0, m1 = 0, n2 = 0, m2 = 0;
+    if (j + 3 < L) tab.get(j + 4, qua_code[qp[j + 3]], n0, m0);
+    s.put(c0, l0);
+    if (j + 4 < L) tab.get(j + 5, qua_code[qp[j + 4]], n1, m1);
+    s.put(c1, l1);
+    if (j + 5 < L) tab.get(j + 6, qua_code[qp[j + 5]], n2, m2);
+    s.put(c2, l2);
+    c0 = n0; l0 = m0; c1 = n1; l1 = m1; c2 = n2; l2 = m2;
+  }
+  if (j < L) s.put(c0, l0);
+  if (j + 1 < L) s.put(c1, l1);
+}
+
+template <class Sink, class Q>
+PHY_HD void quality_record_simple(const u8 *b, u32 ss, u32 L, u32 qs, bool xfer, const u8 *qua_code, const Q &tab, Sink &s) {
   const u8 *qp = b + qs, *sp = b + ss;
   for (u32 j = 0; j < L; ++j) {
     u8 q = qp[j];

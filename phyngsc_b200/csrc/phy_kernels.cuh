@@ -323,7 +323,7 @@ struct Stat1S {
   u32 mism[MAXF][MASKW];
   u32 dna[256];
   u32 qp[8];
-  u32 maxq, maxs;
+  u32 maxq, maxs, inv_minq;
   i32 err;
   u32 nf, ts0, te0;
   u32 off0[MAXF], len0[MAXF];
@@ -344,12 +344,16 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   __shared__ u8 lut[256], dlut[256];
   load_lut(lut);
   for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'G' ? 4 : i == 'T' ? 8 : 0);
+  /* this thread's record (loaded before the span is staged so that the latencies overlap) */
+  const bool active = tid < nrec;
+  const u32 r = r0 + (active ? tid : 0);
+  const u32 ts = d.rstart[r], te = d.te[r], se = d.se[r], nx = d.rstart[r + 1];
+  const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) { if (tid == 0) atomicMin(&d.acc[s].status, (i32)E_UNSUPPORTED); return; }
   u32 *vals = vals_area(dyn_smem, d.span_bytes); /* vals[f * CH + tid] */
   __syncthreads();
   /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
-  const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
   const bool r0_ok = te0 - ts0 + 1 <= R0_MAX;
   if (r0_ok) for (u32 i = tid; i <= te0 - ts0; i += CH) S.r0[i] = d.in[ts0 + i];
   __syncthreads();
@@ -367,9 +371,6 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   __syncthreads();
   const u32 nf = S.nf;
   const bool seed_ok = S.err == 0;
-  const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : 0);
-  const u32 ts = d.rstart[r], te = d.te[r], se = d.se[r], nx = d.rstart[r + 1];
   const u32 L = se - te - 1, qs = se + 3;
   i32 err = 0;
   if (active) {
@@ -410,12 +411,13 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   {
     u32 pr = __reduce_or_sync(0xFFFFFFFFu, pres);
     u32 mq = __reduce_max_sync(0xFFFFFFFFu, myL), ms = __reduce_max_sync(0xFFFFFFFFu, kept);
+    u32 iq = __reduce_max_sync(0xFFFFFFFFu, myL ? ~myL : 0u);
     if (lane == 0) {
       if (pr & 1u) S.dna['A'] = 1;
       if (pr & 2u) S.dna['C'] = 1;
       if (pr & 4u) S.dna['G'] = 1;
       if (pr & 8u) S.dna['T'] = 1;
-      atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms);
+      atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms); atomicMax(&S.inv_minq, iq);
     }
   }
   /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way */
@@ -431,8 +433,12 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       len = t.end - t.start;
       const u32 len0 = S.len0[f], m = len < len0 ? len : len0;
       const u8 *d0 = S.r0 + S.off0[f], *dp = b + t.start;
-      for (u32 p = 0; p < m; ++p)
-        if (dp[p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
+      /* most tokens equal record 0's: find out with a branch-free pass, mark positions only when something differs */
+      u32 diff = 0;
+      for (u32 p = 0; p < m; ++p) diff |= (u32)(dp[p] ^ d0[p]);
+      if (diff)
+        for (u32 p = 0; p < m; ++p)
+          if (dp[p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
     }
     vals[f * CH + tid] = t.v;
     u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   SbAcc *A = d.acc + s;
   if (tid == 0) {
     if (S.err) atomicMin(&A->status, S.err);
-    atomicMax(&A->max_qlen, S.maxq); atomicMax(&A->max_slen, S.maxs);
+    atomicMax(&A->max_qlen, S.maxq); atomicMax(&A->max_slen, S.maxs); atomicMax(&A->inv_min_qlen, S.inv_minq);
   }
   if (tid < 8) {
     u32 m = 0;
@@ -804,19 +810,21 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   __shared__ u8 lut[256];
   load_lut(lut);
+  const bool active = tid < nrec;
+  const u32 r = r0 + (active ? tid : nrec - 1); /* idle lanes shadow the chunk's last record so that warps stay converged */
+  const u32 te = d.te[r], se = d.se[r], L = se - te - 1, rs_r = d.rstart[r];
+  const u32 kx = d.kx[r];
+  const u32 myflags = C.nnc ? arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32] : 0u;
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_field_classes(C, fc);
   __syncthreads();
-  const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : nrec - 1); /* idle lanes shadow the chunk's last record so that warps stay converged */
-  const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
   u32 qbits = 0, dbits = 0;
   if (active) {
-    const u32 kx = d.kx[r];
     const bool xfer = kx >> 15;
     CountSink q; q.init();
-    { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq; quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
+    { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq;
+      if (!C.varlen) quality_record_simple(b, te + 1, L, se + 3, xfer, codes, t, q); else quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
     qbits = (u32)q.bits;
     if (C.plain) dbits = 2 * (kx & 0x7FFFu);
     else {
@@ -833,7 +841,7 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   if (C.nnc) {
     __syncwarp();
     CountSink t; t.init();
-    title_record(b, lut, d.rstart[r], te, C, fc, arena, arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32], lane == 0, PrevShfl(), t);
+    title_record(b, lut, rs_r, te, C, fc, arena, myflags, lane == 0, PrevShfl(), t);
     u32 tb = active ? (u32)t.bits : 0u, x = tb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
@@ -952,6 +960,14 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   __shared__ u8 lut[256];
   load_lut(lut);
+  const bool active = tid < nrec;
+  const u32 i_sb = chunk * CH + (active ? tid : nrec - 1); /* record index inside the subblock (idle lanes shadow the last) */
+  const u32 r = P.first_rec + i_sb;
+  const u32 te = d.te[r], se = d.se[r], L = se - te - 1, rs_r = d.rstart[r];
+  const u32 kx = d.kx[r], my_qoff = d.qoff[r], my_doff = d.doff[r], my_toff = C.nnc ? d.toff[r] : 0u;
+  const u32 cq = arena[C.chunk_off + chunk], cd = arena[C.chunk_off + C.nchunk + chunk];
+  const u32 flags = C.nnc ? arena[C.flagbits_off + i_sb / 32] : 0u;
+  const u32 tblk = C.nnc ? arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w] : 0u;
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_field_classes(C, fc);
@@ -973,24 +989,20 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
     for (u32 i = tid; i < C.qhdr_len; i += CH) or_byte(out, o_qual + i, stage[C.thdr_cap + i]);
     for (u32 i = tid; i < C.dhdr_len; i += CH) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
   }
-  const bool active = tid < nrec;
-  const u32 i_sb = chunk * CH + (active ? tid : nrec - 1); /* record index inside the subblock (idle lanes shadow the last) */
-  const u32 r = P.first_rec + i_sb;
-  const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
   if (active) {
-    const u32 kx = d.kx[r];
     const bool xfer = kx >> 15;
     { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
       OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * C.nb_len);
       k.put(L, C.nb_len); k.finish();
     }
     {
-      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + arena[C.chunk_off + chunk] + d.qoff[r]);
-      { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq; quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
+      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + cq + my_qoff);
+      { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq;
+        if (!C.varlen) quality_record_simple(b, te + 1, L, se + 3, xfer, codes, t, q); else quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
       q.finish();
     }
     {
-      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + arena[C.chunk_off + C.nchunk + chunk] + d.doff[r]);
+      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + cd + my_doff);
       dna_record(b, te + 1, L, xfer, C.plain != 0, codes + 256, C.plain ? (const u64 *)nullptr : (const u64 *)(arena + td[C.tdna].cl_off), dn);
       dn.finish();
     }
@@ -998,15 +1010,14 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   if (C.nnc) {
     /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509); all 32 lanes walk together */
     __syncwarp();
-    const u32 flags = arena[C.flagbits_off + i_sb / 32];
-    const u64 blk_byte = obase + o_title + C.thdr_len + arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w];
-    OrSink t; t.init(outw, blk_byte * 8 + (lane == 0 ? 0u : C.nnc + d.toff[r]), active);
+    const u64 blk_byte = obase + o_title + C.thdr_len + tblk;
+    OrSink t; t.init(outw, blk_byte * 8 + (lane == 0 ? 0u : C.nnc + my_toff), active);
     if (lane == 0) {
       u32 v = 0;
       for (u32 f = 0; f < C.nf; ++f) if (fc[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
       t.put(v, C.nnc);
     }
-    title_record(b, lut, d.rstart[r], te, C, fc, arena, flags, lane == 0, PrevShfl(), t);
+    title_record(b, lut, rs_r, te, C, fc, arena, flags, lane == 0, PrevShfl(), t);
     t.finish();
   }
 }

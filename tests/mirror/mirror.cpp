@@ -60,7 +60,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
     if (st.err) return E_UNSUPPORTED;
     A->dna_occ['A'] += st.acgt[0]; A->dna_occ['C'] += st.acgt[1]; A->dna_occ['G'] += st.acgt[2]; A->dna_occ['T'] += st.acgt[3];
     kx[r] = (u16)(st.kept | (st.xfer << 15));
-    amax(A->max_qlen, L); amax(A->max_slen, st.kept);
+    amax(A->max_qlen, L); amax(A->max_slen, st.kept); amax(A->inv_min_qlen, ~L);
     if (count_seps(b, rstart[r], te[r]) != nf) return E_FIELDS;
     TitleCursor cur; cur.init(b, rstart[r], te[r], lut);
     for (u32 f = 0; f < nf; ++f) {
