@@ -21,6 +21,7 @@ static_assert(sizeof(phy_subblock_desc) == 72, "phy_subblock_desc layout is part
 struct phy_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_rb = nullptr; cudaEvent_t ev_cls = nullptr; BatchHdr *h_hdr2 = nullptr; /* mid-pipeline header readback, overlapped with the statistics kernels */
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   u64 max_batch = 0; u32 max_sb = 0; u32 maxrec = 0; u32 arena_words = 0; u64 out_cap = 0; u32 slack = 0;
   u32 max_tiles = 0;
@@ -60,6 +61,7 @@ struct phy_ctx {
   } while (0)
 
 static const u32 SPAN_MAX = 96 * 1024;
+static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
 static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "classify", "zero_hist", "qhist",
                                           "stat2", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
@@ -112,6 +114,9 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->pev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->s_rb) cudaStreamDestroy(ctx->s_rb);
+  if (ctx->ev_cls) cudaEventDestroy(ctx->ev_cls);
+  if (ctx->h_hdr2) cudaFreeHost(ctx->h_hdr2);
   delete ctx;
 }
 
@@ -130,6 +135,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   ctx->slack = 64 * 1024;
   ctx->max_tiles = (u32)((ctx->max_batch + TILE - 1) / TILE) + 1;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->s_rb, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_cls, cudaEventDisableTiming));
+  CK(cudaHostAlloc(&ctx->h_hdr2, sizeof(BatchHdr), cudaHostAllocDefault));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   CK(cudaMalloc(&ctx->in, ctx->max_batch + 4096));
   CK(cudaMemset(ctx->in, 0, ctx->max_batch + 4096));
@@ -163,12 +171,14 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
     u8 lut[256];
     fill_char_lut(lut);
     CK(cudaMemcpyToSymbol(g_char_lut, lut, sizeof lut));
+    for (u32 c = 0; c < 256; ++c) { u32 a = amb_code((u8)c); lut[c] = a > 1 ? (u8)(79u + 8u * a) : (u8)0; }
+    CK(cudaMemcpyToSymbol(g_xq_lut, lut, sizeof lut));
   }
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_SMEM));
-  CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
-  CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
+  CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
   return PHY_OK;
 }
@@ -259,16 +269,26 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   k_stat1<<<gc, CH, span_v, st>>>(d);
   k_xdelta<<<S, 128, 0, st>>>(d); PMARK();
   k_classify<<<S, 32, 0, st>>>(d); PMARK();
+  /* the batch header now holds the exact size of the packed quality tables: fetch it on a side stream while the
+   * statistics kernels run, so that the encoder kernels get exactly the shared memory they need */
+  CK(cudaEventRecord(ctx->ev_cls, st));
+  CK(cudaStreamWaitEvent(ctx->s_rb, ctx->ev_cls, 0));
+  CK(cudaMemcpyAsync(ctx->h_hdr2, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, ctx->s_rb));
   k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d);
   k_dnacount<<<dim3(16, S), 256, 0, st>>>(d); PMARK();
   k_qhist<<<dim3(H.max_qchunks, S), 256, d.qh_bytes, st>>>(d); PMARK();
   k_stat2<<<gc, CH, (d.tune & 1u) ? d.max_nf * CH * 4 : span_v, st>>>(d); PMARK();
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
-  k_lengths<<<gc, CH, span, st>>>(d); PMARK();
+  CK(cudaStreamSynchronize(ctx->s_rb));
+  {
+    u32 pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;
+    d.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
+  }
+  k_lengths<<<gc, CH, span + d.pk_bytes, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
-  k_emit<<<gc, CH, span, st>>>(d); PMARK();
+  k_emit<<<gc, CH, span + d.pk_bytes, st>>>(d); PMARK();
   ctx->launches += 13;
   CK(cudaGetLastError());
   if (ctx->profile) {

@@ -448,7 +448,8 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   u32 dnastat_off = al.take(nsym); /* exact symbol counts, only filled (by a later pass) when the DNA is Huffman coded */
   C.dnastat_off = dnastat_off;
   C.zero_end = al.used;
-  C.qpk_off = al.take(((C.max_qlen + 1) * nq + 1) / 2);
+  while (al.used & 3u) al.take(1); /* 16-byte alignment: the packed tables are copied to shared memory as vectors */
+  C.qpk_off = al.take(((C.max_qlen + 1) * nq + 1) / 2 + 4);
   C.qpk_bad = 0;
   /* table directory: quality (max_qlen+1), dna (0/1), numeric, char */
   u32 ntab = (C.max_qlen + 1) + (C.plain ? 0 : 1) + ntab_num + ntab_chr;

@@ -47,7 +47,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_qchunks;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
   u32 max_qh_words;    /* max over subblocks of max_qlen * (n_qualities | 1): one private histogram copy */
-  u32 pad;
+  u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
 };
 
 struct SbOut {         /* device -> host, one per subblock */
@@ -70,6 +70,7 @@ struct Dev {
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
   u32 qh_bytes;               /* shared memory for the private quality-histogram copies         */
+  u32 pk_bytes;               /* shared memory behind the span for the packed quality code tables */
   u32 tune;                   /* experiment switches (PHY_TUNE): bit0 = stat2 reads titles straight from global memory */
 };
 
@@ -77,6 +78,12 @@ struct Dev {
 __device__ u8 g_char_lut[256];
 __device__ __forceinline__ void load_lut(u8 *lut) {
   for (u32 i = threadIdx.x; i < 64; i += blockDim.x) ((u32 *)lut)[i] = ((const u32 *)g_char_lut)[i];
+}
+/* ambiguity transfer as one lookup (phyNGSC.cpp:184-206, 575-580): 0 for A/C/G/T and for bytes without an ambiguity
+ * code, else 79 + 8 * amb_code(c), so that the transferred quality byte is q + g_xq_lut[c] */
+__device__ u8 g_xq_lut[256];
+__device__ __forceinline__ void load_xq(u8 *xq) {
+  for (u32 i = threadIdx.x; i < 64; i += blockDim.x) ((u32 *)xq)[i] = ((const u32 *)g_xq_lut)[i];
 }
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
     u32 run = 0;
     for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; }
     d.hdr->NL = run; d.hdr->NR = run / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_qh_words = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_qh_words = 0; d.hdr->max_pk_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (run / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
   for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
-  __shared__ u8 lut[256], dlut[256];
+  __shared__ __align__(16) u8 lut[256], dlut[256];
   load_lut(lut);
   for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'G' ? 4 : i == 'T' ? 8 : 0);
   /* this thread's record (loaded before the span is staged so that the latencies overlap) */
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(32) k_classify(Dev d) {
   u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
   classify_subblock(d.in, g_char_lut, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
   C.payload_len = 0;
-  if (!C.status) atomicMax(&d.hdr->max_qh_words, C.max_qlen * (C.nq | 1u));
+  if (!C.status) { atomicMax(&d.hdr->max_qh_words, C.max_qlen * (C.nq | 1u)); atomicMax(&d.hdr->max_pk_bytes, (C.max_qlen + 1) * C.nq * 2u); }
 }
 
 __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
@@ -688,7 +695,7 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
-  __shared__ u8 lut[256];
+  __shared__ __align__(16) u8 lut[256];
   load_lut(lut);
   /* only the few non-constant tokens of each title are touched: with long records it is cheaper to read them
    * straight from global memory (L1) than to stage whole records */
@@ -787,7 +794,131 @@ __global__ void __launch_bounds__(128) k_huff(Dev d) {
     u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS[w], lane, 32u, WarpSync());
     if (lane == 0) td[t].tree_len = blob;
     __syncwarp();
+    if (t - C.tq0 <= C.max_qlen) { /* quality table: 16-bit copy (len << 12 | code) for the shared-memory walkers */
+      u16 *pk = (u16 *)(arena + C.qpk_off) + (size_t)(t - C.tq0) * D.n;
+      const u64 *cl = (const u64 *)(arena + D.cl_off);
+      bool bad = blob == 0;
+      for (u32 i = lane; i < D.n && blob; i += 32) { u16 e; if (!qpack_entry(cl[i], e)) bad = true; pk[i] = e; }
+      if (bad) atomicOr(&C.qpk_bad, 1u);
+    }
   }
+}
+
+/* ---- per-record walkers of the encoder kernels -------------------------------------------------------------------- */
+/* Shared-memory tables of one CTA: symbol maps, the ambiguity-transfer lookup and (when they fit and no code is longer
+ * than 12 bits) the packed quality code tables of the subblock. */
+struct WalkTabs {
+  const u8 *qmap, *smap, *xq;  /* qua_code[256], sym_code[256], g_xq_lut */
+  const u16 *pk; u32 nq;       /* packed quality tables (nullptr: read the 64-bit entries from the arena) */
+  const u64 *qcl;              /* 64-bit quality entries, table-major */
+  u32 dna_mode;                /* 0 Huffman, 1 two bits per base through smap, 2 two bits per base, alphabet exactly ACGT */
+  const u64 *dcl;              /* DNA code table (Huffman mode) */
+};
+
+__device__ __forceinline__ void put_pk(CountSink &s, u32 e) { s.bits += e >> 12; }
+__device__ __forceinline__ void put_pk2(CountSink &s, u32 e0, u32 e1) { s.bits += (e0 >> 12) + (e1 >> 12); }
+template <class Sink> __device__ __forceinline__ void put_pk(Sink &s, u32 e) { s.put(e & 0xFFFu, e >> 12); }
+template <class Sink> __device__ __forceinline__ void put_pk2(Sink &s, u32 e0, u32 e1) { /* two codes (<= 12 bits each) appended as one */
+  const u32 l1 = e1 >> 12;
+  s.put(((e0 & 0xFFFu) << l1) | (e1 & 0xFFFu), (e0 >> 12) + l1);
+}
+
+/* Quality codes of one record (tasks.cpp:609-619): position k uses table k+1.  Four symbols per step: their bytes,
+ * symbol codes and table entries are loaded together (independent shared-memory loads), then appended pairwise.
+ * The ambiguity transfer (phyNGSC.cpp:575-580) costs two more loads per symbol and is only compiled into the loop
+ * of warps that hold such a record. */
+template <class Sink>
+__device__ __forceinline__ void quality_walk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
+  const bool wx = __any_sync(__activemask(), xfer);
+  const u32 xm = xfer ? 0xFFu : 0u;
+  const u32 nq = T.nq;
+  if (T.pk) {
+    const u16 *row = T.pk + nq;
+    u32 j = 0;
+    if (!wx) {
+      for (; j + 4 <= L; j += 4, row += 4 * nq) {
+        const u32 q0 = qp[j], q1 = qp[j + 1], q2 = qp[j + 2], q3 = qp[j + 3];
+        const u32 c0 = T.qmap[q0], c1 = T.qmap[q1], c2 = T.qmap[q2], c3 = T.qmap[q3];
+        const u32 e0 = row[c0], e1 = row[nq + c1], e2 = row[2 * nq + c2], e3 = row[3 * nq + c3];
+        put_pk2(s, e0, e1); put_pk2(s, e2, e3);
+      }
+    } else {
+      for (; j + 4 <= L; j += 4, row += 4 * nq) {
+        const u32 q0 = qp[j] + (T.xq[sp[j]] & xm), q1 = qp[j + 1] + (T.xq[sp[j + 1]] & xm);
+        const u32 q2 = qp[j + 2] + (T.xq[sp[j + 2]] & xm), q3 = qp[j + 3] + (T.xq[sp[j + 3]] & xm);
+        const u32 c0 = T.qmap[q0], c1 = T.qmap[q1], c2 = T.qmap[q2], c3 = T.qmap[q3];
+        const u32 e0 = row[c0], e1 = row[nq + c1], e2 = row[2 * nq + c2], e3 = row[3 * nq + c3];
+        put_pk2(s, e0, e1); put_pk2(s, e2, e3);
+      }
+    }
+    for (; j < L; ++j, row += nq) put_pk(s, (u32)row[T.qmap[qp[j] + (T.xq[sp[j]] & xm)]]);
+    return;
+  }
+  const u64 *row = T.qcl + nq;
+  for (u32 j = 0; j < L; ++j, row += nq) {
+    const u64 e = row[T.qmap[qp[j] + (T.xq[sp[j]] & xm)]];
+    s.put((u32)e, (u32)(e >> 32));
+  }
+}
+
+/* DNA codes of one record (tasks.cpp:544-557).  With the alphabet exactly ACGT and no ambiguity transfer in the warp,
+ * four bases are turned into eight bits with a handful of word operations: ((c >> 1) & 3) ^ ((c >> 2) & 1) maps
+ * A,C,G,T to 0,1,2,3 and a multiply gathers the four 2-bit fields. */
+template <class Sink>
+__device__ __forceinline__ void dna_walk(const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
+  const bool wx = __any_sync(__activemask(), xfer);
+  if (T.dna_mode == 2 && !wx) {
+    const u32 a = (u32)(size_t)sp & 3u;
+    const u32 *wp = (const u32 *)(sp - a);
+    u32 w0 = wp[0], acc = 0, cnt = 0, j = 0;
+    for (; j + 4 <= L; j += 4) {
+      const u32 w1 = *++wp;
+      const u32 v = __funnelshift_r(w0, w1, a * 8);
+      w0 = w1;
+      const u32 z = ((v >> 1) & 0x03030303u) ^ ((v >> 2) & 0x01010101u);
+      acc = (acc << 8) | ((z * 0x40100401u) >> 24);
+      cnt += 4;
+      if (cnt == 16) { s.put(acc, 32); acc = 0; cnt = 0; }
+    }
+    for (; j < L; ++j) { acc = (acc << 2) | T.smap[sp[j]]; ++cnt; }
+    s.put(acc, 2 * cnt);
+    return;
+  }
+  if (T.dna_mode) {
+    u32 w = 0, cnt = 0;
+    for (u32 j = 0; j < L; ++j) {
+      const u8 c = sp[j];
+      if (xfer && T.xq[c]) continue; /* every non-ACGT base of such a record carries a transferable code */
+      w = (w << 2) | T.smap[c];
+      if (++cnt == 16) { s.put(w, 32); w = 0; cnt = 0; }
+    }
+    s.put(w, 2 * cnt);
+    return;
+  }
+  for (u32 j = 0; j < L; ++j) {
+    const u8 c = sp[j];
+    if (xfer && T.xq[c]) continue;
+    const u64 e = T.dcl[T.smap[c]];
+    s.put((u32)e, (u32)(e >> 32));
+  }
+}
+
+/* Fills the CTA's walker tables; `pk_smem` (d.pk_bytes of shared memory) receives the packed quality tables when they fit. */
+__device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, const u32 *arena, const TableDesc *td, u8 *codes /*[512]*/, u8 *xq /*[256]*/,
+                                               u16 *pk_smem, WalkTabs &T) {
+  for (u32 i = threadIdx.x; i < 64; i += blockDim.x) { ((u32 *)codes)[i] = ((const u32 *)C.qua_code)[i]; ((u32 *)codes)[64 + i] = ((const u32 *)C.sym_code)[i]; }
+  load_xq(xq);
+  T.qmap = codes; T.smap = codes + 256; T.xq = xq; T.nq = C.nq;
+  T.qcl = (const u64 *)(arena + td[C.tq0].cl_off);
+  const u32 pk_bytes = (C.max_qlen + 1) * C.nq * 2u;
+  T.pk = nullptr;
+  if (!C.qpk_bad && pk_bytes <= d.pk_bytes) {
+    const uint4 *src = (const uint4 *)(arena + C.qpk_off);
+    for (u32 i = threadIdx.x; i < (pk_bytes + 15) / 16; i += blockDim.x) ((uint4 *)pk_smem)[i] = src[i];
+    T.pk = pk_smem;
+  }
+  T.dna_mode = !C.plain ? 0u : (C.nsym == 4 && C.symbols[0] == 'A' && C.symbols[1] == 'C' && C.symbols[2] == 'G' && C.symbols[3] == 'T') ? 2u : 1u;
+  T.dcl = C.plain ? (const u64 *)nullptr : (const u64 *)(arena + td[C.tdna].cl_off);
 }
 
 /* ---- lengths ----------------------------------------------------------------------------------------------------- */
@@ -797,7 +928,7 @@ __global__ void __launch_bounds__(128) k_huff(Dev d) {
 __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ FieldClass fc[MAXF];
-  __shared__ u8 codes[512];
+  __shared__ __align__(16) u8 codes[512];
   __shared__ u32 ws[4];
   const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
@@ -806,9 +937,11 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
-  for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
+  __shared__ __align__(16) u8 xq[256];
+  WalkTabs T;
+  load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)((u8 *)dyn_smem + d.span_bytes), T);
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
-  __shared__ u8 lut[256];
+  __shared__ __align__(16) u8 lut[256];
   load_lut(lut);
   const bool active = tid < nrec;
   const u32 r = r0 + (active ? tid : nrec - 1); /* idle lanes shadow the chunk's last record so that warps stay converged */
@@ -820,18 +953,18 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   load_field_classes(C, fc);
   __syncthreads();
   u32 qbits = 0, dbits = 0;
-  if (active) {
+  {
     const bool xfer = kx >> 15;
     CountSink q; q.init();
-    { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq;
-      if (!C.varlen) quality_record_simple(b, te + 1, L, se + 3, xfer, codes, t, q); else quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
-    qbits = (u32)q.bits;
+    quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
+    qbits = active ? (u32)q.bits : 0u;
     if (C.plain) dbits = 2 * (kx & 0x7FFFu);
     else {
       CountSink dn; dn.init();
-      dna_record(b, te + 1, L, xfer, false, codes + 256, (const u64 *)(arena + td[C.tdna].cl_off), dn);
+      dna_walk(b + te + 1, L, xfer, T, dn);
       dbits = (u32)dn.bits;
     }
+    if (!active) dbits = 0;
   }
   u32 qtot, dtot;
   u32 qloc = block_excl_scan<4>(qbits, ws, qtot);
@@ -945,7 +1078,7 @@ __device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
 __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ FieldClass fc[MAXF];
-  __shared__ u8 codes[512];
+  __shared__ __align__(16) u8 codes[512];
   const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
   if (C.status || chunk * CH >= C.R) return;
@@ -956,9 +1089,11 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   u8 *out = d.out + C.out_off;
   u32 *outw = (u32 *)d.out;
   const u64 obase = C.out_off; /* byte offset of the payload inside d.out (16-byte aligned) */
-  for (u32 i = tid; i < 256; i += CH) { codes[i] = C.qua_code[i]; codes[256 + i] = C.sym_code[i]; }
+  __shared__ __align__(16) u8 xq[256];
+  WalkTabs T;
+  load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)((u8 *)dyn_smem + d.span_bytes), T);
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
-  __shared__ u8 lut[256];
+  __shared__ __align__(16) u8 lut[256];
   load_lut(lut);
   const bool active = tid < nrec;
   const u32 i_sb = chunk * CH + (active ? tid : nrec - 1); /* record index inside the subblock (idle lanes shadow the last) */
@@ -989,21 +1124,20 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
     for (u32 i = tid; i < C.qhdr_len; i += CH) or_byte(out, o_qual + i, stage[C.thdr_cap + i]);
     for (u32 i = tid; i < C.dhdr_len; i += CH) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
   }
-  if (active) {
+  {
     const bool xfer = kx >> 15;
-    { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
+    if (active) { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
       OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * C.nb_len);
       k.put(L, C.nb_len); k.finish();
     }
-    {
-      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + cq + my_qoff);
-      { QFull t; t.cl = (const u64 *)(arena + td[C.tq0].cl_off); t.nq = C.nq;
-        if (!C.varlen) quality_record_simple(b, te + 1, L, se + 3, xfer, codes, t, q); else quality_record(b, te + 1, L, se + 3, xfer, codes, t, q); }
+    { /* idle lanes of the last chunk walk the chunk's last record without storing */
+      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + cq + my_qoff, active);
+      quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
       q.finish();
     }
     {
-      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + cd + my_doff);
-      dna_record(b, te + 1, L, xfer, C.plain != 0, codes + 256, C.plain ? (const u64 *)nullptr : (const u64 *)(arena + td[C.tdna].cl_off), dn);
+      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + cd + my_doff, active);
+      dna_walk(b + te + 1, L, xfer, T, dn);
       dn.finish();
     }
   }
