@@ -288,7 +288,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
-  k_emit<<<gc, CH, span + d.pk_bytes, st>>>(d); PMARK();
+  k_emit<<<gc, EMIT_THREADS, span + d.pk_bytes, st>>>(d); PMARK();
   ctx->launches += 13;
   CK(cudaGetLastError());
   if (ctx->profile) {

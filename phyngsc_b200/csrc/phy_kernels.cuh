@@ -34,6 +34,7 @@ constexpr int CH = 128;            /* records per work item (4 warps; one warp =
 constexpr int TILE = 16384;        /* bytes per newline-index tile                                         */
 constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
 constexpr u32 QH_SMEM = 44 * 1024; /* private histogram rows of one quality-histogram CTA                  */
+constexpr int EMIT_MIN_CTAS = 6;   /* register budget of k_emit: 65536 / (256 * 6) = 42 */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
@@ -334,7 +335,8 @@ struct Stat1S {
   i32 err;
   u32 nf, ts0, te0;
   u32 off0[MAXF], len0[MAXF];
-  u32 pvals0[MAXF];
+  u32 v0[MAXF];     /* numeric value / is_num of record 0's tokens */
+  u8 num0[MAXF];
   u8 qflag[256];  /* quality byte seen (after ambiguity transfer) */
   u8 r0[R0_MAX];
 };
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     else {
       TitleCursor c; c.init(S.r0, 0, te0 - ts0, lut);
       Tok t; u32 nf = 0;
-      while (c.next(t)) { if (nf < (u32)MAXF) { S.off0[nf] = t.start; S.len0[nf] = t.end - t.start; } ++nf; }
+      while (c.next(t)) { if (nf < (u32)MAXF) { S.off0[nf] = t.start; S.len0[nf] = t.end - t.start; S.v0[nf] = t.v; S.num0[nf] = t.num ? 1 : 0; } ++nf; }
       S.nf = nf;
       if (nf == 0 || nf > (u32)MAXF || nf > d.max_nf) S.err = E_UNSUPPORTED;
     }
@@ -427,25 +429,53 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms); atomicMax(&S.inv_minq, iq);
     }
   }
-  /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way */
+  /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way.
+   * Most tokens repeat record 0's: a token whose bytes AND separator equal record 0's is that token, so a warp
+   * whose 32 records all pass this comparison neither tokenises the field nor reduces anything -- record 0's own
+   * length and value are folded into the accumulators once per CTA instead. */
   const bool walk = active && !err && seed_ok;
   bool fields_ok = true;
   TitleCursor cur; cur.init(b, ts, te, lut);
+  if (seed_ok && tid < nf) {
+    const u32 l0 = S.len0[tid], k0 = key_of((i32)S.v0[tid]);
+    atomicMax(&S.facc[tid][0], ~l0); atomicMax(&S.facc[tid][1], l0);
+    if (!S.num0[tid]) S.facc[tid][2] = 1;
+    atomicMax(&S.facc[tid][3], k0); atomicMax(&S.facc[tid][4], ~k0);
+  }
   for (u32 f = 0; f < nf && seed_ok; ++f) {
+    const u32 len0 = S.len0[f];
+    const u8 *d0 = S.r0 + S.off0[f];
+    bool ok = walk && fields_ok;
+    bool same = ok && cur.pos + len0 <= te;
+    if (same) {
+      const u8 *dp = b + cur.pos;
+      u32 diff = 0;
+      for (u32 p = 0; p <= len0; ++p) diff |= (u32)(dp[p] ^ d0[p]);
+      same = diff == 0;
+    }
+    if (__all_sync(0xFFFFFFFFu, same || !ok)) {
+      vals[f * CH + tid] = S.v0[f];
+      if (same) cur.pos += len0 + 1;
+      continue;
+    }
     Tok t; t.start = t.end = 0; t.v = 0; t.num = true;
     u32 len = 0;
-    bool ok = walk && fields_ok;
     if (ok && !cur.next(t)) { fields_ok = false; ok = false; t.start = t.end = 0; t.v = 0; t.num = true; }
     if (ok) {
       len = t.end - t.start;
-      const u32 len0 = S.len0[f], m = len < len0 ? len : len0;
-      const u8 *d0 = S.r0 + S.off0[f], *dp = b + t.start;
-      /* most tokens equal record 0's: find out with a branch-free pass, mark positions only when something differs */
-      u32 diff = 0;
-      for (u32 p = 0; p < m; ++p) diff |= (u32)(dp[p] ^ d0[p]);
-      if (diff)
-        for (u32 p = 0; p < m; ++p)
-          if (dp[p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
+      const u32 m = len < len0 ? len : len0;
+      const u8 *dp = b + t.start;
+      if (len0 <= 32) { /* Hamming mask of the field in one register */
+        u32 mm = 0;
+        for (u32 p = 0; p < m; ++p) mm |= (dp[p] != d0[p] ? 1u : 0u) << p;
+        if (mm & ~S.mism[f][0]) atomicOr(&S.mism[f][0], mm);
+      } else {
+        u32 diff = 0;
+        for (u32 p = 0; p < m; ++p) diff |= (u32)(dp[p] ^ d0[p]);
+        if (diff)
+          for (u32 p = 0; p < m; ++p)
+            if (dp[p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
+      }
     }
     vals[f * CH + tid] = t.v;
     u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
@@ -1075,11 +1105,14 @@ __device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
   if (v) atomicOr((u32 *)(base + (pos & ~3u)), (u32)v << (8 * (pos & 3u)));
 }
 
-__global__ void __launch_bounds__(CH) k_emit(Dev d) {
+/* Two threads per record: threads 0..127 write the info length bits and the quality codes, threads 128..255 the DNA
+ * and the title tokens.  The streams are independent, and twice the warps per staged span hide twice the latency. */
+constexpr int EMIT_THREADS = 2 * CH;
+__global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ FieldClass fc[MAXF];
   __shared__ __align__(16) u8 codes[512];
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const u32 s = blockIdx.y, chunk = blockIdx.x, role = threadIdx.x / CH, tid = threadIdx.x % CH, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
   if (C.status || chunk * CH >= C.R) return;
   const SbPlan P = d.plans[s];
@@ -1098,11 +1131,15 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
   const bool active = tid < nrec;
   const u32 i_sb = chunk * CH + (active ? tid : nrec - 1); /* record index inside the subblock (idle lanes shadow the last) */
   const u32 r = P.first_rec + i_sb;
-  const u32 te = d.te[r], se = d.se[r], L = se - te - 1, rs_r = d.rstart[r];
-  const u32 kx = d.kx[r], my_qoff = d.qoff[r], my_doff = d.doff[r], my_toff = C.nnc ? d.toff[r] : 0u;
-  const u32 cq = arena[C.chunk_off + chunk], cd = arena[C.chunk_off + C.nchunk + chunk];
-  const u32 flags = C.nnc ? arena[C.flagbits_off + i_sb / 32] : 0u;
-  const u32 tblk = C.nnc ? arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w] : 0u;
+  const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
+  const u32 kx = d.kx[r];
+  /* role 0: quality offsets; role 1: DNA and title offsets */
+  const u32 my_off = role == 0 ? d.qoff[r] : d.doff[r];
+  const u32 cbase = arena[C.chunk_off + role * C.nchunk + chunk];
+  const bool tit = role == 1 && C.nnc;
+  const u32 rs_r = tit ? d.rstart[r] : 0u, my_toff = tit ? d.toff[r] : 0u;
+  const u32 flags = tit ? arena[C.flagbits_off + i_sb / 32] : 0u;
+  const u32 tblk = tit ? arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w] : 0u;
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_field_classes(C, fc);
@@ -1112,7 +1149,7 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
     /* fixed part of the info stream (phyNGSC.cpp:719-730) and the three staged headers.  Bytes are OR-ed
      * into the zeroed payload word-atomically because a header may end inside a word whose other bytes
      * belong to a bit stream written by another thread. */
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       u8 fx[INFO_FIXED];
       ByteWriter bw; bw.p = fx; bw.n = 0;
       bw.word(C.R); bw.word(C.max_qlen); bw.word(C.max_slen);
@@ -1120,26 +1157,26 @@ __global__ void __launch_bounds__(CH) k_emit(Dev d) {
       for (u32 i = 0; i < INFO_FIXED; ++i) or_byte(out, i, fx[i]);
     }
     const u8 *stage = (const u8 *)(arena + C.stage_off);
-    for (u32 i = tid; i < C.thdr_len; i += CH) or_byte(out, o_title + i, stage[i]);
-    for (u32 i = tid; i < C.qhdr_len; i += CH) or_byte(out, o_qual + i, stage[C.thdr_cap + i]);
-    for (u32 i = tid; i < C.dhdr_len; i += CH) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
+    for (u32 i = threadIdx.x; i < C.thdr_len; i += EMIT_THREADS) or_byte(out, o_title + i, stage[i]);
+    for (u32 i = threadIdx.x; i < C.qhdr_len; i += EMIT_THREADS) or_byte(out, o_qual + i, stage[C.thdr_cap + i]);
+    for (u32 i = threadIdx.x; i < C.dhdr_len; i += EMIT_THREADS) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
   }
-  {
-    const bool xfer = kx >> 15;
+  const bool xfer = kx >> 15;
+  if (role == 0) {
     if (active) { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
       OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * C.nb_len);
       k.put(L, C.nb_len); k.finish();
     }
-    { /* idle lanes of the last chunk walk the chunk's last record without storing */
-      OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + cq + my_qoff, active);
-      quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
-      q.finish();
-    }
-    {
-      OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + cd + my_doff, active);
-      dna_walk(b + te + 1, L, xfer, T, dn);
-      dn.finish();
-    }
+    /* idle lanes of the last chunk walk the chunk's last record without storing */
+    OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + cbase + my_off, active);
+    quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
+    q.finish();
+    return;
+  }
+  {
+    OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + cbase + my_off, active);
+    dna_walk(b + te + 1, L, xfer, T, dn);
+    dn.finish();
   }
   if (C.nnc) {
     /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509); all 32 lanes walk together */
