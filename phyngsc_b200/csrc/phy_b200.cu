@@ -63,8 +63,8 @@ struct phy_ctx {
 static const u32 SPAN_MAX = 96 * 1024;
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
-static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "classify", "zero_hist", "qhist",
-                                          "stat2", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
+static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "classify", "zero_hist", "stat2",
+                                          "qhist", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
 
 extern "C" int phy_abi_version(void) { return PHY_ABI_VERSION; }
 
@@ -276,14 +276,16 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   CK(cudaMemcpyAsync(ctx->h_hdr2, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, ctx->s_rb));
   k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d);
   k_dnacount<<<dim3(16, S), 256, 0, st>>>(d); PMARK();
-  k_qhist<<<dim3(H.max_qchunks, S), 256, d.qh_bytes, st>>>(d); PMARK();
   k_stat2<<<gc, CH, (d.tune & 1u) ? d.max_nf * CH * 4 : span_v, st>>>(d); PMARK();
-  k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
-  CK(cudaStreamSynchronize(ctx->s_rb));
+  CK(cudaStreamSynchronize(ctx->s_rb)); /* classify is long done: stat2 keeps the GPU busy meanwhile */
   {
-    u32 pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;
+    const u32 want = ctx->h_hdr2->max_qh_words * 4u, pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;
+    if (want < d.qh_bytes) d.qh_bytes = want;
+    if (d.qh_bytes < 1024) d.qh_bytes = 1024;
     d.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
   }
+  k_qhist<<<dim3(H.max_qchunks, S), 256, d.qh_bytes, st>>>(d); PMARK();
+  k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
   k_lengths<<<gc, CH, span + d.pk_bytes, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();

@@ -33,7 +33,7 @@ namespace phy {
 constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
 constexpr int TILE = 16384;        /* bytes per newline-index tile                                         */
 constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
-constexpr u32 QH_SMEM = 44 * 1024; /* private histogram rows of one quality-histogram CTA                  */
+constexpr u32 QH_SMEM = 96 * 1024; /* upper limit of the private histogram rows of one quality-histogram CTA   */
 constexpr int EMIT_MIN_CTAS = 6;   /* register budget of k_emit: 65536 / (256 * 6) = 42 */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
@@ -47,7 +47,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u64 next_pos;        /* region-relative position where the next window starts                 */
   u32 max_qchunks;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
-  u32 max_qh_words;    /* max over subblocks of max_qlen * (n_qualities | 1): one private histogram copy */
+  u32 max_qh_words;    /* max over subblocks of the private quality-histogram copies of one k_qhist CTA (words) */
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
 };
 
@@ -557,6 +557,10 @@ __global__ void __launch_bounds__(128) k_xdelta(Dev d) {
   if (tid < nf) { if (mx[tid]) atomicMax(&A->f[tid].kmax_d, mx[tid]); if (mn[tid]) atomicMax(&A->f[tid].kinvmin_d, mn[tid]); }
 }
 
+/* geometry of k_qhist's private histogram copies (see there) */
+__device__ __forceinline__ u32 qh_row_words(u32 nq) { return ((nq + 1) / 2) | 1u; }
+__device__ __forceinline__ u32 qh_slots(u32 Lp) { return Lp <= 256 ? 256 / Lp : 1u; }
+
 /* ---- classify + zero ------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(32) k_classify(Dev d) {
   u32 s = blockIdx.x;
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(32) k_classify(Dev d) {
   u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
   classify_subblock(d.in, g_char_lut, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
   C.payload_len = 0;
-  if (!C.status) { atomicMax(&d.hdr->max_qh_words, C.max_qlen * (C.nq | 1u)); atomicMax(&d.hdr->max_pk_bytes, (C.max_qlen + 1) * C.nq * 2u); }
+  if (!C.status) { atomicMax(&d.hdr->max_qh_words, qh_slots(C.max_qlen) * C.max_qlen * qh_row_words(C.nq)); atomicMax(&d.hdr->max_pk_bytes, (C.max_qlen + 1) * C.nq * 2u); }
 }
 
 __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
@@ -603,82 +607,86 @@ __global__ void __launch_bounds__(256) k_dnacount(Dev d) {
 }
 
 /* ---- per-position quality histogram (tasks.cpp:260-286) ----------------------------------------------------- */
-/* Row (position) p of a private histogram copy is owned by exactly one thread, so the increments need no
- * atomics; the CTA flushes its non-zero counters to the subblock's table with atomicAdd at the end. */
+/* Row (position) p of a private histogram copy is owned by exactly one thread, so the increments need no atomics;
+ * the CTA flushes its non-zero counters to the subblock's table with atomicAdd at the end.  A CTA counts at most
+ * QCH = 1024 records, so the private counters are 16 bits wide; a row is (n_qualities + 1) / 2 | 1 words (odd, so
+ * that the rows of neighbouring positions start in different banks).  Each thread keeps eight records in flight:
+ * the quality bytes come straight from global memory and their latency is what the loop waits for. */
+
 __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ u32 m_qs[QCH];
-  __shared__ u16 m_len[QCH];
-  __shared__ u8 m_x[QCH];
-  __shared__ u8 qcode[256];
+  __shared__ u16 m_len[QCH]; /* read length | ambiguity-transfer flag << 15 */
+  __shared__ __align__(16) u8 qcode[256];
   const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const SbClass &C = d.cls[s];
   if (C.status || chunk * QCH >= C.R) return;
   const SbPlan P = d.plans[s];
   const u32 r0 = P.first_rec + chunk * QCH, nrec = min((u32)QCH, C.R - chunk * QCH);
-  const u32 Lp = C.max_qlen, nq = C.nq, stride = nq | 1u;
+  const u32 Lp = C.max_qlen, nq = C.nq, rw = qh_row_words(nq), rh = rw * 2;
   u32 *gq = d.arena + (size_t)s * d.arena_words + C.qstat_off;
-  for (u32 i = tid; i < 256; i += 256) qcode[i] = C.qua_code[i];
+  for (u32 i = tid; i < 64; i += 256) ((u32 *)qcode)[i] = ((const u32 *)C.qua_code)[i];
   for (u32 i = tid; i < nrec; i += 256) {
     u32 te = d.te[r0 + i], se = d.se[r0 + i];
-    m_qs[i] = se + 3; m_len[i] = (u16)(se - te - 1); m_x[i] = (u8)(d.kx[r0 + i] >> 15);
+    m_qs[i] = se + 3; m_len[i] = (u16)((se - te - 1) | (d.kx[r0 + i] & 0x8000u));
   }
-  u32 *hist = (u32 *)dyn_smem;
-  u32 slots = Lp <= 256 ? 256 / Lp : 1;
-  u32 fit = d.qh_bytes / (Lp * stride * 4);
+  u16 *hist = (u16 *)dyn_smem;
+  u32 slots = qh_slots(Lp);
+  const u32 fit = d.qh_bytes / (Lp * rw * 4);
   if (slots > fit) slots = fit;
   if (slots == 0) { /* rows do not fit in shared memory: count straight into the global table */
     __syncthreads();
     for (u32 i = 0; i < nrec; ++i) {
-      u32 qs = m_qs[i], L = m_len[i];
+      const u32 qs = m_qs[i], L = m_len[i] & 0x7FFFu;
       for (u32 p = tid; p < L; p += 256) {
-        u8 q = d.in[qs + p];
-        if (m_x[i]) { u32 a = amb_code(d.in[qs - 3 - L + p]); if (a > 1) q = xfer_qual(a, q); }
-        u32 c = qcode[q];
+        u32 q = d.in[qs + p];
+        if (m_len[i] & 0x8000u) q += g_xq_lut[d.in[qs - 3 - L + p]];
+        const u32 c = qcode[q];
         atomicAdd(&gq[(p + 1) * nq + c], 1u); atomicAdd(&gq[c], 1u);
       }
     }
     return;
   }
-  for (u32 i = tid; i < slots * Lp * stride; i += 256) hist[i] = 0;
+  for (u32 i = tid; i < slots * Lp * rw; i += 256) ((u32 *)hist)[i] = 0;
   __syncthreads();
   if (Lp <= 256) {
     const u32 slot = tid / Lp, p = tid % Lp;
     if (slot < slots) {
-      u32 *row = hist + (slot * Lp + p) * stride;
-      /* four records in flight per thread so that the byte loads overlap */
-      for (u32 i0 = slot; i0 < nrec; i0 += 4 * slots) {
-        u8 q[4]; bool on[4];
+      u16 *row = hist + (slot * Lp + p) * rh;
+      const u8 *src = d.in + p;
+      for (u32 i0 = slot; i0 < nrec; i0 += 8 * slots) {
+        u32 q[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          u32 i = i0 + k * slots;
-          on[k] = i < nrec && p < m_len[i];
-          q[k] = on[k] ? __ldg(d.in + m_qs[i] + p) : (u8)0;
+        for (int k = 0; k < 8; ++k) {
+          const u32 i = i0 + k * slots;
+          const bool on = i < nrec && p < (m_len[i] & 0x7FFFu);
+          q[k] = on ? (u32)__ldg(src + m_qs[i]) : 0xFFFFFFFFu;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!on[k]) continue;
-          u32 i = i0 + k * slots;
-          u8 qq = q[k];
-          if (m_x[i]) { u32 a = amb_code(d.in[m_qs[i] - 3 - m_len[i] + p]); if (a > 1) qq = xfer_qual(a, qq); }
+        for (int k = 0; k < 8; ++k) {
+          if (q[k] == 0xFFFFFFFFu) continue;
+          const u32 i = i0 + k * slots;
+          u32 qq = q[k];
+          if (m_len[i] & 0x8000u) qq += g_xq_lut[d.in[m_qs[i] - 3 - (m_len[i] & 0x7FFFu) + p]];
           row[qcode[qq]]++;
         }
       }
     }
-  } else {
+  } else { /* reads longer than 256: thread t owns rows t, t + 256, ... of the single copy */
     for (u32 i = 0; i < nrec; ++i) {
-      u32 L = m_len[i], qs = m_qs[i];
+      const u32 L = m_len[i] & 0x7FFFu, qs = m_qs[i];
       for (u32 p = tid; p < L; p += 256) {
-        u8 q = d.in[qs + p];
-        if (m_x[i]) { u32 a = amb_code(d.in[qs - 3 - L + p]); if (a > 1) q = xfer_qual(a, q); }
-        hist[p * stride + qcode[q]]++;
+        u32 q = d.in[qs + p];
+        if (m_len[i] & 0x8000u) q += g_xq_lut[d.in[qs - 3 - L + p]];
+        hist[p * rh + qcode[q]]++;
       }
     }
   }
   __syncthreads();
   for (u32 i = tid; i < Lp * nq; i += 256) {
-    u32 p = i / nq, c = i % nq, v = 0;
-    for (u32 k = 0; k < slots; ++k) v += hist[(k * Lp + p) * stride + c];
+    const u32 p = i / nq, c = i % nq;
+    u32 v = 0;
+    for (u32 k = 0; k < slots; ++k) v += hist[(k * Lp + p) * rh + c];
     if (v) { atomicAdd(&gq[(p + 1) * nq + c], v); atomicAdd(&gq[c], v); }
   }
 }
