@@ -158,32 +158,43 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
 }
 
 /* (a) record splitter, pass 2: line l = 4r+k ends at the l-th newline; k=0 title, 1 sequence, 3 quality.
- * Each thread owns 64 bytes; newline bytes are found with a SIMD byte compare and visited by bit scan. */
+ * Each thread owns 64 bytes.  It first builds the 64-bit mask of its newline bytes with word operations (exact
+ * zero-byte test of w ^ 0x0A0A0A0A, the four flag bits gathered by a multiply), all lanes converged; only then are
+ * the set bits visited -- as many iterations as the thread has newlines, two on average. */
+__device__ __forceinline__ u32 nl_nibble(u32 w) {
+  const u32 x = w ^ 0x0A0A0A0Au;
+  const u32 t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); /* bit 7 of a byte set iff the byte was '\n' */
+  return (t * 0x00204081u) >> 28;
+}
 __device__ __forceinline__ void nl_put(const Dev &d, u32 l, u32 pos) {
-  u32 r = l >> 2, k = l & 3;
-  if (k == 0) d.te[r] = pos; else if (k == 1) d.se[r] = pos; else if (k == 3) d.rstart[r + 1] = pos + 1;
+  const u32 r = l >> 2, k = l & 3;
+  u32 *dst = k == 0 ? d.te + r : k == 1 ? d.se + r : d.rstart + r + 1;
+  if (k != 2) *dst = pos + (k == 3 ? 1u : 0u);
 }
 __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   __shared__ u32 ws[8];
   if (d.hdr->status) return;
-  u32 t = blockIdx.x;
-  u32 p = t * TILE + threadIdx.x * 64;
-  u32 n = nl_count64(d.in, p, d.start_pos, d.len);
+  const u32 t = blockIdx.x;
+  const u32 p = t * TILE + threadIdx.x * 64;
+  const bool whole = p >= d.start_pos && p + 64 <= d.len;
+  u32 mlo = 0, mhi = 0, n = 0;
+  if (whole) {
+    const uint4 *q = (const uint4 *)(d.in + p);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+    mlo = nl_nibble(v0.x) | nl_nibble(v0.y) << 4 | nl_nibble(v0.z) << 8 | nl_nibble(v0.w) << 12 | nl_nibble(v1.x) << 16 | nl_nibble(v1.y) << 20 |
+          nl_nibble(v1.z) << 24 | nl_nibble(v1.w) << 28;
+    mhi = nl_nibble(v2.x) | nl_nibble(v2.y) << 4 | nl_nibble(v2.z) << 8 | nl_nibble(v2.w) << 12 | nl_nibble(v3.x) << 16 | nl_nibble(v3.y) << 20 |
+          nl_nibble(v3.z) << 24 | nl_nibble(v3.w) << 28;
+    n = __popc(mlo) + __popc(mhi);
+  } else {
+    n = nl_count64(d.in, p, d.start_pos, d.len);
+  }
   u32 tot;
   u32 l = d.tile_off[t] + block_excl_scan_256(n, ws, tot);
   if (!n) return;
-  if (p >= d.start_pos && p + 64 <= d.len) {
-    const uint4 *q = (const uint4 *)(d.in + p);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint4 v = __ldg(q + k);
-      u32 w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        u32 m = __vcmpeq4(w[j], 0x0A0A0A0Au) & 0x01010101u;
-        while (m) { u32 bit = __ffs(m) - 1; nl_put(d, l++, p + k * 16 + j * 4 + (bit >> 3)); m &= m - 1; }
-      }
-    }
+  if (whole) {
+    while (mlo) { const u32 bit = __ffs(mlo) - 1; mlo &= mlo - 1; nl_put(d, l++, p + bit); }
+    while (mhi) { const u32 bit = __ffs(mhi) - 1; mhi &= mhi - 1; nl_put(d, l++, p + 32 + bit); }
   } else {
     u32 lo = max(p, d.start_pos), hi = min(p + 64, d.len);
     for (u32 i = lo; i < hi; ++i) if (d.in[i] == '\n') nl_put(d, l++, i);
@@ -655,19 +666,18 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
       u16 *row = hist + (slot * Lp + p) * rh;
       const u8 *src = d.in + p;
       for (u32 i0 = slot; i0 < nrec; i0 += 8 * slots) {
-        u32 q[8];
+        u32 q[8], ml[8]; /* quality byte (or none), read length | transfer flag */
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const u32 i = i0 + k * slots;
-          const bool on = i < nrec && p < (m_len[i] & 0x7FFFu);
-          q[k] = on ? (u32)__ldg(src + m_qs[i]) : 0xFFFFFFFFu;
+          ml[k] = i < nrec ? (u32)m_len[i] : 0u;
+          q[k] = p < (ml[k] & 0x7FFFu) ? (u32)__ldg(src + m_qs[i]) : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (q[k] == 0xFFFFFFFFu) continue;
-          const u32 i = i0 + k * slots;
           u32 qq = q[k];
-          if (m_len[i] & 0x8000u) qq += g_xq_lut[d.in[m_qs[i] - 3 - (m_len[i] & 0x7FFFu) + p]];
+          if (ml[k] & 0x8000u) qq += g_xq_lut[d.in[m_qs[i0 + k * slots] - 3 - (ml[k] & 0x7FFFu) + p]];
           row[qcode[qq]]++;
         }
       }
