@@ -242,6 +242,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     ++pi;                                                                                                         \
   } while (0)
   PMARK();
+  CK(cudaMemsetAsync(ctx->tile_off, 0, (size_t)((d.ntiles + SUPER - 1) / SUPER) * 4, st));
   k_nl_count<<<d.ntiles, 256, 0, st>>>(d); PMARK();
   k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
   k_nl_emit<<<d.ntiles, 256, 0, st>>>(d); PMARK();

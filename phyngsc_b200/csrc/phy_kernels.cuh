@@ -31,7 +31,8 @@
 namespace phy {
 
 constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
-constexpr int TILE = 16384;        /* bytes per newline-index tile                                         */
+constexpr int TILE = 16384;        /* bytes per newline-index tile (256 threads x 64 bytes)                */
+constexpr int SUPER = 64;          /* tiles per supertile: the single-CTA scan runs over supertiles         */
 constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
 constexpr u32 QH_SMEM = 96 * 1024; /* upper limit of the private histogram rows of one quality-histogram CTA   */
 constexpr int EMIT_MIN_CTAS = 6;   /* register budget of k_emit: 65536 / (256 * 6) = 42 */
@@ -130,31 +131,35 @@ __global__ void __launch_bounds__(256) k_nl_count(Dev d) {
   u32 t = blockIdx.x;
   u32 p = t * TILE + threadIdx.x * 64;
   u32 n = nl_count64(d.in, p, d.start_pos, d.len);
-  u32 tot;
-  block_excl_scan_256(n, ws, tot);
-  if (threadIdx.x == 0) d.tile_cnt[t] = tot;
+  n = __reduce_add_sync(0xFFFFFFFFu, n);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    n = __reduce_add_sync(0xFFFFFFFFu, threadIdx.x < 8 ? ws[threadIdx.x] : 0u);
+    if (threadIdx.x == 0) { d.tile_cnt[t] = n; if (n) atomicAdd(&d.tile_off[t / SUPER], n); } /* tile_off: supertile totals, zeroed by the host */
+  }
 }
 
-/* exclusive scan over tiles (single CTA) */
+/* exclusive scan over the supertile totals (single CTA) */
 __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
-  __shared__ u32 part[1024];
-  u32 per = (d.ntiles + 1023) / 1024;
-  u32 b = threadIdx.x * per, e = min(b + per, d.ntiles);
-  u32 s = 0;
-  for (u32 i = b; i < e; ++i) s += d.tile_cnt[i];
-  part[threadIdx.x] = s;
-  __syncthreads();
+  __shared__ u32 ws[32];
+  const u32 nsuper = (d.ntiles + SUPER - 1) / SUPER;
+  u32 carry = 0;
+  for (u32 base = 0; base < nsuper; base += 1024) {
+    const u32 i = base + threadIdx.x;
+    const u32 v = i < nsuper ? d.tile_off[i] : 0u;
+    u32 tot;
+    const u32 ex = block_excl_scan<32>(v, ws, tot);
+    if (i < nsuper) d.tile_off[i] = carry + ex;
+    carry += tot;
+  }
   if (threadIdx.x == 0) {
-    u32 run = 0;
-    for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; }
-    d.hdr->NL = run; d.hdr->NR = run / 4;
+    const u32 total = carry;
+    d.hdr->NL = total; d.hdr->NR = total / 4;
     d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_qh_words = 0; d.hdr->max_pk_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
-    if (run / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
+    if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
-  __syncthreads();
-  u32 run = part[threadIdx.x];
-  for (u32 i = b; i < e; ++i) { d.tile_off[i] = run; run += d.tile_cnt[i]; }
 }
 
 /* (a) record splitter, pass 2: line l = 4r+k ends at the l-th newline; k=0 title, 1 sequence, 3 quality.
@@ -173,6 +178,7 @@ __device__ __forceinline__ void nl_put(const Dev &d, u32 l, u32 pos) {
 }
 __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   __shared__ u32 ws[8];
+  __shared__ u32 tile_base;
   if (d.hdr->status) return;
   const u32 t = blockIdx.x;
   const u32 p = t * TILE + threadIdx.x * 64;
@@ -189,8 +195,16 @@ __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   } else {
     n = nl_count64(d.in, p, d.start_pos, d.len);
   }
+  if (threadIdx.x < 32) { /* newlines before this tile: supertile base + the earlier tiles of the supertile */
+    const u32 t0 = t & ~(u32)(SUPER - 1);
+    u32 a = 0;
+    for (u32 u = t0 + threadIdx.x; u < t; u += 32) a += d.tile_cnt[u];
+    a = __reduce_add_sync(0xFFFFFFFFu, a);
+    if (threadIdx.x == 0) tile_base = d.tile_off[t / SUPER] + a;
+  }
   u32 tot;
-  u32 l = d.tile_off[t] + block_excl_scan_256(n, ws, tot);
+  u32 l = block_excl_scan_256(n, ws, tot); /* its barriers also publish tile_base */
+  l += tile_base;
   if (!n) return;
   if (whole) {
     while (mlo) { const u32 bit = __ffs(mlo) - 1; mlo &= mlo - 1; nl_put(d, l++, p + bit); }
@@ -1095,20 +1109,31 @@ __global__ void __launch_bounds__(256) k_layout(Dev d) {
 }
 
 __global__ void __launch_bounds__(256) k_outscan(Dev d) {
-  if (threadIdx.x != 0) return;
-  u32 S = d.hdr->S;
-  u64 off = 0;
-  for (u32 s = 0; s < S; ++s) {
-    SbClass &C = d.cls[s];
-    SbOut o;
-    o.status = C.status; o.out_off = off; o.out_len = C.status ? 0u : C.payload_len;
-    o.sec_len[0] = C.info_len; o.sec_len[1] = C.title_len; o.sec_len[2] = C.qual_len; o.sec_len[3] = C.dna_len;
-    if (!C.status && off + C.payload_len > d.out_cap) { C.status = E_CAPACITY; o.status = E_CAPACITY; o.out_len = 0; }
-    C.out_off = off;
-    d.sbout[s] = o;
-    off += (o.out_len + 15u) & ~15u;
+  __shared__ u32 ws[8];
+  const u32 S = d.hdr->S;
+  u64 carry = 0;
+  for (u32 base = 0; base < S; base += 256) {
+    const u32 s = base + threadIdx.x;
+    u32 len = 0, pad = 0;
+    if (s < S) { len = d.cls[s].status ? 0u : d.cls[s].payload_len; pad = (len + 15u) & ~15u; }
+    /* payloads are 16-byte aligned: scan in 16-byte units (a batch's output is far below 64 GiB) */
+    u32 tot;
+    const u32 ex = block_excl_scan_256(pad >> 4, ws, tot);
+    if (s < S) {
+      SbClass &C = d.cls[s];
+      const u64 off = carry + ((u64)ex << 4);
+      SbOut o;
+      o.status = C.status; o.out_off = off; o.out_len = len;
+      o.sec_len[0] = C.info_len; o.sec_len[1] = C.title_len; o.sec_len[2] = C.qual_len; o.sec_len[3] = C.dna_len;
+      /* a payload that does not fit takes no space, but the later ones keep the offsets of the scan: they all lie
+       * beyond the capacity as well and fail the same way */
+      if (!C.status && off + len > d.out_cap) { C.status = E_CAPACITY; o.status = E_CAPACITY; o.out_len = 0; }
+      C.out_off = off;
+      d.sbout[s] = o;
+    }
+    carry += (u64)tot << 4;
   }
-  d.hdr->total_out = off;
+  if (threadIdx.x == 0) d.hdr->total_out = carry < d.out_cap ? carry : d.out_cap;
 }
 
 __global__ void __launch_bounds__(256) k_zero_out(Dev d) {
