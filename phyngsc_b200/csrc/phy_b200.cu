@@ -63,8 +63,8 @@ struct phy_ctx {
 static const u32 SPAN_MAX = 96 * 1024;
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
-static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "classify", "zero_hist", "stat2",
-                                          "qhist", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
+static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "qhist", "classify", "zero_hist",
+                                          "stat2", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
 
 extern "C" int phy_abi_version(void) { return PHY_ABI_VERSION; }
 
@@ -130,7 +130,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   if (ctx->max_batch >= (1ull << 32) - (1u << 20)) { ctx->err = "max_batch_bytes must be < 4 GiB"; return PHY_ERR_ARG; }
   ctx->max_sb = max_sb ? max_sb : 192;
   ctx->maxrec = (u32)(ctx->max_batch / 32) + 1024;
-  ctx->arena_words = (2u << 20) / 4;
+  ctx->arena_words = (2u << 20) / 4 + RAW_WORDS; /* coding scratch + the raw quality table */
   ctx->out_cap = ctx->max_batch / 2 + (1u << 20);
   ctx->slack = 64 * 1024;
   ctx->max_tiles = (u32)((ctx->max_batch + TILE - 1) / TILE) + 1;
@@ -221,8 +221,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.span_bytes = 0;
   static const int tune_env = getenv("PHY_TUNE") ? atoi(getenv("PHY_TUNE")) : -1;
   u32 tune = tune_env >= 0 ? (u32)tune_env : 0u;
-  static const u32 qh_smem = getenv("PHY_QH_KB") ? (u32)atoi(getenv("PHY_QH_KB")) * 1024u : QH_SMEM;
-  d.tune = tune; d.qh_bytes = qh_smem;
+  d.tune = tune;
   cudaStream_t st = ctx->stream;
   ctx->last_S = 0;
   if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
@@ -269,6 +268,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   PMARK();
   k_stat1<<<gc, CH, span_v, st>>>(d);
   k_xdelta<<<S, 128, 0, st>>>(d); PMARK();
+  k_qhist<<<dim3(H.max_qchunks, S), 256, QH_SMEM, st>>>(d); PMARK();
   k_classify<<<S, 32, 0, st>>>(d); PMARK();
   /* the batch header now holds the exact size of the packed quality tables: fetch it on a side stream while the
    * statistics kernels run, so that the encoder kernels get exactly the shared memory they need */
@@ -280,12 +280,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   k_stat2<<<gc, CH, (d.tune & 1u) ? d.max_nf * CH * 4 : span_v, st>>>(d); PMARK();
   CK(cudaStreamSynchronize(ctx->s_rb)); /* classify is long done: stat2 keeps the GPU busy meanwhile */
   {
-    const u32 want = ctx->h_hdr2->max_qh_words * 4u, pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;
-    if (want < d.qh_bytes) d.qh_bytes = want;
-    if (d.qh_bytes < 1024) d.qh_bytes = 1024;
+    const u32 pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;
     d.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
   }
-  k_qhist<<<dim3(H.max_qchunks, S), 256, d.qh_bytes, st>>>(d); PMARK();
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
   k_lengths<<<gc, CH, span + d.pk_bytes, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
@@ -470,17 +467,28 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
   u32 nd = 0, nb = 0;
   u64 out_used = 0, next_pos = 0;
   float k_ms = 0, h2d_ms = 0, d2h_ms = 0;
+  u64 h2d_bytes = 0;
   int worst = 0;
   const bool patch_nl = st.is_last && region[region_len - 1] != '\n';
 
-  /* enqueue the upload of the batch that starts at `base` into buffer `slot` (stream s_in) */
+  /* enqueue the upload of the batch that starts at `base` into buffer `slot` (stream s_in).  Bytes that the
+   * previous upload already brought to the device (the tail of the other buffer: consecutive batches overlap by one
+   * window + slack) are copied device-to-device instead of crossing PCIe a second time. */
+  u64 up_base = 0, up_blen = 0; int up_slot = -1; /* last upload issued on s_in */
   auto upload = [&](u64 base, int slot, u64 &blen, bool &final, u64 &len) -> int {
     blen = region_len - base;
     if (blen > ctx->max_batch) blen = ctx->max_batch;
     final = base + blen == region_len;
     len = blen;
     CK(cudaEventRecord(ctx->ev_h0[slot], ctx->s_in));
-    CK(cudaMemcpyAsync(inb[slot], region + base, blen, cudaMemcpyHostToDevice, ctx->s_in));
+    u64 carry = 0;
+    if (up_slot >= 0 && up_slot != slot && base >= up_base && base < up_base + up_blen) {
+      carry = up_base + up_blen - base;
+      if (carry > blen) carry = blen;
+      CK(cudaMemcpyAsync(inb[slot], inb[up_slot] + (base - up_base), carry, cudaMemcpyDeviceToDevice, ctx->s_in));
+    }
+    if (blen > carry) CK(cudaMemcpyAsync(inb[slot] + carry, region + base + carry, blen - carry, cudaMemcpyHostToDevice, ctx->s_in));
+    h2d_bytes += blen - carry;
     if (final && patch_nl) { /* virtual trailing newline, see patch_trailing_newline */
       CK(cudaMemcpyAsync(inb[slot] + blen, ctx->h_nl, 64, cudaMemcpyHostToDevice, ctx->s_in));
       len += 1;
@@ -488,6 +496,7 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
       CK(cudaMemsetAsync(inb[slot] + blen, 0, 64, ctx->s_in));
     }
     CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    up_base = base; up_blen = blen; up_slot = slot;
     return PHY_OK;
   };
 
@@ -558,6 +567,7 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
     for (int i = 0; i < 2 && i < (int)nb; ++i) if (cudaEventElapsedTime(&t, ctx->ev_h0[i], ctx->ev_in[i]) == cudaSuccess) h2d_ms += t;
     if (nb > 2) h2d_ms = h2d_ms / 2 * nb; /* extrapolated from the last two batches */
   }
+  (void)h2d_bytes;
   *inout_n_descs = nd;
   if (result) {
     memset(result, 0, sizeof *result);

@@ -34,7 +34,12 @@ constexpr int CH = 128;            /* records per work item (4 warps; one warp =
 constexpr int TILE = 16384;        /* bytes per newline-index tile (256 threads x 64 bytes)                */
 constexpr int SUPER = 64;          /* tiles per supertile: the single-CTA scan runs over supertiles         */
 constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
-constexpr u32 QH_SMEM = 96 * 1024; /* upper limit of the private histogram rows of one quality-histogram CTA   */
+constexpr u32 QH_SMEM = 48 * 1024; /* private histogram rows of one quality-histogram CTA                          */
+constexpr u32 QR_COLS = 96;        /* columns of a private row: quality bytes 33..128, 16-bit counters              */
+constexpr u32 QR_ROWW = 49;        /* words per private row (96 counters + one pad word: odd, so that the rows of
+                                      neighbouring positions start in different banks)                             */
+constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
+constexpr u32 RAW_WORDS = RAW_ROWS * 256;
 constexpr int EMIT_MIN_CTAS = 6;   /* register budget of k_emit: 65536 / (256 * 6) = 42 */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
@@ -48,7 +53,6 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u64 next_pos;        /* region-relative position where the next window starts                 */
   u32 max_qchunks;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
-  u32 max_qh_words;    /* max over subblocks of the private quality-histogram copies of one k_qhist CTA (words) */
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
 };
 
@@ -71,7 +75,6 @@ struct Dev {
   i64 batch_base, region_len; i32 batch_is_final; u32 slack;
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
-  u32 qh_bytes;               /* shared memory for the private quality-histogram copies         */
   u32 pk_bytes;               /* shared memory behind the span for the packed quality code tables */
   u32 tune;                   /* experiment switches (PHY_TUNE): bit0 = stat2 reads titles straight from global memory */
 };
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_qh_words = 0; d.hdr->max_pk_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -362,7 +365,6 @@ struct Stat1S {
   u32 off0[MAXF], len0[MAXF];
   u32 v0[MAXF];     /* numeric value / is_num of record 0's tokens */
   u8 num0[MAXF];
-  u8 qflag[256];  /* quality byte seen (after ambiguity transfer) */
   u8 r0[R0_MAX];
 };
 
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
   __shared__ __align__(16) u8 lut[256], dlut[256];
   load_lut(lut);
-  for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'G' ? 4 : i == 'T' ? 8 : 0);
+  for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'T' ? 4 : i == 'G' ? 8 : 0);
   /* this thread's record (loaded before the span is staged so that the latencies overlap) */
   const bool active = tid < nrec;
   const u32 r = r0 + (active ? tid : 0);
@@ -415,30 +417,47 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       if ((c0 >= '0' && c0 <= '3') || (c1 >= '0' && c1 <= '3')) err = E_COLORSPACE;
     }
   }
-  /* sequence / quality (phyNGSC.cpp:549-619): one pass; records with ambiguity codes take a second one.
-   * Only the PRESENCE of A/C/G/T is recorded here (that decides plain 2-bit coding); exact symbol counts are
-   * taken by k_dnacount in the rare Huffman-DNA case. */
+  /* sequence (phyNGSC.cpp:549-619).  Four bases per step: the 2-bit index (c >> 1) & 3 selects the byte the base
+   * must equal ("ACTG"[idx]) and a one-hot presence byte with two byte permutes, so a read of plain A/C/G/T costs
+   * about three instructions per base and its quality line is not touched at all -- the quality alphabet comes from
+   * k_qhist's raw histogram.  Only records that hold another byte walk their bases and qualities one by one.
+   * Only the PRESENCE of A/C/G/T is recorded here (that decides plain 2-bit coding); exact symbol counts are taken
+   * by k_dnacount in the rare Huffman-DNA case. */
   u32 kept = 0, pres = 0, myL = 0;
   if (active && !err) {
-    bool ok = true, nul = false;
-    u32 namb = 0;
     const u8 *sp = b + te + 1, *qp = b + qs;
-    for (u32 j = 0; j < L; ++j) {
-      u8 c = sp[j], q = qp[j];
-      u32 f = dlut[c];
-      if (f) { pres |= f; S.qflag[q] = 1; }
-      else { ++namb; nul = nul || c == 0; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; }
-    }
-    const u32 xfer = (namb && ok) ? 1u : 0u;
-    if (namb) {
-      for (u32 j = 0; j < L; ++j) {
-        u8 c = sp[j], q = qp[j];
-        if (dlut[c]) continue;
-        if (xfer) S.qflag[xfer_qual(amb_code(c), q)] = 1;
-        else { atomicAdd(&S.dna[c], 1u); S.qflag[q] = 1; }
+    u32 bad = 0, ph = 0, j = 0;
+    {
+      const u32 a = (u32)(size_t)sp & 3u;
+      const u32 *wp = (const u32 *)(sp - a);
+      u32 w0 = wp[0];
+      for (; j + 4 <= L; j += 4) {
+        const u32 w1 = *++wp;
+        const u32 v = __funnelshift_r(w0, w1, a * 8);
+        w0 = w1;
+        const u32 z = (v >> 1) & 0x03030303u;
+        const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
+        bad |= __byte_perm(0x47544341u, 0, sel) ^ v;
+        ph |= __byte_perm(0x08040201u, 0, sel);
       }
+      for (; j < L; ++j) { const u32 f = dlut[sp[j]]; ph |= f; bad |= f ? 0u : 1u; }
     }
-    if (nul) err = E_UNSUPPORTED;
+    u32 xfer = 0, namb = 0;
+    if (bad) { /* some base is not A/C/G/T: decide the ambiguity transfer (phyNGSC.cpp:549-588) */
+      bool ok = true, nul = false;
+      ph = 0;
+      for (j = 0; j < L; ++j) {
+        const u8 c = sp[j], q = qp[j];
+        const u32 f = dlut[c];
+        if (f) ph |= f;
+        else { ++namb; nul = nul || c == 0; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; }
+      }
+      xfer = (namb && ok) ? 1u : 0u;
+      if (!xfer) for (j = 0; j < L; ++j) { const u8 c = sp[j]; if (!dlut[c]) atomicAdd(&S.dna[c], 1u); }
+      if (nul) err = E_UNSUPPORTED;
+    }
+    ph |= ph >> 16; ph |= ph >> 8;
+    pres = ph & 0xFu;
     kept = xfer ? L - namb : L; myL = L;
     d.kx[r] = (u16)(kept | (xfer << 15));
   }
@@ -449,8 +468,8 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     if (lane == 0) {
       if (pr & 1u) S.dna['A'] = 1;
       if (pr & 2u) S.dna['C'] = 1;
-      if (pr & 4u) S.dna['G'] = 1;
-      if (pr & 8u) S.dna['T'] = 1;
+      if (pr & 4u) S.dna['T'] = 1;
+      if (pr & 8u) S.dna['G'] = 1;
       atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms); atomicMax(&S.inv_minq, iq);
     }
   }
@@ -540,12 +559,6 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     if (S.err) atomicMin(&A->status, S.err);
     atomicMax(&A->max_qlen, S.maxq); atomicMax(&A->max_slen, S.maxs); atomicMax(&A->inv_min_qlen, S.inv_minq);
   }
-  if (tid < 8) {
-    u32 m = 0;
-    for (u32 k = 0; k < 32; ++k) m |= S.qflag[tid * 32 + k] ? 1u << k : 0u;
-    if (tid == 0 && (m & 1u)) atomicMin(&A->status, (i32)E_UNSUPPORTED); /* NUL quality byte */
-    if (m) atomicOr(&A->qpresent[tid], m);
-  }
   for (u32 i = tid; i < 256; i += CH) if (S.dna[i]) atomicAdd(&A->dna_occ[i], S.dna[i]);
   if (seed_ok)
     for (u32 i = tid; i < nf * 8; i += CH) {
@@ -560,6 +573,8 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     }
 }
 
+__device__ __forceinline__ u32 *raw_table(const Dev &d, u32 s) { return d.arena + (size_t)(s + 1) * d.arena_words - RAW_WORDS; }
+
 /* min / max of the numeric deltas that cross a chunk boundary (tasks.cpp:149-166 runs over all records) */
 __global__ void __launch_bounds__(128) k_xdelta(Dev d) {
   __shared__ u32 mx[MAXF], mn[MAXF], nf_s;
@@ -567,6 +582,12 @@ __global__ void __launch_bounds__(128) k_xdelta(Dev d) {
   const SbPlan P = d.plans[s];
   SbAcc *A = d.acc + s;
   if (P.status || A->status) return;
+  { /* the raw per-position quality table of k_qhist: rows 0..max_qlen of 256 counters */
+    if (A->max_qlen + 1 > RAW_ROWS) { if (tid == 0) atomicMin(&A->status, (i32)E_UNSUPPORTED); return; }
+    uint4 *raw = (uint4 *)raw_table(d, s);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (u32 i = tid; i < (A->max_qlen + 1) * 64; i += 128) raw[i] = z;
+  }
   const u32 nchunk = (P.n_records + CH - 1) / CH;
   if (tid < MAXF) { mx[tid] = 0; mn[tid] = 0; }
   if (tid == 0) nf_s = min((u32)MAXF, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
@@ -582,29 +603,49 @@ __global__ void __launch_bounds__(128) k_xdelta(Dev d) {
   if (tid < nf) { if (mx[tid]) atomicMax(&A->f[tid].kmax_d, mx[tid]); if (mn[tid]) atomicMax(&A->f[tid].kinvmin_d, mn[tid]); }
 }
 
-/* geometry of k_qhist's private histogram copies (see there) */
-__device__ __forceinline__ u32 qh_row_words(u32 nq) { return ((nq + 1) / 2) | 1u; }
-__device__ __forceinline__ u32 qh_slots(u32 Lp) { return Lp <= 256 ? 256 / Lp : 1u; }
-
 /* ---- classify + zero ------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(32) k_classify(Dev d) {
   u32 s = blockIdx.x;
-  if (threadIdx.x != 0) return;
   const SbPlan P = d.plans[s];
   SbClass &C = d.cls[s];
+  if (!P.status && !d.acc[s].status) { /* quality alphabet = the bytes counted by k_qhist (row 0 of the raw table holds the totals) */
+    u32 *raw = raw_table(d, s);
+    const u32 rows = d.acc[s].max_qlen;
+    u32 tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (u32 p = 1; p <= rows; ++p) {
+#pragma unroll
+      for (u32 k = 0; k < 8; ++k) tot[k] += raw[p * 256 + k * 32 + threadIdx.x];
+    }
+#pragma unroll
+    for (u32 k = 0; k < 8; ++k) {
+      raw[k * 32 + threadIdx.x] = tot[k]; /* row 0: quality_stats[0] (tasks.cpp:281) */
+      const u32 m = __ballot_sync(0xFFFFFFFFu, tot[k] != 0);
+      if (threadIdx.x == 0) d.acc[s].qpresent[k] = m;
+    }
+    if (threadIdx.x == 0 && (d.acc[s].qpresent[0] & 1u)) d.acc[s].status = E_UNSUPPORTED; /* NUL quality byte */
+    __syncwarp();
+  }
+  if (threadIdx.x != 0) return;
   if (P.status) { C.status = P.status; C.R = P.n_records; C.payload_len = 0; return; }
   u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
-  classify_subblock(d.in, g_char_lut, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words, C);
+  classify_subblock(d.in, g_char_lut, d.acc[s], P.n_records, ts0, te0, d.arena + (size_t)s * d.arena_words, d.arena_words - RAW_WORDS, C);
   C.payload_len = 0;
-  if (!C.status) { atomicMax(&d.hdr->max_qh_words, qh_slots(C.max_qlen) * C.max_qlen * qh_row_words(C.nq)); atomicMax(&d.hdr->max_pk_bytes, (C.max_qlen + 1) * C.nq * 2u); }
+  if (!C.status) atomicMax(&d.hdr->max_pk_bytes, (C.max_qlen + 1) * C.nq * 2u);
 }
 
+/* Clears the title / DNA histograms and fills the per-position quality frequency tables (tasks.cpp:260-286:
+ * quality_stats[p][qua_code[q]]) from the raw table: column q of row p becomes entry qua_code[q] of table p. */
 __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
   u32 s = blockIdx.y;
   const SbClass &C = d.cls[s];
   if (C.status) return;
   u32 *a = d.arena + (size_t)s * d.arena_words;
-  for (u32 i = C.zero_begin + blockIdx.x * 256 + threadIdx.x; i < C.zero_end; i += gridDim.x * 256) a[i] = 0;
+  const u32 *raw = raw_table(d, s);
+  const u32 nq = C.nq, nqs = (C.max_qlen + 1) * nq; /* the quality tables are the first words of the zeroed range */
+  for (u32 i = C.zero_begin + blockIdx.x * 256 + threadIdx.x; i < C.zero_end; i += gridDim.x * 256) {
+    const u32 k = i - C.qstat_off;
+    a[i] = k < nqs ? raw[(k / nq) * 256 + C.quals[k % nq]] : 0u;
+  }
 }
 
 /* Exact DNA symbol counts (sym_stats, tasks.cpp:233-236), needed only when more than four symbols force
@@ -632,86 +673,133 @@ __global__ void __launch_bounds__(256) k_dnacount(Dev d) {
 }
 
 /* ---- per-position quality histogram (tasks.cpp:260-286) ----------------------------------------------------- */
-/* Row (position) p of a private histogram copy is owned by exactly one thread, so the increments need no atomics;
- * the CTA flushes its non-zero counters to the subblock's table with atomicAdd at the end.  A CTA counts at most
- * QCH = 1024 records, so the private counters are 16 bits wide; a row is (n_qualities + 1) / 2 | 1 words (odd, so
- * that the rows of neighbouring positions start in different banks).  Each thread keeps eight records in flight:
- * the quality bytes come straight from global memory and their latency is what the loop waits for. */
-
+/* Runs BEFORE the classification: it counts raw quality bytes (after the ambiguity transfer, phyNGSC.cpp:575-580)
+ * per read position into the subblock's raw table raw[position + 1][byte] (row 0 = totals); the quality alphabet
+ * and the coded tables are derived from it afterwards (k_classify, k_zero_hist).
+ * Row (position) p of a private copy in shared memory is owned by exactly one thread, so the increments need no
+ * atomics.  A CTA counts at most QCH = 1024 records, so the private counters are 16 bits wide; a private row holds
+ * the bytes 33..128 (anything else -- transferred ambiguity codes, garbage -- goes straight to the global table).
+ * `slots` copies of the rows work on different records.  The records are first split into a plain list and the
+ * (rare) list of records with an ambiguity transfer; the plain loop keeps eight quality bytes in flight per thread
+ * and has no per-symbol test at all when every plain record is at least as long as the row range. */
 __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ u32 m_qs[QCH];
-  __shared__ u16 m_len[QCH]; /* read length | ambiguity-transfer flag << 15 */
-  __shared__ __align__(16) u8 qcode[256];
+  __shared__ u32 m_qs[QCH + 64];   /* start of the quality line: plain records from the front (padded with dummies), */
+  __shared__ u16 m_len[QCH + 64];  /* records with an ambiguity transfer from the back                                */
+  __shared__ u32 n_plain, n_x, min_len;
   const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-  const SbClass &C = d.cls[s];
-  if (C.status || chunk * QCH >= C.R) return;
   const SbPlan P = d.plans[s];
-  const u32 r0 = P.first_rec + chunk * QCH, nrec = min((u32)QCH, C.R - chunk * QCH);
-  const u32 Lp = C.max_qlen, nq = C.nq, rw = qh_row_words(nq), rh = rw * 2;
-  u32 *gq = d.arena + (size_t)s * d.arena_words + C.qstat_off;
-  for (u32 i = tid; i < 64; i += 256) ((u32 *)qcode)[i] = ((const u32 *)C.qua_code)[i];
-  for (u32 i = tid; i < nrec; i += 256) {
-    u32 te = d.te[r0 + i], se = d.se[r0 + i];
-    m_qs[i] = se + 3; m_len[i] = (u16)((se - te - 1) | (d.kx[r0 + i] & 0x8000u));
+  if (P.status || d.acc[s].status || chunk * QCH >= P.n_records) return;
+  const u32 r0 = P.first_rec + chunk * QCH, nrec = min((u32)QCH, P.n_records - chunk * QCH);
+  const u32 Lp = d.acc[s].max_qlen;
+  u32 *raw = raw_table(d, s);
+  if (tid == 0) { n_plain = 0; n_x = 0; min_len = 0xFFFFFFFFu; }
+  __syncthreads();
+  for (u32 i0 = 0; i0 < nrec; i0 += 256) { /* one shared-memory atomic per warp and list */
+    const u32 i = i0 + tid, lane = tid & 31;
+    const bool on = i < nrec;
+    u32 te = 0, se = 0; bool x = false;
+    if (on) { te = d.te[r0 + i]; se = d.se[r0 + i]; x = d.kx[r0 + i] & 0x8000u; }
+    const u32 bx = __ballot_sync(0xFFFFFFFFu, on && x), bp = __ballot_sync(0xFFFFFFFFu, on && !x);
+    u32 basex = 0, basep = 0;
+    if (lane == 0) { if (bx) basex = atomicAdd(&n_x, (u32)__popc(bx)); if (bp) basep = atomicAdd(&n_plain, (u32)__popc(bp)); }
+    basex = __shfl_sync(0xFFFFFFFFu, basex, 0); basep = __shfl_sync(0xFFFFFFFFu, basep, 0);
+    if (on) {
+      const u32 below = (1u << lane) - 1u;
+      const u32 k = x ? QCH + 63 - (basex + __popc(bx & below)) : basep + __popc(bp & below);
+      m_qs[k] = se + 3; m_len[k] = (u16)(se - te - 1);
+    }
+  }
+  __syncthreads();
+  if (Lp == 0) return;
+  const u32 RP = Lp < 250 ? Lp : 250;            /* rows per pass (250 rows fill the 48 KB) */
+  u32 slots = 256 / RP;
+  { const u32 fit = QH_SMEM / (RP * QR_ROWW * 4); if (slots > fit) slots = fit; }
+  const u32 np = n_plain, nx = n_x;
+  {
+    u32 ml = 0xFFFFFFFFu;
+    for (u32 i = tid; i < np; i += 256) ml = min(ml, (u32)m_len[i]);
+    ml = __reduce_min_sync(0xFFFFFFFFu, ml);
+    if ((tid & 31) == 0 && ml != 0xFFFFFFFFu) atomicMin(&min_len, ml);
+    const u32 np_pad = (np + 8 * slots - 1) / (8 * slots) * (8 * slots);
+    for (u32 i = np + tid; i < np_pad; i += 256) { m_qs[i] = m_qs[0]; m_len[i] = 0; } /* dummies: a valid address, no symbols */
   }
   u16 *hist = (u16 *)dyn_smem;
-  u32 slots = qh_slots(Lp);
-  const u32 fit = d.qh_bytes / (Lp * rw * 4);
-  if (slots > fit) slots = fit;
-  if (slots == 0) { /* rows do not fit in shared memory: count straight into the global table */
+  const u32 slot = tid / RP, p = tid % RP;
+  const bool owner = slot < slots;
+  u16 *row = hist + (slot * RP + p) * (QR_ROWW * 2);
+  for (u32 p0 = 0; p0 < Lp; p0 += RP) {
+    for (u32 i = tid; i < slots * RP * QR_ROWW; i += 256) ((u32 *)hist)[i] = 0;
     __syncthreads();
-    for (u32 i = 0; i < nrec; ++i) {
-      const u32 qs = m_qs[i], L = m_len[i] & 0x7FFFu;
-      for (u32 p = tid; p < L; p += 256) {
-        u32 q = d.in[qs + p];
-        if (m_len[i] & 0x8000u) q += g_xq_lut[d.in[qs - 3 - L + p]];
-        const u32 c = qcode[q];
-        atomicAdd(&gq[(p + 1) * nq + c], 1u); atomicAdd(&gq[c], 1u);
-      }
-    }
-    return;
-  }
-  for (u32 i = tid; i < slots * Lp * rw; i += 256) ((u32 *)hist)[i] = 0;
-  __syncthreads();
-  if (Lp <= 256) {
-    const u32 slot = tid / Lp, p = tid % Lp;
-    if (slot < slots) {
-      u16 *row = hist + (slot * Lp + p) * rh;
-      const u8 *src = d.in + p;
-      for (u32 i0 = slot; i0 < nrec; i0 += 8 * slots) {
-        u32 q[8], ml[8]; /* quality byte (or none), read length | transfer flag */
+    const u32 pos = p0 + p;
+    if (owner) {
+      const u8 *src = d.in + pos;
+      u32 *grow = raw + (pos + 1) * 256;
+      if (min_len >= p0 + RP) { /* every plain record covers this row range (dummies excepted: they end the list) */
+        const u32 full = np / (8 * slots) * (8 * slots);
+        for (u32 i0 = slot; i0 < full; i0 += 8 * slots) {
+          u32 q[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 8; ++k) q[k] = __ldg(src + m_qs[i0 + k * slots]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const u32 c = q[k] - 33u;
+            if (c < QR_COLS) row[c]++;
+            else atomicAdd(grow + q[k], 1u);
+          }
+        }
+        for (u32 i = full + slot; i < np; i += slots) {
+          const u32 qq = __ldg(src + m_qs[i]), c = qq - 33u;
+          if (c < QR_COLS) row[c]++;
+          else atomicAdd(grow + qq, 1u);
+        }
+      } else {
+        for (u32 i0 = slot; i0 < np; i0 += 8 * slots) {
+          u32 q[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const u32 i = i0 + k * slots;
+            q[k] = pos < (u32)m_len[i] ? (u32)__ldg(src + m_qs[i]) : 0xFFFFFFFFu;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (q[k] == 0xFFFFFFFFu) continue;
+            const u32 c = q[k] - 33u;
+            if (c < QR_COLS) row[c]++;
+            else atomicAdd(grow + q[k], 1u);
+          }
+        }
+      }
+      /* ambiguity-transfer records: the base under a transferred quality byte selects the offset */
+      for (u32 i0 = slot; i0 < nx; i0 += 4 * slots) {
+        u32 q[4], c4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
           const u32 i = i0 + k * slots;
-          ml[k] = i < nrec ? (u32)m_len[i] : 0u;
-          q[k] = p < (ml[k] & 0x7FFFu) ? (u32)__ldg(src + m_qs[i]) : 0xFFFFFFFFu;
+          q[k] = 0xFFFFFFFFu; c4[k] = 0;
+          if (i < nx) {
+            const u32 L = m_len[QCH + 63 - i], qs = m_qs[QCH + 63 - i];
+            if (pos < L) { q[k] = __ldg(src + qs); c4[k] = __ldg(src + qs - 3 - L); }
+          }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           if (q[k] == 0xFFFFFFFFu) continue;
-          u32 qq = q[k];
-          if (ml[k] & 0x8000u) qq += g_xq_lut[d.in[m_qs[i0 + k * slots] - 3 - (ml[k] & 0x7FFFu) + p]];
-          row[qcode[qq]]++;
+          const u32 qq = q[k] + g_xq_lut[c4[k]], c = qq - 33u;
+          if (c < QR_COLS) row[c]++;
+          else atomicAdd(grow + qq, 1u);
         }
       }
     }
-  } else { /* reads longer than 256: thread t owns rows t, t + 256, ... of the single copy */
-    for (u32 i = 0; i < nrec; ++i) {
-      const u32 L = m_len[i] & 0x7FFFu, qs = m_qs[i];
-      for (u32 p = tid; p < L; p += 256) {
-        u32 q = d.in[qs + p];
-        if (m_len[i] & 0x8000u) q += g_xq_lut[d.in[qs - 3 - L + p]];
-        hist[p * rh + qcode[q]]++;
-      }
+    __syncthreads();
+    const u32 rows = min(RP, Lp - p0);
+    for (u32 i = tid; i < rows * QR_COLS; i += 256) {
+      const u32 pr = i / QR_COLS, c = i % QR_COLS;
+      u32 v = 0;
+      for (u32 k = 0; k < slots; ++k) v += hist[(k * RP + pr) * (QR_ROWW * 2) + c];
+      if (v) atomicAdd(raw + (p0 + pr + 1) * 256 + 33 + c, v);
     }
-  }
-  __syncthreads();
-  for (u32 i = tid; i < Lp * nq; i += 256) {
-    const u32 p = i / nq, c = i % nq;
-    u32 v = 0;
-    for (u32 k = 0; k < slots; ++k) v += hist[(k * Lp + p) * rh + c];
-    if (v) { atomicAdd(&gq[(p + 1) * nq + c], v); atomicAdd(&gq[c], v); }
+    __syncthreads();
   }
 }
 

@@ -35,3 +35,14 @@ for i in range(2):
     d, o, res = ctx.compress_region(pin.array, prm, out=pout.array)
     dt = time.perf_counter() - t
     print(f"e2e pinned run {i}: {dt * 1e3:.2f} ms wall  {data.size / dt / 1e9:.2f} GB/s  (h2d {res.h2d_ms:.2f} k {res.kernel_ms:.2f} d2h {res.d2h_ms:.2f})")
+
+if os.environ.get("PROBE_E2E_SWEEP"):
+    for bmb in (32, 64, 128, 256):
+        cx = api.Context(0, max_batch_bytes=bmb << 20, max_subblocks=(bmb << 20) // (4 << 20) + 16)
+        best = 1e9
+        for i in range(4):
+            t = time.perf_counter()
+            d, o, res = cx.compress_region(pin.array, prm, out=pout.array)
+            best = min(best, time.perf_counter() - t)
+        print(f"e2e batch {bmb:4d} MiB: best {best * 1e3:.2f} ms  {data.size / best / 1e9:.2f} GB/s  batches {res.n_batches} (h2d {res.h2d_ms:.2f} k {res.kernel_ms:.2f} d2h {res.d2h_ms:.2f})")
+        cx.close()
