@@ -61,6 +61,7 @@ struct phy_ctx {
   } while (0)
 
 static const u32 SPAN_MAX = 96 * 1024;
+static const u32 QH_DYN_MAX = 200 * 1024; /* private rows + span buffers of k_qhist */
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
 static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "qhist", "classify", "zero_hist",
@@ -176,7 +177,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   }
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
-  CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_SMEM));
+  CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_DYN_MAX));
   CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
@@ -246,7 +247,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
   k_nl_emit<<<d.ntiles, 256, 0, st>>>(d); PMARK();
   k_plan<<<1, 32, 0, st>>>(d);
-  k_spanmax<<<ctx->max_sb, 256, 0, st>>>(d); PMARK();
+  k_spanmax<<<dim3(8, ctx->max_sb), 256, 0, st>>>(d); PMARK();
   ctx->launches += 5;
   CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_state, ctx->plan_state, sizeof(PlanState), cudaMemcpyDeviceToHost, st));
@@ -265,10 +266,26 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
   dim3 gc(H.max_chunks, S);
+  u32 qh_dyn = 0;
   PMARK();
   k_stat1<<<gc, CH, span_v, st>>>(d);
   k_xdelta<<<S, 128, 0, st>>>(d); PMARK();
-  k_qhist<<<dim3(H.max_qchunks, S), 256, QH_SMEM, st>>>(d); PMARK();
+  { /* k_qhist: private table of min(longest read, 256) rows beside two stage buffers.  Long records are staged in
+     * groups of 64 or 32 instead of 128 so that two CTAs still fit an SM (fewer, larger groups beat more CTAs: the
+     * per-group barriers and list building are what a CTA spends its time on besides counting). */
+    static const u32 budget = getenv("PHY_QH_KB") ? (u32)atoi(getenv("PHY_QH_KB")) * 1024u : 112u * 1024; /* two CTAs per SM */
+    d.qh_rows = H.max_len < 1 ? 1u : H.max_len > 256 ? 256u : H.max_len;
+    const u32 hb = (d.qh_rows * QR_ROWW * 4 + 15u) & ~15u;
+    const u32 spans[3] = {span, (H.max_span64 + 16 + 1023) & ~1023u, (H.max_span32 + 16 + 1023) & ~1023u};
+    int pick = 0;
+    while (pick < 2 && hb + 2 * spans[pick] > budget) ++pick;
+    d.qh_recs = 128u >> pick; d.qh_stage = spans[pick] > SPAN_MAX ? SPAN_MAX : spans[pick];
+    u32 nb = 2;
+    if (hb + nb * d.qh_stage > QH_DYN_MAX) nb = 1;
+    d.qh_nbuf = nb;
+    qh_dyn = hb + d.qh_nbuf * d.qh_stage;
+  }
+  k_qhist<<<dim3(H.max_qchunks, S), 256, qh_dyn, st>>>(d); PMARK();
   k_classify<<<S, 32, 0, st>>>(d); PMARK();
   /* the batch header now holds the exact size of the packed quality tables: fetch it on a side stream while the
    * statistics kernels run, so that the encoder kernels get exactly the shared memory they need */

@@ -33,11 +33,8 @@ namespace phy {
 constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
 constexpr int TILE = 16384;        /* bytes per newline-index tile (256 threads x 64 bytes)                */
 constexpr int SUPER = 64;          /* tiles per supertile: the single-CTA scan runs over supertiles         */
-constexpr int QCH = 1024;          /* records per quality-histogram work item                              */
-constexpr u32 QH_SMEM = 48 * 1024; /* private histogram rows of one quality-histogram CTA                          */
-constexpr u32 QR_COLS = 96;        /* columns of a private row: quality bytes 33..128, 16-bit counters              */
-constexpr u32 QR_ROWW = 49;        /* words per private row (96 counters + one pad word: odd, so that the rows of
-                                      neighbouring positions start in different banks)                             */
+constexpr int QCH = 2048;          /* records per quality-histogram work item (16 chunks)                  */
+constexpr u32 QR_ROWW = 97;        /* words per row of k_qhist's private table (odd: neighbouring rows start in different banks) */
 constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
 constexpr int EMIT_MIN_CTAS = 6;   /* register budget of k_emit: 65536 / (256 * 6) = 42 */
@@ -54,6 +51,8 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_qchunks;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
+  u32 max_len;         /* longest sequence line of the batch's subblocks */
+  u32 max_span64, max_span32; /* widest 64- / 32-record span (k_qhist may stage smaller groups than the 128-record chunk) */
 };
 
 struct SbOut {         /* device -> host, one per subblock */
@@ -76,6 +75,9 @@ struct Dev {
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
   u32 pk_bytes;               /* shared memory behind the span for the packed quality code tables */
+  u32 qh_nbuf;                /* span buffers (pipeline stages) of a k_qhist CTA, 1..8 */
+  u32 qh_rows;                /* rows of a k_qhist CTA's private table */
+  u32 qh_recs, qh_stage;      /* records per pipeline stage of k_qhist (128, 64 or 32) and the bytes of a stage buffer */
   u32 tune;                   /* experiment switches (PHY_TUNE): bit0 = stat2 reads titles straight from global memory */
 };
 
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -322,19 +324,26 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
 /* Exact shared-memory needs of the per-record kernels: the widest 128-record span (plus the record before
  * it) and the largest field count over all subblocks of the batch. */
 __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
-  const u32 s = blockIdx.x;
+  const u32 s = blockIdx.y;
   if (s >= d.hdr->S) return; /* launched for the context's capacity: the host learns S only afterwards */
   const SbPlan P = d.plans[s];
   if (P.status) return;
-  u32 mx = 0;
-  for (u32 c = threadIdx.x; c * CH < P.n_records; c += 256) {
-    u32 r0 = P.first_rec + c * CH, nrec = min((u32)CH, P.n_records - c * CH);
-    u32 lo = d.rstart[r0] & ~15u;
-    mx = max(mx, d.rstart[r0 + nrec] - lo);
+  u32 mx = 0, m64 = 0, m32 = 0, ml = 0;
+  for (u32 g = blockIdx.x * 256 + threadIdx.x; g * 32 < P.n_records; g += gridDim.x * 256) { /* 32-record groups */
+    const u32 i = g * 32, r0 = P.first_rec + i, n = P.n_records;
+    const u32 lo = d.rstart[r0] & ~15u;
+    m32 = max(m32, d.rstart[P.first_rec + min(i + 32, n)] - lo);
+    if ((g & 1u) == 0) m64 = max(m64, d.rstart[P.first_rec + min(i + 64, n)] - lo);
+    if ((g & 3u) == 0) mx = max(mx, d.rstart[P.first_rec + min(i + CH, n)] - lo);
   }
-  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) ml = max(ml, d.se[P.first_rec + i] - d.te[P.first_rec + i] - 1);
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx); m64 = __reduce_max_sync(0xFFFFFFFFu, m64); m32 = __reduce_max_sync(0xFFFFFFFFu, m32);
+  ml = __reduce_max_sync(0xFFFFFFFFu, ml);
   if ((threadIdx.x & 31) == 0 && mx) atomicMax(&d.hdr->max_span, mx);
-  if (threadIdx.x == 0) atomicMax(&d.hdr->max_nf, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
+  if ((threadIdx.x & 31) == 0 && m64) atomicMax(&d.hdr->max_span64, m64);
+  if ((threadIdx.x & 31) == 0 && m32) atomicMax(&d.hdr->max_span32, m32);
+  if ((threadIdx.x & 31) == 0 && ml) atomicMax(&d.hdr->max_len, ml);
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&d.hdr->max_nf, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
 }
 
 /* ---- record spans in shared memory ------------------------------------------------------------------- */
@@ -678,128 +687,171 @@ __global__ void __launch_bounds__(256) k_dnacount(Dev d) {
  * and the coded tables are derived from it afterwards (k_classify, k_zero_hist).
  * Row (position) p of a private copy in shared memory is owned by exactly one thread, so the increments need no
  * atomics.  A CTA counts at most QCH = 1024 records, so the private counters are 16 bits wide; a private row holds
- * the bytes 33..128 (anything else -- transferred ambiguity codes, garbage -- goes straight to the global table).
+ * the bytes 33..127 (anything else -- transferred ambiguity codes, garbage -- goes straight to the global table).
  * `slots` copies of the rows work on different records.  The records are first split into a plain list and the
  * (rare) list of records with an ambiguity transfer; the plain loop keeps eight quality bytes in flight per thread
  * and has no per-symbol test at all when every plain record is at least as long as the row range. */
+/* ---- bulk-copy span pipeline ------------------------------------------------------------------------------------ */
+/* A CTA that walks several 128-record chunks streams their bytes into shared memory with the bulk-copy engine
+ * (cp.async.bulk, one request per chunk issued by one thread, completion counted on an mbarrier), double-buffered so
+ * that the next chunk arrives while the current one is processed.  No thread spends instructions on the copy. */
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  u32 ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 20)) __trap(); /* a lost copy must not hang the GPU */
+  } while (!ok);
+}
+/* one thread: request bytes [lo & ~15, hi) of the batch (rounded up to 16) into `dst` (shared address, 16-byte aligned) */
+__device__ __forceinline__ void span_request(const u8 *in, u32 lo, u32 hi, u32 dst, u32 bar) {
+  const u32 alo = lo & ~15u, n = (hi - alo + 15u) & ~15u;
+  mbar_expect_tx(bar, n);
+  bulk_g2s(dst, in + alo, n, bar);
+}
+
+constexpr int QU = 8;          /* records in flight per thread */
+__device__ __forceinline__ u32 lds_u8(u32 addr) { u16 v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sm_red_inc(u32 addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
+/* dynamic shared memory: [qh_rows * QR_ROWW words: the CTA's private table][qh_nbuf span buffers] */
 __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ u32 m_qs[QCH + 64];   /* start of the quality line: plain records from the front (padded with dummies), */
-  __shared__ u16 m_len[QCH + 64];  /* records with an ambiguity transfer from the back                                */
-  __shared__ u32 n_plain, n_x, min_len;
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  __shared__ __align__(8) u64 bars[8];
+  __shared__ u32 m_qs[CH + 64];  /* shared-memory address of the quality line: plain records from the front (padded with */
+  __shared__ u16 m_len[CH + 64]; /* dummies), records with an ambiguity transfer from the back                           */
+  __shared__ u32 n_plain, n_x;
+  __shared__ u32 c_lo[QCH / 32 + 1]; /* first byte of each of the CTA's record groups (and the end of the last) */
+  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const SbPlan P = d.plans[s];
-  if (P.status || d.acc[s].status || chunk * QCH >= P.n_records) return;
-  const u32 r0 = P.first_rec + chunk * QCH, nrec = min((u32)QCH, P.n_records - chunk * QCH);
+  if (P.status || d.acc[s].status) return;
+  const u32 QS = d.qh_recs; /* records per pipeline stage */
+  const u32 nchunk = (P.n_records + QS - 1) / QS, c0 = blockIdx.x * (QCH / QS), c1 = min(c0 + QCH / QS, nchunk);
+  if (c0 >= nchunk) return;
+  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * QS, P.n_records)];
   const u32 Lp = d.acc[s].max_qlen;
-  u32 *raw = raw_table(d, s);
-  if (tid == 0) { n_plain = 0; n_x = 0; min_len = 0xFFFFFFFFu; }
-  __syncthreads();
-  for (u32 i0 = 0; i0 < nrec; i0 += 256) { /* one shared-memory atomic per warp and list */
-    const u32 i = i0 + tid, lane = tid & 31;
-    const bool on = i < nrec;
-    u32 te = 0, se = 0; bool x = false;
-    if (on) { te = d.te[r0 + i]; se = d.se[r0 + i]; x = d.kx[r0 + i] & 0x8000u; }
-    const u32 bx = __ballot_sync(0xFFFFFFFFu, on && x), bp = __ballot_sync(0xFFFFFFFFu, on && !x);
-    u32 basex = 0, basep = 0;
-    if (lane == 0) { if (bx) basex = atomicAdd(&n_x, (u32)__popc(bx)); if (bp) basep = atomicAdd(&n_plain, (u32)__popc(bp)); }
-    basex = __shfl_sync(0xFFFFFFFFu, basex, 0); basep = __shfl_sync(0xFFFFFFFFu, basep, 0);
-    if (on) {
-      const u32 below = (1u << lane) - 1u;
-      const u32 k = x ? QCH + 63 - (basex + __popc(bx & below)) : basep + __popc(bp & below);
-      m_qs[k] = se + 3; m_len[k] = (u16)(se - te - 1);
-    }
-  }
-  __syncthreads();
   if (Lp == 0) return;
-  const u32 RP = Lp < 250 ? Lp : 250;            /* rows per pass (250 rows fill the 48 KB) */
-  u32 slots = 256 / RP;
-  { const u32 fit = QH_SMEM / (RP * QR_ROWW * 4); if (slots > fit) slots = fit; }
-  const u32 np = n_plain, nx = n_x;
-  {
-    u32 ml = 0xFFFFFFFFu;
-    for (u32 i = tid; i < np; i += 256) ml = min(ml, (u32)m_len[i]);
-    ml = __reduce_min_sync(0xFFFFFFFFu, ml);
-    if ((tid & 31) == 0 && ml != 0xFFFFFFFFu) atomicMin(&min_len, ml);
-    const u32 np_pad = (np + 8 * slots - 1) / (8 * slots) * (8 * slots);
-    for (u32 i = np + tid; i < np_pad; i += 256) { m_qs[i] = m_qs[0]; m_len[i] = 0; } /* dummies: a valid address, no symbols */
-  }
-  u16 *hist = (u16 *)dyn_smem;
+  u32 *raw = raw_table(d, s);
+  const u32 RP = Lp < d.qh_rows ? Lp : d.qh_rows;  /* rows (read positions) per pass */
+  const u32 slots = RP < 256 ? 256 / RP : 1u;      /* records the CTA counts side by side */
+  u32 *hist = (u32 *)dyn_smem;
+  const u32 nbuf = d.qh_nbuf;
+  const u32 hist_a = (u32)__cvta_generic_to_shared(hist), buf_a0 = hist_a + ((d.qh_rows * (QR_ROWW * 4) + 15u) & ~15u), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);
+  if (tid == 0) { for (u32 k = 0; k < nbuf; ++k) mbar_init(bar_a0 + 8 * k, 1); mbar_fence_init(); }
+  /* one thread: request chunk c into stage (c - c0) % nbuf */
+  auto request = [&](u32 c) {
+    const u32 st = (c - c0) % nbuf;
+    span_request(d.in, c_lo[c - c0], c_lo[c - c0 + 1], buf_a0 + st * d.qh_stage, bar_a0 + 8 * st);
+  };
   const u32 slot = tid / RP, p = tid % RP;
   const bool owner = slot < slots;
-  u16 *row = hist + (slot * RP + p) * (QR_ROWW * 2);
+  u32 phases = 0; /* bit b: parity to wait for on barrier b */
+  /* row p of the private table: counters 0..94 = bytes 33..127, 95 = "some other byte" (those go to the global table one
+   * by one), 96 = no symbol.  Rows are QR_ROWW = 97 words apart, so the 32 positions a warp works on fall into 32 banks. */
   for (u32 p0 = 0; p0 < Lp; p0 += RP) {
-    for (u32 i = tid; i < slots * RP * QR_ROWW; i += 256) ((u32 *)hist)[i] = 0;
-    __syncthreads();
-    const u32 pos = p0 + p;
-    if (owner) {
-      const u8 *src = d.in + pos;
-      u32 *grow = raw + (pos + 1) * 256;
-      if (min_len >= p0 + RP) { /* every plain record covers this row range (dummies excepted: they end the list) */
-        const u32 full = np / (8 * slots) * (8 * slots);
-        for (u32 i0 = slot; i0 < full; i0 += 8 * slots) {
-          u32 q[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) q[k] = __ldg(src + m_qs[i0 + k * slots]);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const u32 c = q[k] - 33u;
-            if (c < QR_COLS) row[c]++;
-            else atomicAdd(grow + q[k], 1u);
-          }
+    for (u32 i = tid; i < RP * QR_ROWW; i += 256) hist[i] = 0;
+    __syncthreads(); /* also: barriers initialised, c_lo filled, previous pass has left the buffers */
+    if (tid == 0) for (u32 c = c0; c < c1 && c < c0 + (nbuf > 1 ? nbuf - 1 : 1u); ++c) request(c); /* fill the pipeline */
+    /* this thread's record of the first chunk */
+    u32 te = 0, se = 0, kx = 0;
+    { const u32 i = c0 * QS + tid; if (tid < QS && i < P.n_records) { te = d.te[P.first_rec + i]; se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; } }
+    for (u32 c = c0; c < c1; ++c) {
+      const u32 b = (c - c0) % nbuf;
+      const u32 buf_b = buf_a0 + b * d.qh_stage, bar_b = bar_a0 + 8 * b;
+      const u32 nrec = min(QS, P.n_records - c * QS);
+      if (tid == 0) { n_plain = 0; n_x = 0; }
+      if (nbuf > 1 && tid == 0 && c + nbuf - 1 < c1) request(c + nbuf - 1); /* into the stage that iteration c-1 has left */
+      const u32 alo = c_lo[c - c0] & ~15u;
+      __syncthreads();
+      /* record lists of this chunk (order is irrelevant for a histogram) */
+      bool covers = true;
+      if (tid < ((QS + 31u) & ~31u)) {
+        const bool on = tid < nrec, x = on && (kx & 0x8000u);
+        const u32 L = se - te - 1;
+        const u32 bx = __ballot_sync(0xFFFFFFFFu, x), bp = __ballot_sync(0xFFFFFFFFu, on && !x);
+        u32 basex = 0, basep = 0;
+        if (lane == 0) { if (bx) basex = atomicAdd(&n_x, (u32)__popc(bx)); if (bp) basep = atomicAdd(&n_plain, (u32)__popc(bp)); }
+        basex = __shfl_sync(0xFFFFFFFFu, basex, 0); basep = __shfl_sync(0xFFFFFFFFu, basep, 0);
+        if (on) {
+          const u32 below = (1u << lane) - 1u;
+          const u32 k = x ? CH + 63 - (basex + __popc(bx & below)) : basep + __popc(bp & below);
+          m_qs[k] = buf_b + (se + 3 - alo); m_len[k] = (u16)L;
+          covers = x || L >= p0 + RP;
         }
-        for (u32 i = full + slot; i < np; i += slots) {
-          const u32 qq = __ldg(src + m_qs[i]), c = qq - 33u;
-          if (c < QR_COLS) row[c]++;
-          else atomicAdd(grow + qq, 1u);
-        }
-      } else {
-        for (u32 i0 = slot; i0 < np; i0 += 8 * slots) {
-          u32 q[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const u32 i = i0 + k * slots;
-            q[k] = pos < (u32)m_len[i] ? (u32)__ldg(src + m_qs[i]) : 0xFFFFFFFFu;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (q[k] == 0xFFFFFFFFu) continue;
-            const u32 c = q[k] - 33u;
-            if (c < QR_COLS) row[c]++;
-            else atomicAdd(grow + q[k], 1u);
-          }
-        }
+        /* next chunk's record, in flight while this chunk is counted */
+        const u32 i = (c + 1) * QS + tid;
+        te = se = kx = 0;
+        if (tid < QS && c + 1 < c1 && i < P.n_records) { te = d.te[P.first_rec + i]; se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; }
       }
-      /* ambiguity-transfer records: the base under a transferred quality byte selects the offset */
-      for (u32 i0 = slot; i0 < nx; i0 += 4 * slots) {
-        u32 q[4], c4[4];
+      const bool uniform = __syncthreads_and(covers);
+      const u32 np = n_plain, nx = n_x;
+      const u32 np_pad = (np + QU * slots - 1) / (QU * slots) * (QU * slots);
+      for (u32 i = np + tid; i < np_pad; i += 256) { m_qs[i] = buf_b; m_len[i] = 0; } /* dummies: a valid address, no symbols */
+      mbar_wait(bar_b, (phases >> b) & 1u); phases ^= 1u << b;
+      __syncthreads();
+      if (owner)
+        for (u32 pr = p; pr < RP; pr += 256) { /* more than 256 rows per pass: a thread takes several positions */
+          const u32 pos = p0 + pr, row_a = hist_a + pr * (QR_ROWW * 4);
+          if (uniform) { /* every plain record covers this row range: no per-symbol length test */
+            const u32 full = np / (QU * slots) * (QU * slots);
+            for (u32 i0 = slot; i0 < full; i0 += QU * slots) {
+              u32 q[QU];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const u32 i = i0 + k * slots;
-          q[k] = 0xFFFFFFFFu; c4[k] = 0;
-          if (i < nx) {
-            const u32 L = m_len[QCH + 63 - i], qs = m_qs[QCH + 63 - i];
-            if (pos < L) { q[k] = __ldg(src + qs); c4[k] = __ldg(src + qs - 3 - L); }
+              for (int k = 0; k < QU; ++k) q[k] = lds_u8(m_qs[i0 + k * slots] + pos);
+#pragma unroll
+              for (int k = 0; k < QU; ++k) sm_red_inc(row_a + 4 * min(q[k] - 33u, 95u));
+            }
+            for (u32 i = full + slot; i < np; i += slots) sm_red_inc(row_a + 4 * min(lds_u8(m_qs[i] + pos) - 33u, 95u));
+          } else {
+            for (u32 i0 = slot; i0 < np; i0 += QU * slots) {
+              u32 q[QU];
+#pragma unroll
+              for (int k = 0; k < QU; ++k) {
+                const u32 i = i0 + k * slots;
+                q[k] = 96u;
+                if (pos < (u32)m_len[i]) q[k] = min(lds_u8(m_qs[i] + pos) - 33u, 95u);
+              }
+#pragma unroll
+              for (int k = 0; k < QU; ++k) sm_red_inc(row_a + 4 * q[k]);
+            }
+          }
+          /* ambiguity-transfer records: the base under a transferred quality byte selects the offset */
+          for (u32 i = slot; i < nx; i += slots) {
+            const u32 L = m_len[CH + 63 - i], qa = m_qs[CH + 63 - i];
+            if (pos >= L) continue;
+            const u32 qq = lds_u8(qa + pos) + g_xq_lut[lds_u8(qa - 3 - L + pos)], cc = qq - 33u;
+            if (cc < 95u) sm_red_inc(row_a + 4 * cc);
+            else atomicAdd(raw + (pos + 1) * 256 + qq, 1u);
           }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (q[k] == 0xFFFFFFFFu) continue;
-          const u32 qq = q[k] + g_xq_lut[c4[k]], c = qq - 33u;
-          if (c < QR_COLS) row[c]++;
-          else atomicAdd(grow + qq, 1u);
+      __syncthreads(); /* the chunk's buffer and lists are free again */
+      if (nbuf == 1 && tid == 0 && c + 1 < c1) request(c + 1);
+    }
+    const u32 rows = min(RP, Lp - p0);
+    { /* bytes outside 33..127 in plain records (counter 95 of a row): rare; recount them exactly from global memory */
+      bool any = false;
+      for (u32 pr = tid; pr < rows; pr += 256) any = any || hist[pr * QR_ROWW + 95] != 0;
+      if (__syncthreads_or(any)) {
+        const u32 i_end = min(c1 * QS, P.n_records);
+        for (u32 i = c0 * QS + tid; i < i_end; i += 256) {
+          const u32 r = P.first_rec + i;
+          if (d.kx[r] & 0x8000u) continue;
+          const u32 tei = d.te[r], sei = d.se[r], L = sei - tei - 1;
+          for (u32 pr = 0; pr < rows && p0 + pr < L; ++pr)
+            if (hist[pr * QR_ROWW + 95]) { const u32 v = d.in[sei + 3 + p0 + pr]; if (v - 33u >= 95u) atomicAdd(raw + (p0 + pr + 1) * 256 + v, 1u); }
         }
       }
     }
-    __syncthreads();
-    const u32 rows = min(RP, Lp - p0);
-    for (u32 i = tid; i < rows * QR_COLS; i += 256) {
-      const u32 pr = i / QR_COLS, c = i % QR_COLS;
-      u32 v = 0;
-      for (u32 k = 0; k < slots; ++k) v += hist[(k * RP + pr) * (QR_ROWW * 2) + c];
+    for (u32 i = tid; i < rows * 95; i += 256) {
+      const u32 pr = i / 95, c = i % 95, v = hist[pr * QR_ROWW + c];
       if (v) atomicAdd(raw + (p0 + pr + 1) * 256 + 33 + c, v);
     }
-    __syncthreads();
   }
 }
 
