@@ -176,7 +176,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
     CK(cudaMemcpyToSymbol(g_xq_lut, lut, sizeof lut));
   }
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
-  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
+  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_DYN_MAX));
   CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
@@ -262,7 +262,6 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
-  if ((tune_env < 0 || (tune_env & 8)) && H.max_span / CH > 200) d.tune |= 1u; /* records beyond ~200 B: stat2 reads its few title tokens directly */
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
   dim3 gc(H.max_chunks, S);
@@ -294,7 +293,12 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   CK(cudaMemcpyAsync(ctx->h_hdr2, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, ctx->s_rb));
   k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d);
   k_dnacount<<<dim3(16, S), 256, 0, st>>>(d); PMARK();
-  k_stat2<<<gc, CH, (d.tune & 1u) ? d.max_nf * CH * 4 : span_v, st>>>(d); PMARK();
+  {
+    static const int nbuf_env = getenv("PHY_S2_NBUF") ? atoi(getenv("PHY_S2_NBUF")) : 1;
+    d.s2_nbuf = (nbuf_env == 2 && 2 * span + d.max_nf * CH * 4 <= 200u * 1024) ? 2u : 1u;
+    const u32 dyn = d.s2_nbuf * span + d.max_nf * CH * 4;
+    k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, S), CH, dyn, st>>>(d); PMARK();
+  }
   CK(cudaStreamSynchronize(ctx->s_rb)); /* classify is long done: stat2 keeps the GPU busy meanwhile */
   {
     const u32 pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;

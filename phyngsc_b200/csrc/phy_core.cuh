@@ -210,6 +210,8 @@ struct FieldClass {
   i32 min_v, max_v, min_d, max_d, base;
   u32 diff, bits_num, bits_val, bits_len;
   u32 tab;          /* table id of the numeric Huffman table                   */
+  u32 cl_off;       /* arena word offset of that table's code array            */
+  u32 freq_off;     /* ... and of its frequency array                          */
   u32 slotmap_off;  /* arena word offset of u16[CHARPOS(+pad)] table ids       */
   u8 sep, kind, is_delta, has_table, is_len_const, pad[3];
   u32 mism[MASKW];
@@ -223,6 +225,8 @@ struct SbClass {
   u32 ts0, te0;                /* title line of record 0 (batch-relative positions)                   */
   /* arena layout (word offsets unless stated) */
   u32 ntab, tabdesc_off, tq0, tdna, tchr0, qstat_off, dnastat_off, zero_begin, zero_end;
+  u32 chr_cl_off;              /* code array of char table tchr0; table tchr0 + k follows 512 * k words later */
+  u32 chr_freq_off;            /* frequency array of char table tchr0; table tchr0 + k follows 256 * k words later */
   u32 qpk_off, qpk_bad;        /* quality tables packed to 16 bits (len << 12 | code); qpk_bad != 0 when a code is longer than 12 bits */
   u32 nblk, flagbits_off;
   u32 blkloc_off;              /* per 32-record title block: byte offset inside its chunk */
@@ -235,6 +239,8 @@ struct SbClass {
   u64 qbits_total, dbits_total;
   u64 out_off;
   u8 symbols[256], quals[256], sym_code[256], qua_code[256];
+  u8 ncf[MAXF];                /* the nnc non-constant fields in title order ...                              */
+  u16 ncskip[MAXF];            /* ... and the bytes of constant tokens (with their separators) in front of each */
   FieldClass f[MAXF];
 };
 
@@ -409,7 +415,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
     bool any_mism = false;
     for (int k = 0; k < MASKW; ++k) any_mism = any_mism || a.mism[k] != 0;
     F.is_len_const = (F.min_len == F.len0 && F.max_len == F.len0) ? 1 : 0;
-    F.has_table = 0; F.is_delta = 0; F.tab = NOTAB; F.slotmap_off = 0; F.diff = 0; F.base = 0;
+    F.has_table = 0; F.is_delta = 0; F.tab = NOTAB; F.cl_off = 0; F.freq_off = 0; F.slotmap_off = 0; F.diff = 0; F.base = 0;
     F.bits_num = F.bits_val = F.bits_len = 0;
     F.min_v = F.max_v = F.min_d = F.max_d = 0;
     if (F.is_len_const && !any_mism) { F.kind = K_CONST; continue; }
@@ -441,6 +447,13 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
     }
   }
   C.nnc = nnc;
+  { /* walkers visit only the non-constant fields: constant tokens in between are stepped over in one addition */
+    u32 k = 0, skip = 0;
+    for (u32 f = 0; f < nf; ++f) {
+      if (C.f[f].kind == K_CONST) { skip += C.f[f].len0 + 1; continue; }
+      C.ncf[k] = (u8)f; C.ncskip[k] = (u16)skip; ++k; skip = 0;
+    }
+  }
   /* numeric + char histograms */
   u32 numhist_off[MAXF];
   for (u32 f = 0; f < nf; ++f) numhist_off[f] = (C.f[f].kind == K_NUM && C.f[f].has_table) ? al.take(C.f[f].diff) : 0;
@@ -517,7 +530,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   for (u32 f = 0; f < nf; ++f) {
     FieldClass &F = C.f[f];
     if (F.kind == K_NUM && F.has_table) {
-      F.tab = tid;
+      F.tab = tid; F.cl_off = cl_off; F.freq_off = numhist_off[f];
       td[tid].n = F.diff; td[tid].freq_off = numhist_off[f]; td[tid].cl_off = cl_off; td[tid].tree_off = tree_off;
       td[tid].tree_len = 0; td[tid].dst = 0;
       cl_off += 2 * F.diff; tree_off += align_up(tree_blob_cap(F.diff), 4) / 4; ++tid;
@@ -525,6 +538,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   }
   u32 slot = 0;
   C.tchr0 = tid; /* char tables are numbered consecutively from here */
+  C.chr_cl_off = cl_off; C.chr_freq_off = chrhist_off;
   for (u32 f = 0; f < nf; ++f) {
     FieldClass &F = C.f[f];
     if (F.kind != K_STR) continue;
@@ -672,16 +686,18 @@ PHY_HD void dna_record(const u8 *b, u32 ss, u32 L, bool xfer, bool plain, const 
  * 1; `first` = first record of its 32-record block; prev(f, v) yields the previous record's numeric value
  * of field f given this record's value v -- it is called for EVERY numeric field of EVERY record, in field
  * order, so that on the GPU it can be a warp shuffle (lane = record of the block; all 32 lanes walk
- * together); tables are reached through `arena` (table directory + slot maps). */
+ * together); tables are reached through `arena` (table directory + slot maps).  FC / ncf / ncskip are the field classes
+ * and the list of non-constant fields of C (the GPU passes shared-memory copies). */
 template <class Sink, class Prev>
-PHY_HD void title_record(const u8 *b, const u8 *lut, u32 ts, u32 te, const SbClass &C, const FieldClass *FC, const u32 *arena, u32 flags,
+PHY_HD void title_record(const u8 *b, const u8 *lut, u32 ts, u32 te, const SbClass &C, const FieldClass *FC, const u8 *ncf, const u16 *ncskip,
+                         const u32 *arena, u32 flags,
                          bool first, Prev prev, Sink &s) {
   TitleCursor cur; cur.init(b, ts, te, lut);
-  const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   Tok t;
-  for (u32 f = 0; f < C.nf; ++f) {
+  for (u32 k = 0; k < C.nnc; ++k) {
+    const u32 f = ncf[k];
     const FieldClass &F = FC[f];
-    if (F.kind == K_CONST) { cur.skip(F.len0); continue; } /* every record carries record 0's token here */
+    cur.pos += ncskip[k]; /* every record carries record 0's tokens in the constant fields */
     if (!cur.next(t)) break;
     bool flag = (flags >> f) & 1u;
     if (F.kind == K_NUM) {
@@ -691,7 +707,7 @@ PHY_HD void title_record(const u8 *b, const u8 *lut, u32 ts, u32 te, const SbCla
       else if (!flag) {
         u32 x = F.is_delta ? (u32)wsub(wsub(v, pv), F.min_d) : (u32)wsub(v, F.min_v);
         if (F.has_table) { /* x < diff for real records; lanes that only shadow a record may see anything */
-          u64 e = ((const u64 *)(arena + td[F.tab].cl_off))[x < F.diff ? x : 0u];
+          u64 e = ((const u64 *)(arena + F.cl_off))[x < F.diff ? x : 0u];
           s.put((u32)e, (u32)(e >> 32));
         }
         else s.put(x, F.bits_num);
@@ -705,7 +721,7 @@ PHY_HD void title_record(const u8 *b, const u8 *lut, u32 ts, u32 te, const SbCla
     for (u32 j = 0; j < len; ++j) {
       if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
         u32 tid = sm[j < 128 ? j : 128];
-        u64 e = ((const u64 *)(arena + td[tid].cl_off))[b[t.start + j]];
+        u64 e = ((const u64 *)(arena + C.chr_cl_off + (tid - C.tchr0) * 512u))[b[t.start + j]];
         s.put((u32)e, (u32)(e >> 32));
       }
     }

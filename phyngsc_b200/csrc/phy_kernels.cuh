@@ -76,9 +76,10 @@ struct Dev {
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
   u32 pk_bytes;               /* shared memory behind the span for the packed quality code tables */
   u32 qh_nbuf;                /* span buffers (pipeline stages) of a k_qhist CTA, 1..8 */
+  u32 s2_nbuf;                /* stage buffers of a k_stat2 CTA (1 or 2) */
   u32 qh_rows;                /* rows of a k_qhist CTA's private table */
   u32 qh_recs, qh_stage;      /* records per pipeline stage of k_qhist (128, 64 or 32) and the bytes of a stage buffer */
-  u32 tune;                   /* experiment switches (PHY_TUNE): bit0 = stat2 reads titles straight from global memory */
+  u32 tune;                   /* experiment switches (PHY_TUNE) */
 };
 
 /* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
@@ -856,9 +857,6 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
 }
 
 /* ---- shared pieces of the per-record title kernels ------------------------------------------------------------ */
-__device__ __forceinline__ void load_field_classes(const SbClass &C, FieldClass *fc) {
-  for (u32 i = threadIdx.x; i < C.nf * (sizeof(FieldClass) / 4); i += blockDim.x) ((u32 *)fc)[i] = ((const u32 *)C.f)[i];
-}
 
 /* previous record's numeric value = the neighbouring lane's (lane = record of the 32-record block).  Lane 0
  * receives garbage, which is never used: the first record of a block is coded raw (tasks.cpp:455-458). */
@@ -883,100 +881,131 @@ __device__ __forceinline__ bool span_issue(const u8 *in, u32 lo, u32 hi, u8 *sme
 }
 
 constexpr int CSLOTS = 8; /* per-position char tables whose histogram a CTA keeps in shared memory */
+constexpr int S2G = 8;    /* 128-record chunks per k_stat2 CTA */
 
+/* field classes and the list of non-constant fields of a subblock, copied to shared memory once per CTA */
+struct TitleTabs { FieldClass fc[MAXF]; u16 ncskip[MAXF]; u8 ncf[MAXF]; };
+__device__ __forceinline__ void load_title_tabs(const SbClass &C, TitleTabs &T) {
+  for (u32 i = threadIdx.x; i < C.nf * (sizeof(FieldClass) / 4); i += blockDim.x) ((u32 *)T.fc)[i] = ((const u32 *)C.f)[i];
+  for (u32 i = threadIdx.x; i < MAXF / 2; i += blockDim.x) ((u32 *)T.ncskip)[i] = ((const u32 *)C.ncskip)[i];
+  for (u32 i = threadIdx.x; i < MAXF / 4; i += blockDim.x) ((u32 *)T.ncf)[i] = ((const u32 *)C.ncf)[i];
+}
+
+/* A CTA walks S2G consecutive chunks of one subblock; their bytes arrive through the bulk-copy pipeline (span_request)
+ * while the previous chunk is processed, tables are loaded and the private char histograms flushed once per CTA.
+ * Only the non-constant fields are visited (SbClass::ncf / ncskip).
+ * One stage buffer and more resident CTAs beat two buffers and fewer CTAs here (measured on 36 bp: 0.34 vs 0.44 ms).
+ * dynamic shared memory: [s2_nbuf stage buffers of span_bytes][nnc x CH numeric values] */
 __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ FieldClass fc[MAXF];
-  __shared__ u32 pvals0[MAXF];
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  const SbClass &C = d.cls[s];
-  if (C.status || chunk * CH >= C.R) return;
-  if (C.nnc == 0) return; /* every field constant: no histogram, no block flag is ever read */
-  const SbPlan P = d.plans[s];
-  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
-  u32 *arena = d.arena + (size_t)s * d.arena_words;
-  const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
-  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
+  __shared__ TitleTabs T;
+  __shared__ u32 pvals[2][MAXF];
+  __shared__ __align__(8) u64 bars[2];
+  __shared__ u32 c_lo[S2G + 1];
   __shared__ __align__(16) u8 lut[256];
-  load_lut(lut);
-  /* only the few non-constant tokens of each title are touched: with long records it is cheaper to read them
-   * straight from global memory (L1) than to stage whole records */
-  const bool direct = d.tune & 1u; /* chosen per batch by the host: long records -> direct, short records -> staged span */
-  const u8 *b = direct ? d.in : stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  if (!b) return; /* cannot happen: stat1 staged the same span */
-  u32 *vals = direct ? (u32 *)dyn_smem : vals_area(dyn_smem, d.span_bytes);
-  /* char histograms of the first CSLOTS per-position tables are privatised in shared memory */
   __shared__ u32 chist[CSLOTS * 256];
+  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const SbClass &C = d.cls[s];
+  if (C.status || C.nnc == 0) return; /* every field constant: no histogram, no block flag is ever read */
+  const u32 c0 = blockIdx.x * S2G, c1 = min(c0 + S2G, C.nchunk);
+  if (c0 >= C.nchunk) return;
+  const SbPlan P = d.plans[s];
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  const u32 nnc = C.nnc, R = C.R;
+  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * CH, R)];
+  load_lut(lut);
+  const u32 nbuf = d.s2_nbuf;
+  u32 *vals = (u32 *)((u8 *)dyn_smem + nbuf * d.span_bytes); /* vals[k * CH + tid], k = index in the non-constant list */
+  /* char histograms of the first CSLOTS per-position tables are privatised in shared memory */
   const u32 ncs = min(C.ntab - C.tchr0, (u32)CSLOTS);
   for (u32 i = tid; i < ncs * 256; i += CH) chist[i] = 0;
-  load_field_classes(C, fc);
+  load_title_tabs(C, T);
+  const u32 buf_a0 = (u32)__cvta_generic_to_shared(dyn_smem), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);
+  if (tid == 0) { mbar_init(bar_a0, 1); mbar_init(bar_a0 + 8, 1); mbar_fence_init(); }
+  if (tid < nnc && c0 > 0) pvals[0][tid] = d.chunk_last[((size_t)P.chunk_base + c0 - 1) * MAXF + C.ncf[tid]]; /* record before the first chunk */
   __syncthreads();
-  const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : 0);
-  const u32 nf = C.nf;
-  const u32 wbase = tid & ~31u;
-  u32 flags = 0;
-  /* one walk: string fields are finished here, numeric values are parked in shared memory */
-  TitleCursor cur; cur.init(b, d.rstart[r], d.te[r], lut);
-  for (u32 f = 0; f < nf; ++f) {
-    const FieldClass &F = fc[f];
-    if (F.kind == K_CONST) { cur.skip(F.len0); continue; }
-    Tok t; t.start = t.end = 0; t.v = 0; t.num = false;
-    if (active) cur.next(t);
-    if (F.kind == K_NUM) { vals[f * CH + tid] = t.v; continue; }
-    u32 len = t.end - t.start;
-    u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
-    bool pred = true;
-    if (active) {
-      pred = len == len_lo;
-      const u8 *a = b + t.start, *a0 = b + st_lo;
-      for (u32 j = 0; pred && j < len; ++j) pred = a[j] == a0[j];
-      const u16 *sm = (const u16 *)(arena + F.slotmap_off);
-      for (u32 j = 0; j < len; ++j)
-        if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
-          /* lanes of the warp that are at the same character of the same table add once, together */
-          u32 tab = sm[j < 128 ? j : 128], loc = tab - C.tchr0, ch = a[j];
-          u32 grp = __match_any_sync(__activemask(), (tab << 8) | ch);
-          if ((u32)(__ffs(grp) - 1) == lane) {
-            if (loc < ncs) atomicAdd(&chist[loc * 256 + ch], (u32)__popc(grp));
-            else atomicAdd(arena + td[tab].freq_off + ch, (u32)__popc(grp));
+  auto request = [&](u32 c) { const u32 st = (c - c0) % nbuf; span_request(d.in, c_lo[c - c0], c_lo[c - c0 + 1], buf_a0 + st * d.span_bytes, bar_a0 + 8 * st); };
+  if (tid == 0) request(c0);
+  u32 phases = 0;
+  u32 ts = 0, te = 0;
+  { const u32 i = c0 * CH + tid; if (i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; } }
+  for (u32 c = c0; c < c1; ++c) {
+    const u32 st = (c - c0) % nbuf, pb = (c - c0) & 1u;
+    const u32 nrec = min((u32)CH, R - c * CH);
+    const bool active = tid < nrec;
+    const u32 r = P.first_rec + c * CH + (active ? tid : 0);
+    const u32 wbase = tid & ~31u;
+    if (nbuf == 2 && tid == 0 && c + 1 < c1) request(c + 1);
+    const u32 my_ts = ts, my_te = te;
+    { const u32 i = (c + 1) * CH + tid; if (c + 1 < c1 && i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; } } /* next chunk's record */
+    mbar_wait(bar_a0 + 8 * st, (phases >> st) & 1u); phases ^= 1u << st;
+    const u8 *b = (const u8 *)dyn_smem + st * d.span_bytes - (c_lo[c - c0] & ~15u);
+    u32 flags = 0;
+    /* one walk: string fields are finished here, numeric values are parked in shared memory */
+    TitleCursor cur; cur.init(b, my_ts, my_te, lut);
+    for (u32 k = 0; k < nnc; ++k) {
+      const u32 f = T.ncf[k];
+      const FieldClass &F = T.fc[f];
+      cur.pos += T.ncskip[k];
+      Tok t; t.start = t.end = 0; t.v = 0; t.num = false;
+      if (active) cur.next(t);
+      if (F.kind == K_NUM) { vals[k * CH + tid] = t.v; continue; }
+      u32 len = t.end - t.start;
+      u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
+      bool pred = true;
+      if (active) {
+        pred = len == len_lo;
+        const u8 *a = b + t.start, *a0 = b + st_lo;
+        for (u32 j = 0; pred && j < len; ++j) pred = a[j] == a0[j];
+        const u16 *sm = (const u16 *)(arena + F.slotmap_off);
+        for (u32 j = 0; j < len; ++j)
+          if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
+            /* lanes of the warp that are at the same character of the same table add once, together */
+            u32 tab = sm[j < 128 ? j : 128], loc = tab - C.tchr0, ch = a[j];
+            u32 grp = __match_any_sync(__activemask(), (tab << 8) | ch);
+            if ((u32)(__ffs(grp) - 1) == lane) {
+              if (loc < ncs) atomicAdd(&chist[loc * 256 + ch], (u32)__popc(grp));
+              else atomicAdd(arena + C.chr_freq_off + loc * 256 + ch, (u32)__popc(grp));
+            }
           }
-        }
-    }
-    if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
-  }
-  if (tid < nf && chunk > 0) pvals0[tid] = d.chunk_last[((size_t)P.chunk_base + chunk - 1) * MAXF + tid]; /* record before the chunk */
-  __syncthreads();
-  for (u32 f = 0; f < nf; ++f) {
-    const FieldClass &F = fc[f];
-    if (F.kind != K_NUM) continue;
-    i32 v = (i32)vals[f * CH + tid];
-    i32 pv = (i32)(tid > 0 ? vals[f * CH + tid - 1] : pvals0[f]);
-    i32 dl = wsub(v, pv);
-    bool hasd = active && r > P.first_rec;
-    bool pred;
-    if (F.is_delta) {
-      /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
-      i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
-      if (nrec - wbase < 2) bd = 0;
-      pred = !active || lane < 2 || dl == bd;
-      pred = __all_sync(0xFFFFFFFFu, pred) && bd == F.min_d;
-      if (F.has_table) warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(dl, F.base), hasd);
-    } else {
-      i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
-      pred = __all_sync(0xFFFFFFFFu, !active || v == v_lo);
-      if (F.has_table) {
-        warp_hist_add(arena + td[F.tab].freq_off, (u32)wsub(v, F.base), active);
-        if (active && r == P.first_rec) atomicAdd(arena + td[F.tab].freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
       }
+      if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
     }
-    if (pred) flags |= 1u << f;
+    __syncthreads();
+    for (u32 k = 0; k < nnc; ++k) {
+      const u32 f = T.ncf[k];
+      const FieldClass &F = T.fc[f];
+      if (F.kind != K_NUM) continue;
+      i32 v = (i32)vals[k * CH + tid];
+      i32 pv = (i32)(tid > 0 ? vals[k * CH + tid - 1] : pvals[pb][k]);
+      if (tid == CH - 1) pvals[pb ^ 1u][k] = (u32)v; /* record before the next chunk */
+      i32 dl = wsub(v, pv);
+      bool hasd = active && r > P.first_rec;
+      bool pred;
+      if (F.is_delta) {
+        /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
+        i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
+        if (nrec - wbase < 2) bd = 0;
+        pred = !active || lane < 2 || dl == bd;
+        pred = __all_sync(0xFFFFFFFFu, pred) && bd == F.min_d;
+        if (F.has_table) warp_hist_add(arena + F.freq_off, (u32)wsub(dl, F.base), hasd);
+      } else {
+        i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
+        pred = __all_sync(0xFFFFFFFFu, !active || v == v_lo);
+        if (F.has_table) {
+          warp_hist_add(arena + F.freq_off, (u32)wsub(v, F.base), active);
+          if (active && r == P.first_rec) atomicAdd(arena + F.freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
+        }
+      }
+      if (pred) flags |= 1u << f;
+    }
+    if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (c * CH + wbase) / 32] = flags;
+    __syncthreads(); /* the stage buffer and the value table are free again */
+    if (nbuf == 1 && tid == 0 && c + 1 < c1) request(c + 1);
   }
-  if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (chunk * CH + wbase) / 32] = flags;
-  __syncthreads();
   for (u32 i = tid; i < ncs * 256; i += CH) {
     u32 v = chist[i];
-    if (v) atomicAdd(arena + td[C.tchr0 + (i >> 8)].freq_off + (i & 255u), v);
+    if (v) atomicAdd(arena + C.chr_freq_off + i, v);
   }
 }
 
@@ -1129,7 +1158,7 @@ __device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, c
  * turns into chunk bases with a short scan. */
 __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ FieldClass fc[MAXF];
+  __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
   __shared__ u32 ws[4];
   const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -1152,7 +1181,7 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   const u32 myflags = C.nnc ? arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32] : 0u;
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) return; /* cannot happen: stat1 staged a wider span */
-  load_field_classes(C, fc);
+  load_title_tabs(C, TT);
   __syncthreads();
   u32 qbits = 0, dbits = 0;
   {
@@ -1176,7 +1205,7 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   if (C.nnc) {
     __syncwarp();
     CountSink t; t.init();
-    title_record(b, lut, rs_r, te, C, fc, arena, myflags, lane == 0, PrevShfl(), t);
+    title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, myflags, lane == 0, PrevShfl(), t);
     u32 tb = active ? (u32)t.bits : 0u, x = tb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
@@ -1293,7 +1322,7 @@ __device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
 constexpr int EMIT_THREADS = 2 * CH;
 __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ FieldClass fc[MAXF];
+  __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
   const u32 s = blockIdx.y, chunk = blockIdx.x, role = threadIdx.x / CH, tid = threadIdx.x % CH, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
@@ -1325,7 +1354,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
   const u32 tblk = tit ? arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w] : 0u;
   const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
   if (!b) return; /* cannot happen: stat1 staged a wider span */
-  load_field_classes(C, fc);
+  load_title_tabs(C, TT);
   __syncthreads();
   const u32 o_title = C.info_len, o_qual = o_title + C.title_len, o_dna = o_qual + C.qual_len;
   if (chunk == 0) {
@@ -1368,10 +1397,10 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
     OrSink t; t.init(outw, blk_byte * 8 + (lane == 0 ? 0u : C.nnc + my_toff), active);
     if (lane == 0) {
       u32 v = 0;
-      for (u32 f = 0; f < C.nf; ++f) if (fc[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
+      for (u32 k = 0; k < C.nnc; ++k) v = (v << 1) | ((flags >> TT.ncf[k]) & 1u);
       t.put(v, C.nnc);
     }
-    title_record(b, lut, rs_r, te, C, fc, arena, flags, lane == 0, PrevShfl(), t);
+    title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, flags, lane == 0, PrevShfl(), t);
     t.finish();
   }
 }

@@ -151,7 +151,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
       u32 hi = lo + 32 < R ? lo + 32 : R; u64 bits = C->nnc;
       for (u32 r = lo; r < hi; ++r) {
         CountSink ts; ts.init();
-        title_record(b, lut, rstart[r], te[r], *C, C->f, arena, arena[C->flagbits_off + lo / 32], r == lo, prev_of(r), ts);
+        title_record(b, lut, rstart[r], te[r], *C, C->f, C->ncf, C->ncskip, arena, arena[C->flagbits_off + lo / 32], r == lo, prev_of(r), ts);
         bits += ts.bits;
       }
       blkoff[lo / 32] = (u32)((bits + 7) / 8);
@@ -200,7 +200,7 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
         u32 v = 0;
         for (u32 f = 0; f < nf; ++f) if (C->f[f].kind != K_CONST) v = (v << 1) | ((flags >> f) & 1u);
         ts.put(v, C->nnc);
-        for (u32 r = lo; r < hi; ++r) title_record(b, lut, rstart[r], te[r], *C, C->f, arena, flags, r == lo, prev_of(r), ts);
+        for (u32 r = lo; r < hi; ++r) title_record(b, lut, rstart[r], te[r], *C, C->f, C->ncf, C->ncskip, arena, flags, r == lo, prev_of(r), ts);
         ts.finish();
       }
       sec_len[0] = C->info_len; sec_len[1] = C->title_len; sec_len[2] = C->qual_len; sec_len[3] = C->dna_len;
