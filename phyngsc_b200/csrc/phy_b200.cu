@@ -305,11 +305,11 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     d.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
   }
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
-  k_lengths<<<gc, CH, span + d.pk_bytes, st>>>(d); PMARK();
+  k_lengths<<<dim3((H.max_chunks + ENG - 1) / ENG, S), CH, span + d.pk_bytes, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
-  k_emit<<<gc, EMIT_THREADS, span + d.pk_bytes, st>>>(d); PMARK();
+  k_emit<<<dim3((H.max_chunks + ENG - 1) / ENG, S), EMIT_THREADS, span + d.pk_bytes, st>>>(d); PMARK();
   ctx->launches += 13;
   CK(cudaGetLastError());
   if (ctx->profile) {

@@ -37,7 +37,7 @@ constexpr int QCH = 2048;          /* records per quality-histogram work item (1
 constexpr u32 QR_ROWW = 97;        /* words per row of k_qhist's private table (odd: neighbouring rows start in different banks) */
 constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
-constexpr int EMIT_MIN_CTAS = 6;   /* register budget of k_emit: 65536 / (256 * 6) = 42 */
+constexpr int EMIT_MIN_CTAS = 5;   /* register budget of k_emit: 65536 / (256 * 5) = 51 */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
@@ -1156,71 +1156,117 @@ __device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, c
 /* Bit length of every record in the three bodies.  Offsets are kept two-level: local to the 128-record chunk
  * (qoff/doff/toff per record, title block offsets per 32-record block) plus one total per chunk that k_layout
  * turns into chunk bases with a short scan. */
+constexpr int ENG = 8; /* 128-record chunks per CTA of the encoder kernels (k_lengths, k_emit) */
+
+/* One stage buffer fed by the bulk-copy engine: the CTA's next chunk is requested as soon as every thread has left
+ * the current one (chunks of an encoder CTA are short; more resident CTAs hide the copy better than a second buffer). */
+struct ChunkStage {
+  u32 buf_a, bar_a, phase;
+  const u8 *buf;
+  __device__ __forceinline__ void init(void *smem, u64 *bar) { /* followed by a __syncthreads() of the caller */
+    buf = (const u8 *)smem; buf_a = (u32)__cvta_generic_to_shared(smem); bar_a = (u32)__cvta_generic_to_shared(bar); phase = 0;
+    if (threadIdx.x == 0) { mbar_init(bar_a, 1); mbar_fence_init(); }
+  }
+  __device__ __forceinline__ void request(const u8 *in, u32 lo, u32 hi) const { span_request(in, lo, hi, buf_a, bar_a); } /* one thread */
+  __device__ __forceinline__ const u8 *wait(u32 lo) { mbar_wait(bar_a, phase); phase ^= 1u; return buf - (lo & ~15u); } /* p[pos] valid for the chunk's positions */
+};
+
 __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
-  __shared__ u32 ws[4];
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  __shared__ __align__(16) u8 xq[256];
+  __shared__ __align__(16) u8 lut[256];
+  __shared__ u32 ws[3][4];
+  __shared__ __align__(8) u64 bar;
+  __shared__ u32 c_lo[ENG + 1];
+  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
-  if (C.status || chunk * CH >= C.R) return;
+  if (C.status) return;
+  const u32 nchunk = C.nchunk, c0 = blockIdx.x * ENG, c1 = min(c0 + ENG, nchunk);
+  if (c0 >= nchunk) return;
   const SbPlan P = d.plans[s];
-  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
-  __shared__ __align__(16) u8 xq[256];
+  const u32 R = C.R, nnc = C.nnc, plain = C.plain, flagbits_off = C.flagbits_off, blkloc_off = C.blkloc_off, chunk_off = C.chunk_off;
   WalkTabs T;
   load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)((u8 *)dyn_smem + d.span_bytes), T);
-  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
-  __shared__ __align__(16) u8 lut[256];
   load_lut(lut);
-  const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : nrec - 1); /* idle lanes shadow the chunk's last record so that warps stay converged */
-  const u32 te = d.te[r], se = d.se[r], L = se - te - 1, rs_r = d.rstart[r];
-  const u32 kx = d.kx[r];
-  const u32 myflags = C.nnc ? arena[C.flagbits_off + (chunk * CH + (active ? tid : nrec - 1)) / 32] : 0u;
-  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_title_tabs(C, TT);
+  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * CH, R)];
+  ChunkStage stage; stage.init(dyn_smem, &bar);
   __syncthreads();
-  u32 qbits = 0, dbits = 0;
+  if (tid == 0) stage.request(d.in, c_lo[0], c_lo[1]);
+  /* this thread's record of the first chunk (idle lanes shadow the chunk's last record so that warps stay converged) */
+  u32 n_te, n_se, n_rs, n_kx, n_fl = 0;
   {
-    const bool xfer = kx >> 15;
-    CountSink q; q.init();
-    quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
-    qbits = active ? (u32)q.bits : 0u;
-    if (C.plain) dbits = 2 * (kx & 0x7FFFu);
-    else {
-      CountSink dn; dn.init();
-      dna_walk(b + te + 1, L, xfer, T, dn);
-      dbits = (u32)dn.bits;
+    const u32 i = min(c0 * CH + tid, R - 1), r = P.first_rec + i;
+    n_te = d.te[r]; n_se = d.se[r]; n_rs = d.rstart[r]; n_kx = d.kx[r];
+    if (nnc) n_fl = arena[flagbits_off + i / 32];
+  }
+  for (u32 c = c0; c < c1; ++c) {
+    const u32 nrec = min((u32)CH, R - c * CH);
+    const bool active = tid < nrec;
+    const u32 r = P.first_rec + c * CH + (active ? tid : nrec - 1);
+    const u32 te = n_te, se = n_se, rs_r = n_rs, kx = n_kx, myflags = n_fl, L = se - te - 1;
+    if (c + 1 < c1) { /* next chunk's record, in flight while this chunk is walked */
+      const u32 i = min((c + 1) * CH + tid, R - 1), rn = P.first_rec + i;
+      n_te = d.te[rn]; n_se = d.se[rn]; n_rs = d.rstart[rn]; n_kx = d.kx[rn];
+      if (nnc) n_fl = arena[flagbits_off + i / 32];
     }
-    if (!active) dbits = 0;
-  }
-  u32 qtot, dtot;
-  u32 qloc = block_excl_scan<4>(qbits, ws, qtot);
-  u32 dloc = block_excl_scan<4>(dbits, ws, dtot);
-  if (active) { d.qoff[r] = qloc; d.doff[r] = dloc; }
-  u32 blk_bytes = 0;
-  if (C.nnc) {
-    __syncwarp();
-    CountSink t; t.init();
-    title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, myflags, lane == 0, PrevShfl(), t);
-    u32 tb = active ? (u32)t.bits : 0u, x = tb;
+    const u8 *b = stage.wait(c_lo[c - c0]);
+    u32 qbits = 0, dbits = 0;
+    {
+      const bool xfer = kx >> 15;
+      CountSink q; q.init();
+      quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
+      qbits = active ? (u32)q.bits : 0u;
+      if (plain) dbits = 2 * (kx & 0x7FFFu);
+      else {
+        CountSink dn; dn.init();
+        dna_walk(b + te + 1, L, xfer, T, dn);
+        dbits = (u32)dn.bits;
+      }
+      if (!active) dbits = 0;
+    }
+    u32 blk_bytes = 0, tb = 0, tx = 0;
+    if (nnc) {
+      __syncwarp();
+      CountSink t; t.init();
+      title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, myflags, lane == 0, PrevShfl(), t);
+      tb = active ? (u32)t.bits : 0u; tx = tb;
+    }
+    /* offsets inside the chunk: the three warp scans run together, one exchange through shared memory */
+    u32 qx = qbits, dx = dbits;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x += y; }
-    if (active) d.toff[r] = x - tb; /* bits of the block's earlier records (the flag bits come on top) */
-    u32 sum = __shfl_sync(0xFFFFFFFFu, x, 31);
-    if ((tid & ~31u) < nrec) blk_bytes = (C.nnc + sum + 7) / 8;
-  }
-  /* title block offsets local to the chunk */
-  u32 ttot;
-  u32 tloc = block_excl_scan<4>(lane == 0 ? blk_bytes : 0u, ws, ttot);
-  if (lane == 0 && (tid & ~31u) < nrec) arena[C.blkloc_off + chunk * (CH / 32) + w] = tloc;
-  if (tid == 0) {
-    arena[C.chunk_off + chunk] = qtot;
-    arena[C.chunk_off + C.nchunk + chunk] = dtot;
-    arena[C.chunk_off + 2 * C.nchunk + chunk] = ttot;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 yq = __shfl_up_sync(0xFFFFFFFFu, qx, o), yd = __shfl_up_sync(0xFFFFFFFFu, dx, o), yt = __shfl_up_sync(0xFFFFFFFFu, tx, o);
+      if (lane >= (u32)o) { qx += yq; dx += yd; tx += yt; }
+    }
+    if (nnc) {
+      if (active) d.toff[r] = tx - tb; /* bits of the block's earlier records (the flag bits come on top) */
+      const u32 sum = __shfl_sync(0xFFFFFFFFu, tx, 31);
+      if ((tid & ~31u) < nrec) blk_bytes = (nnc + sum + 7) / 8;
+    }
+    if (lane == 31) { ws[0][w] = qx; ws[1][w] = dx; }
+    if (lane == 0) ws[2][w] = blk_bytes;
+    __syncthreads();
+    u32 qbase = 0, dbase = 0, tloc = 0, qtot = 0, dtot = 0, ttot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const u32 a = ws[0][k], e = ws[1][k], g = ws[2][k];
+      if ((u32)k < w) { qbase += a; dbase += e; tloc += g; }
+      qtot += a; dtot += e; ttot += g;
+    }
+    if (active) { d.qoff[r] = qbase + qx - qbits; d.doff[r] = dbase + dx - dbits; }
+    if (lane == 0 && (tid & ~31u) < nrec) arena[blkloc_off + c * (CH / 32) + w] = tloc; /* title block offsets local to the chunk */
+    if (tid == 0) {
+      arena[chunk_off + c] = qtot;
+      arena[chunk_off + nchunk + c] = dtot;
+      arena[chunk_off + 2 * nchunk + c] = ttot;
+    }
+    __syncthreads(); /* every thread has left the stage buffer (and ws) */
+    if (tid == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
   }
 }
 
@@ -1324,40 +1370,46 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
-  const u32 s = blockIdx.y, chunk = blockIdx.x, role = threadIdx.x / CH, tid = threadIdx.x % CH, lane = tid & 31, w = tid >> 5;
+  __shared__ __align__(16) u8 xq[256];
+  __shared__ __align__(16) u8 lut[256];
+  __shared__ __align__(8) u64 bar;
+  __shared__ u32 c_lo[ENG + 1];
+  const u32 s = blockIdx.y, role = threadIdx.x / CH, tid = threadIdx.x % CH, lane = tid & 31, w = tid >> 5;
   const SbClass &C = d.cls[s];
-  if (C.status || chunk * CH >= C.R) return;
+  if (C.status) return;
+  const u32 nchunk = C.nchunk, c0 = blockIdx.x * ENG, c1 = min(c0 + ENG, nchunk);
+  if (c0 >= nchunk) return;
   const SbPlan P = d.plans[s];
-  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, C.R - chunk * CH);
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   u8 *out = d.out + C.out_off;
   u32 *outw = (u32 *)d.out;
   const u64 obase = C.out_off; /* byte offset of the payload inside d.out (16-byte aligned) */
-  __shared__ __align__(16) u8 xq[256];
+  const u32 R = C.R, nnc = C.nnc, nb_len = C.nb_len;
+  const bool tit = role == 1 && nnc;
   WalkTabs T;
   load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)((u8 *)dyn_smem + d.span_bytes), T);
-  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
-  __shared__ __align__(16) u8 lut[256];
   load_lut(lut);
-  const bool active = tid < nrec;
-  const u32 i_sb = chunk * CH + (active ? tid : nrec - 1); /* record index inside the subblock (idle lanes shadow the last) */
-  const u32 r = P.first_rec + i_sb;
-  const u32 te = d.te[r], se = d.se[r], L = se - te - 1;
-  const u32 kx = d.kx[r];
-  /* role 0: quality offsets; role 1: DNA and title offsets */
-  const u32 my_off = role == 0 ? d.qoff[r] : d.doff[r];
-  const u32 cbase = arena[C.chunk_off + role * C.nchunk + chunk];
-  const bool tit = role == 1 && C.nnc;
-  const u32 rs_r = tit ? d.rstart[r] : 0u, my_toff = tit ? d.toff[r] : 0u;
-  const u32 flags = tit ? arena[C.flagbits_off + i_sb / 32] : 0u;
-  const u32 tblk = tit ? arena[C.chunk_off + 2 * C.nchunk + chunk] + arena[C.blkloc_off + chunk * (CH / 32) + w] : 0u;
-  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  if (!b) return; /* cannot happen: stat1 staged a wider span */
   load_title_tabs(C, TT);
+  if (threadIdx.x <= c1 - c0) c_lo[threadIdx.x] = d.rstart[P.first_rec + min((c0 + threadIdx.x) * CH, R)];
+  ChunkStage stage; stage.init(dyn_smem, &bar);
   __syncthreads();
+  if (threadIdx.x == 0) stage.request(d.in, c_lo[0], c_lo[1]);
   const u32 o_title = C.info_len, o_qual = o_title + C.title_len, o_dna = o_qual + C.qual_len;
-  if (chunk == 0) {
+  /* bit positions of the three bodies inside d.out */
+  const u64 q_bit0 = (obase + o_qual + C.qhdr_len) * 8, d_bit0 = (obase + o_dna + C.dhdr_len) * 8, t_byte0 = obase + o_title + C.thdr_len;
+  const u32 *cbase_p = arena + C.chunk_off + role * nchunk, *tbase_p = arena + C.chunk_off + 2 * nchunk, *blkloc_p = arena + C.blkloc_off;
+  const u32 *flag_p = arena + C.flagbits_off;
+  const u32 *off_p = role == 0 ? d.qoff : d.doff;
+  /* this thread's record of the first chunk (idle lanes shadow the chunk's last record); role 0 needs the quality
+   * offsets, role 1 the DNA and title offsets */
+  u32 n_te, n_se, n_kx, n_off, n_cbase, n_rs = 0, n_toff = 0, n_fl = 0, n_tblk = 0;
+  {
+    const u32 i = min(c0 * CH + tid, R - 1), r = P.first_rec + i;
+    n_te = d.te[r]; n_se = d.se[r]; n_kx = d.kx[r]; n_off = off_p[r]; n_cbase = cbase_p[c0];
+    if (tit) { n_rs = d.rstart[r]; n_toff = d.toff[r]; n_fl = flag_p[i / 32]; n_tblk = tbase_p[c0] + blkloc_p[c0 * (CH / 32) + w]; }
+  }
+  if (c0 == 0) {
     /* fixed part of the info stream (phyNGSC.cpp:719-730) and the three staged headers.  Bytes are OR-ed
      * into the zeroed payload word-atomically because a header may end inside a word whose other bytes
      * belong to a bit stream written by another thread. */
@@ -1368,40 +1420,54 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
       bw.byte((u8)C.nsym); bw.byte(0); bw.byte((u8)C.nq); bw.word(C.flags);
       for (u32 i = 0; i < INFO_FIXED; ++i) or_byte(out, i, fx[i]);
     }
-    const u8 *stage = (const u8 *)(arena + C.stage_off);
-    for (u32 i = threadIdx.x; i < C.thdr_len; i += EMIT_THREADS) or_byte(out, o_title + i, stage[i]);
-    for (u32 i = threadIdx.x; i < C.qhdr_len; i += EMIT_THREADS) or_byte(out, o_qual + i, stage[C.thdr_cap + i]);
-    for (u32 i = threadIdx.x; i < C.dhdr_len; i += EMIT_THREADS) or_byte(out, o_dna + i, stage[C.thdr_cap + C.qhdr_cap + i]);
+    const u8 *hs = (const u8 *)(arena + C.stage_off);
+    for (u32 i = threadIdx.x; i < C.thdr_len; i += EMIT_THREADS) or_byte(out, o_title + i, hs[i]);
+    for (u32 i = threadIdx.x; i < C.qhdr_len; i += EMIT_THREADS) or_byte(out, o_qual + i, hs[C.thdr_cap + i]);
+    for (u32 i = threadIdx.x; i < C.dhdr_len; i += EMIT_THREADS) or_byte(out, o_dna + i, hs[C.thdr_cap + C.qhdr_cap + i]);
   }
-  const bool xfer = kx >> 15;
-  if (role == 0) {
-    if (active) { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
-      OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * C.nb_len);
-      k.put(L, C.nb_len); k.finish();
+  for (u32 c = c0; c < c1; ++c) {
+    const u32 nrec = min((u32)CH, R - c * CH);
+    const bool active = tid < nrec;
+    const u32 i_sb = c * CH + (active ? tid : nrec - 1); /* record index inside the subblock */
+    const u32 te = n_te, se = n_se, kx = n_kx, my_off = n_off, cbase = n_cbase, rs_r = n_rs, my_toff = n_toff, flags = n_fl, tblk = n_tblk;
+    const u32 L = se - te - 1;
+    if (c + 1 < c1) { /* next chunk's record, in flight while this chunk is encoded */
+      const u32 i = min((c + 1) * CH + tid, R - 1), rn = P.first_rec + i;
+      n_te = d.te[rn]; n_se = d.se[rn]; n_kx = d.kx[rn]; n_off = off_p[rn]; n_cbase = cbase_p[c + 1];
+      if (tit) { n_rs = d.rstart[rn]; n_toff = d.toff[rn]; n_fl = flag_p[i / 32]; n_tblk = tbase_p[c + 1] + blkloc_p[(c + 1) * (CH / 32) + w]; }
     }
-    /* idle lanes of the last chunk walk the chunk's last record without storing */
-    OrSink q; q.init(outw, (obase + o_qual + C.qhdr_len) * 8 + cbase + my_off, active);
-    quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
-    q.finish();
-    return;
-  }
-  {
-    OrSink dn; dn.init(outw, (obase + o_dna + C.dhdr_len) * 8 + cbase + my_off, active);
-    dna_walk(b + te + 1, L, xfer, T, dn);
-    dn.finish();
-  }
-  if (C.nnc) {
-    /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509); all 32 lanes walk together */
-    __syncwarp();
-    const u64 blk_byte = obase + o_title + C.thdr_len + tblk;
-    OrSink t; t.init(outw, blk_byte * 8 + (lane == 0 ? 0u : C.nnc + my_toff), active);
-    if (lane == 0) {
-      u32 v = 0;
-      for (u32 k = 0; k < C.nnc; ++k) v = (v << 1) | ((flags >> TT.ncf[k]) & 1u);
-      t.put(v, C.nnc);
+    const u8 *b = stage.wait(c_lo[c - c0]);
+    const bool xfer = kx >> 15;
+    if (role == 0) {
+      if (active) { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
+        OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * nb_len);
+        k.put(L, nb_len); k.finish();
+      }
+      /* idle lanes of the last chunk walk the chunk's last record without storing */
+      OrSink q; q.init(outw, q_bit0 + cbase + my_off, active);
+      quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
+      q.finish();
+    } else {
+      {
+        OrSink dn; dn.init(outw, d_bit0 + cbase + my_off, active);
+        dna_walk(b + te + 1, L, xfer, T, dn);
+        dn.finish();
+      }
+      if (nnc) {
+        /* title body: blocks of 32 records, byte-aligned (tasks.cpp:393-509); all 32 lanes walk together */
+        __syncwarp();
+        OrSink t; t.init(outw, (t_byte0 + tblk) * 8 + (lane == 0 ? 0u : nnc + my_toff), active);
+        if (lane == 0) {
+          u32 v = 0;
+          for (u32 k = 0; k < nnc; ++k) v = (v << 1) | ((flags >> TT.ncf[k]) & 1u);
+          t.put(v, nnc);
+        }
+        title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, flags, lane == 0, PrevShfl(), t);
+        t.finish();
+      }
     }
-    title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, flags, lane == 0, PrevShfl(), t);
-    t.finish();
+    __syncthreads(); /* every thread has left the stage buffer */
+    if (threadIdx.x == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
   }
 }
 
