@@ -267,7 +267,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   dim3 gc(H.max_chunks, S);
   u32 qh_dyn = 0;
   PMARK();
-  k_stat1<<<gc, CH, span_v, st>>>(d);
+  k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, S), CH, span_v, st>>>(d);
   k_xdelta<<<S, 128, 0, st>>>(d); PMARK();
   { /* k_qhist: private table of min(longest read, 256) rows beside two stage buffers.  Long records are staged in
      * groups of 64 or 32 instead of 128 so that two CTAs still fit an SM (fewer, larger groups beat more CTAs: the

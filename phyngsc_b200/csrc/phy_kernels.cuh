@@ -363,6 +363,45 @@ __device__ __forceinline__ const u8 *stage_span(const u8 *in, u32 lo, u32 hi, u8
 /* Dynamic shared memory of the per-record kernels: [span_bytes: staged records][vals: nf x CH numeric values] */
 __device__ __forceinline__ u32 *vals_area(uint4 *dyn, u32 span_bytes) { return (u32 *)((u8 *)dyn + span_bytes); }
 
+/* ---- bulk-copy span pipeline ------------------------------------------------------------------------------------ */
+/* A CTA that walks several 128-record chunks streams their bytes into shared memory with the bulk-copy engine
+ * (cp.async.bulk, one request per chunk issued by one thread, completion counted on an mbarrier), double-buffered so
+ * that the next chunk arrives while the current one is processed.  No thread spends instructions on the copy. */
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  u32 ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 20)) __trap(); /* a lost copy must not hang the GPU */
+  } while (!ok);
+}
+/* one thread: request bytes [lo & ~15, hi) of the batch (rounded up to 16) into `dst` (shared address, 16-byte aligned) */
+__device__ __forceinline__ void span_request(const u8 *in, u32 lo, u32 hi, u32 dst, u32 bar) {
+  const u32 alo = lo & ~15u, n = (hi - alo + 15u) & ~15u;
+  mbar_expect_tx(bar, n);
+  bulk_g2s(dst, in + alo, n, bar);
+}
+
+/* One stage buffer fed by the bulk-copy engine: the CTA's next chunk is requested as soon as every thread has left
+ * the current one (chunks of an encoder CTA are short; more resident CTAs hide the copy better than a second buffer). */
+struct ChunkStage {
+  u32 buf_a, bar_a, phase;
+  const u8 *buf;
+  __device__ __forceinline__ void init(void *smem, u64 *bar) { /* followed by a __syncthreads() of the caller */
+    buf = (const u8 *)smem; buf_a = (u32)__cvta_generic_to_shared(smem); bar_a = (u32)__cvta_generic_to_shared(bar); phase = 0;
+    if (threadIdx.x == 0) { mbar_init(bar_a, 1); mbar_fence_init(); }
+  }
+  __device__ __forceinline__ void request(const u8 *in, u32 lo, u32 hi) const { span_request(in, lo, hi, buf_a, bar_a); } /* one thread */
+  __device__ __forceinline__ const u8 *wait(u32 lo) { mbar_wait(bar_a, phase); phase ^= 1u; return buf - (lo & ~15u); } /* p[pos] valid for the chunk's positions */
+};
+
 /* ---- stat1 ---------------------------------------------------------------------------------------------- */
 struct Stat1S {
   u32 facc[MAXF][8];
@@ -378,32 +417,39 @@ struct Stat1S {
   u8 r0[R0_MAX];
 };
 
+constexpr int S1G = 8; /* 128-record chunks per k_stat1 CTA */
+
+/* A CTA walks S1G consecutive chunks of one subblock (bulk-copy staging, ChunkStage); record 0 is tokenised and the
+ * shared-memory accumulators are flushed to the subblock's once per CTA.
+ * dynamic shared memory: [span_bytes stage buffer][nf x CH numeric values] */
 __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ Stat1S S;
-  const u32 s = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  const SbPlan P = d.plans[s];
-  if (P.status || chunk * CH >= P.n_records) return;
-  const u32 r0 = P.first_rec + chunk * CH, nrec = min((u32)CH, P.n_records - chunk * CH);
-  for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
-  const u32 lo = d.rstart[r0], hi = d.rstart[r0 + nrec];
+  __shared__ __align__(8) u64 bar;
+  __shared__ u32 c_lo[S1G + 1];
   __shared__ __align__(16) u8 lut[256], dlut[256];
+  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const SbPlan P = d.plans[s];
+  const u32 R = P.n_records, nchunk = (R + CH - 1) / CH, c0 = blockIdx.x * S1G, c1 = min(c0 + S1G, nchunk);
+  if (P.status || c0 >= nchunk) return;
+  for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
   load_lut(lut);
   for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'T' ? 4 : i == 'G' ? 8 : 0);
-  /* this thread's record (loaded before the span is staged so that the latencies overlap) */
-  const bool active = tid < nrec;
-  const u32 r = r0 + (active ? tid : 0);
-  const u32 ts = d.rstart[r], te = d.te[r], se = d.se[r], nx = d.rstart[r + 1];
+  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * CH, R)];
   const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
-  const u8 *b = stage_span(d.in, lo, hi, (u8 *)dyn_smem, d.span_bytes);
-  if (!b) { if (tid == 0) atomicMin(&d.acc[s].status, (i32)E_UNSUPPORTED); return; }
+  ChunkStage stage; stage.init(dyn_smem, &bar);
   u32 *vals = vals_area(dyn_smem, d.span_bytes); /* vals[f * CH + tid] */
-  __syncthreads();
   /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
   const bool r0_ok = te0 - ts0 + 1 <= R0_MAX;
   if (r0_ok) for (u32 i = tid; i <= te0 - ts0; i += CH) S.r0[i] = d.in[ts0 + i];
   __syncthreads();
+  {
+    bool fits = true;
+    for (u32 k = 0; k < c1 - c0; ++k) fits = fits && c_lo[k + 1] - (c_lo[k] & ~15u) + 16 <= d.span_bytes;
+    if (!fits) { if (tid == 0) atomicMin(&d.acc[s].status, (i32)E_UNSUPPORTED); return; } /* records far beyond the reference's 500-byte domain */
+  }
   if (tid == 0) {
+    stage.request(d.in, c_lo[0], c_lo[1]);
     S.ts0 = ts0; S.te0 = te0;
     if (!r0_ok) S.err = E_UNSUPPORTED;
     else {
@@ -414,17 +460,33 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       if (nf == 0 || nf > (u32)MAXF || nf > d.max_nf) S.err = E_UNSUPPORTED;
     }
   }
+  /* this thread's record of the first chunk */
+  u32 n_ts = 0, n_te = 0, n_se = 0, n_nx = 0;
+  { const u32 i = c0 * CH + tid; if (i < R) { const u32 r = P.first_rec + i; n_ts = d.rstart[r]; n_te = d.te[r]; n_se = d.se[r]; n_nx = d.rstart[r + 1]; } }
   __syncthreads();
   const u32 nf = S.nf;
   const bool seed_ok = S.err == 0;
+  if (seed_ok && tid < nf) { /* record 0's own token lengths and values, folded in once per CTA (see the field loop) */
+    const u32 l0 = S.len0[tid], k0 = key_of((i32)S.v0[tid]);
+    atomicMax(&S.facc[tid][0], ~l0); atomicMax(&S.facc[tid][1], l0);
+    if (!S.num0[tid]) S.facc[tid][2] = 1;
+    atomicMax(&S.facc[tid][3], k0); atomicMax(&S.facc[tid][4], ~k0);
+  }
+  for (u32 c = c0; c < c1; ++c) {
+  const u32 nrec = min((u32)CH, R - c * CH);
+  const bool active = tid < nrec;
+  const u32 r = P.first_rec + c * CH + (active ? tid : 0);
+  const u32 ts = n_ts, te = n_te, se = n_se, nx = n_nx;
+  { const u32 i = (c + 1) * CH + tid; if (c + 1 < c1 && i < R) { const u32 rn = P.first_rec + i; n_ts = d.rstart[rn]; n_te = d.te[rn]; n_se = d.se[rn]; n_nx = d.rstart[rn + 1]; } }
+  const u8 *b = stage.wait(c_lo[c - c0]);
   const u32 L = se - te - 1, qs = se + 3;
   i32 err = 0;
   if (active) {
     if (L == 0 || b[se + 1] != '+' || b[se + 2] != '\n' || nx != 2 * se - te + 3) err = E_MALFORMED;
     else if (L > (u32)MAX_READ) err = E_UNSUPPORTED;
     else if (r == P.first_rec) { /* colour space, phyNGSC.cpp:473-487: not implemented */
-      u8 c0 = b[te + 1], c1 = b[te + 2];
-      if ((c0 >= '0' && c0 <= '3') || (c1 >= '0' && c1 <= '3')) err = E_COLORSPACE;
+      u8 c0b = b[te + 1], c1b = b[te + 2];
+      if ((c0b >= '0' && c0b <= '3') || (c1b >= '0' && c1b <= '3')) err = E_COLORSPACE;
     }
   }
   /* sequence (phyNGSC.cpp:549-619).  Four bases per step: the 2-bit index (c >> 1) & 3 selects the byte the base
@@ -490,12 +552,6 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   const bool walk = active && !err && seed_ok;
   bool fields_ok = true;
   TitleCursor cur; cur.init(b, ts, te, lut);
-  if (seed_ok && tid < nf) {
-    const u32 l0 = S.len0[tid], k0 = key_of((i32)S.v0[tid]);
-    atomicMax(&S.facc[tid][0], ~l0); atomicMax(&S.facc[tid][1], l0);
-    if (!S.num0[tid]) S.facc[tid][2] = 1;
-    atomicMax(&S.facc[tid][3], k0); atomicMax(&S.facc[tid][4], ~k0);
-  }
   for (u32 f = 0; f < nf && seed_ok; ++f) {
     const u32 len0 = S.len0[f];
     const u8 *d0 = S.r0 + S.off0[f];
@@ -549,7 +605,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   /* deltas inside the chunk; the delta across the chunk boundary is folded in by k_xdelta from the values of
    * the chunk's first / last record, so that no thread has to parse the neighbouring chunk's record */
   if (seed_ok && tid < nf) {
-    const size_t row = ((size_t)P.chunk_base + chunk) * MAXF + tid;
+    const size_t row = ((size_t)P.chunk_base + c) * MAXF + tid;
     d.chunk_first[row] = vals[tid * CH];
     d.chunk_last[row] = vals[tid * CH + nrec - 1];
   }
@@ -562,7 +618,9 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     if (lane == 0) { atomicMax(&S.facc[f][5], kmax); atomicMax(&S.facc[f][6], kinv); }
   }
   if (err) atomicMin(&S.err, err);
-  __syncthreads();
+  __syncthreads(); /* every thread has left the stage buffer and the value table */
+  if (tid == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
+  } /* chunk loop */
   /* flush to the subblock accumulators */
   SbAcc *A = d.acc + s;
   if (tid == 0) {
@@ -692,32 +750,6 @@ __global__ void __launch_bounds__(256) k_dnacount(Dev d) {
  * `slots` copies of the rows work on different records.  The records are first split into a plain list and the
  * (rare) list of records with an ambiguity transfer; the plain loop keeps eight quality bytes in flight per thread
  * and has no per-symbol test at all when every plain record is at least as long as the row range. */
-/* ---- bulk-copy span pipeline ------------------------------------------------------------------------------------ */
-/* A CTA that walks several 128-record chunks streams their bytes into shared memory with the bulk-copy engine
- * (cp.async.bulk, one request per chunk issued by one thread, completion counted on an mbarrier), double-buffered so
- * that the next chunk arrives while the current one is processed.  No thread spends instructions on the copy. */
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  u32 ok = 0, spins = 0;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++spins > (1u << 20)) __trap(); /* a lost copy must not hang the GPU */
-  } while (!ok);
-}
-/* one thread: request bytes [lo & ~15, hi) of the batch (rounded up to 16) into `dst` (shared address, 16-byte aligned) */
-__device__ __forceinline__ void span_request(const u8 *in, u32 lo, u32 hi, u32 dst, u32 bar) {
-  const u32 alo = lo & ~15u, n = (hi - alo + 15u) & ~15u;
-  mbar_expect_tx(bar, n);
-  bulk_g2s(dst, in + alo, n, bar);
-}
-
 constexpr int QU = 8;          /* records in flight per thread */
 __device__ __forceinline__ u32 lds_u8(u32 addr) { u16 v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sm_red_inc(u32 addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
@@ -1157,19 +1189,6 @@ __device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, c
  * (qoff/doff/toff per record, title block offsets per 32-record block) plus one total per chunk that k_layout
  * turns into chunk bases with a short scan. */
 constexpr int ENG = 8; /* 128-record chunks per CTA of the encoder kernels (k_lengths, k_emit) */
-
-/* One stage buffer fed by the bulk-copy engine: the CTA's next chunk is requested as soon as every thread has left
- * the current one (chunks of an encoder CTA are short; more resident CTAs hide the copy better than a second buffer). */
-struct ChunkStage {
-  u32 buf_a, bar_a, phase;
-  const u8 *buf;
-  __device__ __forceinline__ void init(void *smem, u64 *bar) { /* followed by a __syncthreads() of the caller */
-    buf = (const u8 *)smem; buf_a = (u32)__cvta_generic_to_shared(smem); bar_a = (u32)__cvta_generic_to_shared(bar); phase = 0;
-    if (threadIdx.x == 0) { mbar_init(bar_a, 1); mbar_fence_init(); }
-  }
-  __device__ __forceinline__ void request(const u8 *in, u32 lo, u32 hi) const { span_request(in, lo, hi, buf_a, bar_a); } /* one thread */
-  __device__ __forceinline__ const u8 *wait(u32 lo) { mbar_wait(bar_a, phase); phase ^= 1u; return buf - (lo & ~15u); } /* p[pos] valid for the chunk's positions */
-};
 
 __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
   extern __shared__ uint4 dyn_smem[];
