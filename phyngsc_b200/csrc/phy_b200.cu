@@ -62,6 +62,7 @@ struct phy_ctx {
 
 static const u32 SPAN_MAX = 96 * 1024;
 static const u32 QH_DYN_MAX = 200 * 1024; /* private rows + span buffers of k_qhist */
+static const u32 ENC_STAGE_MAX = 24 * 1024; /* a warp's stage in the encoder kernels: 32 records of up to 768 bytes on average */
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
 static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "qhist", "classify", "zero_hist",
@@ -178,8 +179,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_DYN_MAX));
-  CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
-  CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + PK_SMEM_MAX)));
+  CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
+  CK(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
+  CK(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
   return PHY_OK;
 }
@@ -305,11 +307,23 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     d.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
   }
   k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
-  k_lengths<<<dim3((H.max_chunks + ENG - 1) / ENG, S), CH, span + d.pk_bytes, st>>>(d); PMARK();
+  {
+    u32 es = (H.max_span32 + 16 + 255) & ~255u;
+    d.enc_stage = es > ENC_STAGE_MAX ? ENC_STAGE_MAX : es; /* wider blocks fail their subblock with PHY_ERR_UNSUPPORTED */
+  }
+  const dim3 ge((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), S);
+  const u32 enc_dyn = d.pk_bytes + EW * d.enc_stage;
+  k_lengths<<<ge, EW * 32, enc_dyn, st>>>(d); PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
-  k_emit<<<dim3((H.max_chunks + ENG - 1) / ENG, S), EMIT_THREADS, span + d.pk_bytes, st>>>(d); PMARK();
+  { /* one warp per block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
+    static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
+    const bool pair = pair_env >= 0 ? pair_env != 0 : (enc_dyn + 7 * 1024) * 4 > 227u * 1024;
+    if (pair) k_emit<true><<<dim3((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), S), EW * 32, d.pk_bytes + EP * d.enc_stage, st>>>(d);
+    else k_emit<false><<<ge, EW * 32, enc_dyn, st>>>(d);
+    PMARK();
+  }
   ctx->launches += 13;
   CK(cudaGetLastError());
   if (ctx->profile) {

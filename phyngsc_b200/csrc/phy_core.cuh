@@ -229,8 +229,8 @@ struct SbClass {
   u32 chr_freq_off;            /* frequency array of char table tchr0; table tchr0 + k follows 256 * k words later */
   u32 qpk_off, qpk_bad;        /* quality tables packed to 16 bits (len << 12 | code); qpk_bad != 0 when a code is longer than 12 bits */
   u32 nblk, flagbits_off;
-  u32 blkloc_off;              /* per 32-record title block: byte offset inside its chunk */
-  u32 nchunk, chunk_off;       /* per 128-record chunk: [3][nchunk] totals -> bases of quality bits, dna bits, title bytes */
+  u32 nchunk;                  /* 128-record chunks (work items of the statistics kernels) */
+  u32 blk3_off;                /* per 32-record block: [3][nblk] totals -> bases of quality bits, dna bits, title bytes */
   u32 stage_off;               /* header staging: title | quality | dna header bytes                  */
   u32 thdr_cap, qhdr_cap, dhdr_cap;
   u32 arena_used;
@@ -471,9 +471,8 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   for (u32 f = 0; f < nf; ++f) if (C.f[f].kind == K_STR) C.f[f].slotmap_off = al.take((CHARPOS + 1) / 2 + 1);
   C.nblk = (R + 31) / 32;
   C.flagbits_off = al.take(C.nblk);
-  C.blkloc_off = al.take(C.nblk);
   C.nchunk = (R + CHUNK_RECORDS - 1) / CHUNK_RECORDS;
-  C.chunk_off = al.take(3 * C.nchunk);
+  C.blk3_off = al.take(3 * C.nblk);
   if (al.used & 1) al.take(1); /* 8-byte alignment for the code tables */
   u32 cl_off = al.used;
   u64 cl_words = 2ull * ((u64)(C.max_qlen + 1) * nq + (C.plain ? 0 : nsym) + (u64)ntab_chr * 256);

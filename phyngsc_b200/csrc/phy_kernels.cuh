@@ -37,7 +37,6 @@ constexpr int QCH = 2048;          /* records per quality-histogram work item (1
 constexpr u32 QR_ROWW = 97;        /* words per row of k_qhist's private table (odd: neighbouring rows start in different banks) */
 constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
-constexpr int EMIT_MIN_CTAS = 5;   /* register budget of k_emit: 65536 / (256 * 5) = 51 */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
@@ -78,6 +77,7 @@ struct Dev {
   u32 qh_nbuf;                /* span buffers (pipeline stages) of a k_qhist CTA, 1..8 */
   u32 s2_nbuf;                /* stage buffers of a k_stat2 CTA (1 or 2) */
   u32 qh_rows;                /* rows of a k_qhist CTA's private table */
+  u32 enc_stage;              /* bytes of one warp's stage buffer in the encoder kernels (a 32-record block) */
   u32 qh_recs, qh_stage;      /* records per pipeline stage of k_qhist (128, 64 or 32) and the bytes of a stage buffer */
   u32 tune;                   /* experiment switches (PHY_TUNE) */
 };
@@ -1188,52 +1188,75 @@ __device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, c
 /* Bit length of every record in the three bodies.  Offsets are kept two-level: local to the 128-record chunk
  * (qoff/doff/toff per record, title block offsets per 32-record block) plus one total per chunk that k_layout
  * turns into chunk bases with a short scan. */
-constexpr int ENG = 8; /* 128-record chunks per CTA of the encoder kernels (k_lengths, k_emit) */
+/* The encoder kernels (k_lengths, k_emit) are warp-autonomous: a warp owns EGW consecutive 32-record blocks (one title
+ * block = one warp = one lane per record), streams each block's bytes into its own shared-memory stage with the
+ * bulk-copy engine and never meets the other warps of the CTA after the tables are loaded -- no block barrier in the
+ * loop, so a warp with long or ambiguous records does not hold the others up.
+ * dynamic shared memory: [pk_bytes packed quality tables][EW stages of enc_stage bytes] */
+constexpr int EW = 8;   /* warps per encoder CTA */
+constexpr int EGW = 8;  /* 32-record blocks per warp */
 
-__global__ void __launch_bounds__(CH) k_lengths(Dev d) {
+struct WarpStage {
+  u32 buf_a, bar_a, phase;
+  const u8 *buf;
+  __device__ __forceinline__ void init(void *smem, u64 *bar, bool leader) { /* followed by a barrier of the caller */
+    buf = (const u8 *)smem; buf_a = (u32)__cvta_generic_to_shared(smem); bar_a = (u32)__cvta_generic_to_shared(bar); phase = 0;
+    if (leader) { mbar_init(bar_a, 1); mbar_fence_init(); }
+  }
+  __device__ __forceinline__ void request(const u8 *in, u32 lo, u32 hi) const { span_request(in, lo, hi, buf_a, bar_a); } /* one lane */
+  __device__ __forceinline__ const u8 *wait(u32 lo) { mbar_wait(bar_a, phase); phase ^= 1u; return buf - (lo & ~15u); }
+};
+
+__global__ void __launch_bounds__(EW * 32) k_lengths(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
   __shared__ __align__(16) u8 xq[256];
   __shared__ __align__(16) u8 lut[256];
-  __shared__ u32 ws[3][4];
-  __shared__ __align__(8) u64 bar;
-  __shared__ u32 c_lo[ENG + 1];
-  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const SbClass &C = d.cls[s];
+  __shared__ __align__(8) u64 bars[EW];
+  __shared__ u32 g_lo[EW][EGW + 1];
+  const u32 s = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  SbClass &C = d.cls[s];
   if (C.status) return;
-  const u32 nchunk = C.nchunk, c0 = blockIdx.x * ENG, c1 = min(c0 + ENG, nchunk);
-  if (c0 >= nchunk) return;
+  const u32 nblk = C.nblk;
+  if (blockIdx.x * (EW * EGW) >= nblk) return;
+  const u32 g0 = min((blockIdx.x * EW + w) * EGW, nblk), g1 = min(g0 + EGW, nblk);
   const SbPlan P = d.plans[s];
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
-  const u32 R = C.R, nnc = C.nnc, plain = C.plain, flagbits_off = C.flagbits_off, blkloc_off = C.blkloc_off, chunk_off = C.chunk_off;
+  const u32 R = C.R, nnc = C.nnc, plain = C.plain, flagbits_off = C.flagbits_off, blk3_off = C.blk3_off;
   WalkTabs T;
-  load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)((u8 *)dyn_smem + d.span_bytes), T);
+  load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)dyn_smem, T);
   load_lut(lut);
   load_title_tabs(C, TT);
-  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * CH, R)];
-  ChunkStage stage; stage.init(dyn_smem, &bar);
+  if (lane <= g1 - g0) g_lo[w][lane] = d.rstart[P.first_rec + min((g0 + lane) * 32, R)];
+  WarpStage stage; stage.init((u8 *)dyn_smem + d.pk_bytes + w * d.enc_stage, &bars[w], lane == 0);
   __syncthreads();
-  if (tid == 0) stage.request(d.in, c_lo[0], c_lo[1]);
-  /* this thread's record of the first chunk (idle lanes shadow the chunk's last record so that warps stay converged) */
+  if (g0 >= g1) return;
+  {
+    bool fits = true;
+    for (u32 k = 0; k < g1 - g0; ++k) fits = fits && g_lo[w][k + 1] - (g_lo[w][k] & ~15u) + 16 <= d.enc_stage;
+    if (!fits) { if (lane == 0) atomicMin(&C.status, (i32)E_UNSUPPORTED); return; } /* records far beyond the reference's 500-byte domain */
+  }
+  if (lane == 0) stage.request(d.in, g_lo[w][0], g_lo[w][1]);
+  /* this lane's record of the first block (idle lanes shadow the block's last record so that the warp stays converged) */
   u32 n_te, n_se, n_rs, n_kx, n_fl = 0;
   {
-    const u32 i = min(c0 * CH + tid, R - 1), r = P.first_rec + i;
+    const u32 i = min(g0 * 32 + lane, R - 1), r = P.first_rec + i;
     n_te = d.te[r]; n_se = d.se[r]; n_rs = d.rstart[r]; n_kx = d.kx[r];
-    if (nnc) n_fl = arena[flagbits_off + i / 32];
+    if (nnc) n_fl = arena[flagbits_off + g0];
   }
-  for (u32 c = c0; c < c1; ++c) {
-    const u32 nrec = min((u32)CH, R - c * CH);
-    const bool active = tid < nrec;
-    const u32 r = P.first_rec + c * CH + (active ? tid : nrec - 1);
+  for (u32 g = g0; g < g1; ++g) {
+    const u32 nrec = min(32u, R - g * 32);
+    const bool active = lane < nrec;
+    const u32 r = P.first_rec + g * 32 + (active ? lane : nrec - 1);
     const u32 te = n_te, se = n_se, rs_r = n_rs, kx = n_kx, myflags = n_fl, L = se - te - 1;
-    if (c + 1 < c1) { /* next chunk's record, in flight while this chunk is walked */
-      const u32 i = min((c + 1) * CH + tid, R - 1), rn = P.first_rec + i;
+    if (g + 1 < g1) { /* next block's record, in flight while this block is walked */
+      const u32 i = min((g + 1) * 32 + lane, R - 1), rn = P.first_rec + i;
       n_te = d.te[rn]; n_se = d.se[rn]; n_rs = d.rstart[rn]; n_kx = d.kx[rn];
-      if (nnc) n_fl = arena[flagbits_off + i / 32];
+      if (nnc) n_fl = arena[flagbits_off + g + 1];
     }
-    const u8 *b = stage.wait(c_lo[c - c0]);
+    const u8 *b = stage.wait(g_lo[w][g - g0]);
     u32 qbits = 0, dbits = 0;
     {
       const bool xfer = kx >> 15;
@@ -1248,44 +1271,31 @@ __global__ void __launch_bounds__(CH) k_lengths(Dev d) {
       }
       if (!active) dbits = 0;
     }
-    u32 blk_bytes = 0, tb = 0, tx = 0;
+    u32 tb = 0, tx = 0;
     if (nnc) {
       __syncwarp();
       CountSink t; t.init();
       title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, myflags, lane == 0, PrevShfl(), t);
       tb = active ? (u32)t.bits : 0u; tx = tb;
     }
-    /* offsets inside the chunk: the three warp scans run together, one exchange through shared memory */
+    __syncwarp(); /* every lane has left the stage */
+    if (lane == 0 && g + 1 < g1) stage.request(d.in, g_lo[w][g + 1 - g0], g_lo[w][g + 2 - g0]);
+    /* offsets inside the block */
     u32 qx = qbits, dx = dbits;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u32 yq = __shfl_up_sync(0xFFFFFFFFu, qx, o), yd = __shfl_up_sync(0xFFFFFFFFu, dx, o), yt = __shfl_up_sync(0xFFFFFFFFu, tx, o);
       if (lane >= (u32)o) { qx += yq; dx += yd; tx += yt; }
     }
-    if (nnc) {
-      if (active) d.toff[r] = tx - tb; /* bits of the block's earlier records (the flag bits come on top) */
-      const u32 sum = __shfl_sync(0xFFFFFFFFu, tx, 31);
-      if ((tid & ~31u) < nrec) blk_bytes = (nnc + sum + 7) / 8;
+    if (active) {
+      d.qoff[r] = qx - qbits; d.doff[r] = dx - dbits;
+      if (nnc) d.toff[r] = tx - tb; /* bits of the block's earlier records (the flag bits come on top) */
     }
-    if (lane == 31) { ws[0][w] = qx; ws[1][w] = dx; }
-    if (lane == 0) ws[2][w] = blk_bytes;
-    __syncthreads();
-    u32 qbase = 0, dbase = 0, tloc = 0, qtot = 0, dtot = 0, ttot = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const u32 a = ws[0][k], e = ws[1][k], g = ws[2][k];
-      if ((u32)k < w) { qbase += a; dbase += e; tloc += g; }
-      qtot += a; dtot += e; ttot += g;
+    if (lane == 31) {
+      arena[blk3_off + g] = qx;
+      arena[blk3_off + nblk + g] = dx;
+      arena[blk3_off + 2 * nblk + g] = nnc ? (nnc + tx + 7) / 8 : 0u;
     }
-    if (active) { d.qoff[r] = qbase + qx - qbits; d.doff[r] = dbase + dx - dbits; }
-    if (lane == 0 && (tid & ~31u) < nrec) arena[blkloc_off + c * (CH / 32) + w] = tloc; /* title block offsets local to the chunk */
-    if (tid == 0) {
-      arena[chunk_off + c] = qtot;
-      arena[chunk_off + nchunk + c] = dtot;
-      arena[chunk_off + 2 * nchunk + c] = ttot;
-    }
-    __syncthreads(); /* every thread has left the stage buffer (and ws) */
-    if (tid == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
   }
 }
 
@@ -1332,9 +1342,9 @@ __global__ void __launch_bounds__(256) k_layout(Dev d) {
       for (u32 i = tid & 31; i < tlen[t]; i += 32) dst[i] = src[i];
     }
   }
-  u64 qb = cta_scan_inplace(arena + C.chunk_off, C.nchunk, ws, &ovf);
-  u64 db = cta_scan_inplace(arena + C.chunk_off + C.nchunk, C.nchunk, ws, &ovf);
-  u64 tb = C.nnc ? cta_scan_inplace(arena + C.chunk_off + 2 * C.nchunk, C.nchunk, ws, &ovf) : 0;
+  u64 qb = cta_scan_inplace(arena + C.blk3_off, C.nblk, ws, &ovf);
+  u64 db = cta_scan_inplace(arena + C.blk3_off + C.nblk, C.nblk, ws, &ovf);
+  u64 tb = C.nnc ? cta_scan_inplace(arena + C.blk3_off + 2 * C.nblk, C.nblk, ws, &ovf) : 0;
   __syncthreads();
   if (tid == 0) {
     if (ovf || tb > 0x7FFFFFFFull) { C.status = E_CAPACITY; return; }
@@ -1382,22 +1392,32 @@ __device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
   if (v) atomicOr((u32 *)(base + (pos & ~3u)), (u32)v << (8 * (pos & 3u)));
 }
 
-/* Two threads per record: threads 0..127 write the info length bits and the quality codes, threads 128..255 the DNA
- * and the title tokens.  The streams are independent, and twice the warps per staged span hide twice the latency. */
-constexpr int EMIT_THREADS = 2 * CH;
-__global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
+/* k_emit<false>: one warp per 32-record block writes all four streams (short records: enough warps fit an SM).
+ * k_emit<true> pairs two warps on every block: the even warp writes the info length bits and the quality codes, the
+ * odd warp the DNA and the title tokens.  The streams are independent, the pair shares one stage (twice the warps per
+ * staged byte -- what long records need to keep an SM busy) and meets only at its own named barrier before the next
+ * block is requested. */
+constexpr int EP = EW / 2; /* warp pairs (= stages) per k_emit<true> CTA */
+__device__ __forceinline__ void pair_sync(u32 pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+template <bool PAIR>
+__global__ void __launch_bounds__(EW * 32, PAIR ? 5 : 4) k_emit(Dev d) {
+  constexpr u32 NST = PAIR ? EP : EW; /* stages per CTA */
   extern __shared__ uint4 dyn_smem[];
   __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
   __shared__ __align__(16) u8 xq[256];
   __shared__ __align__(16) u8 lut[256];
-  __shared__ __align__(8) u64 bar;
-  __shared__ u32 c_lo[ENG + 1];
-  const u32 s = blockIdx.y, role = threadIdx.x / CH, tid = threadIdx.x % CH, lane = tid & 31, w = tid >> 5;
+  __shared__ __align__(8) u64 bars[NST];
+  __shared__ u32 g_lo[NST][EGW + 1];
+  const u32 s = blockIdx.y, lane = threadIdx.x & 31, w = PAIR ? threadIdx.x >> 6 : threadIdx.x >> 5; /* w: stage */
+  const u32 role = PAIR ? (threadIdx.x >> 5) & 1u : 0u;
+  const bool do_q = !PAIR || role == 0, do_d = !PAIR || role == 1;
   const SbClass &C = d.cls[s];
   if (C.status) return;
-  const u32 nchunk = C.nchunk, c0 = blockIdx.x * ENG, c1 = min(c0 + ENG, nchunk);
-  if (c0 >= nchunk) return;
+  const u32 nblk = C.nblk;
+  if (blockIdx.x * (NST * EGW) >= nblk) return;
+  const u32 g0 = min((blockIdx.x * NST + w) * EGW, nblk), g1 = min(g0 + EGW, nblk);
   const SbPlan P = d.plans[s];
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
@@ -1405,30 +1425,15 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
   u32 *outw = (u32 *)d.out;
   const u64 obase = C.out_off; /* byte offset of the payload inside d.out (16-byte aligned) */
   const u32 R = C.R, nnc = C.nnc, nb_len = C.nb_len;
-  const bool tit = role == 1 && nnc;
   WalkTabs T;
-  load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)((u8 *)dyn_smem + d.span_bytes), T);
+  load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)dyn_smem, T);
   load_lut(lut);
   load_title_tabs(C, TT);
-  if (threadIdx.x <= c1 - c0) c_lo[threadIdx.x] = d.rstart[P.first_rec + min((c0 + threadIdx.x) * CH, R)];
-  ChunkStage stage; stage.init(dyn_smem, &bar);
+  if (role == 0 && lane <= g1 - g0) g_lo[w][lane] = d.rstart[P.first_rec + min((g0 + lane) * 32, R)];
+  WarpStage stage; stage.init((u8 *)dyn_smem + d.pk_bytes + w * d.enc_stage, &bars[w], role == 0 && lane == 0);
   __syncthreads();
-  if (threadIdx.x == 0) stage.request(d.in, c_lo[0], c_lo[1]);
   const u32 o_title = C.info_len, o_qual = o_title + C.title_len, o_dna = o_qual + C.qual_len;
-  /* bit positions of the three bodies inside d.out */
-  const u64 q_bit0 = (obase + o_qual + C.qhdr_len) * 8, d_bit0 = (obase + o_dna + C.dhdr_len) * 8, t_byte0 = obase + o_title + C.thdr_len;
-  const u32 *cbase_p = arena + C.chunk_off + role * nchunk, *tbase_p = arena + C.chunk_off + 2 * nchunk, *blkloc_p = arena + C.blkloc_off;
-  const u32 *flag_p = arena + C.flagbits_off;
-  const u32 *off_p = role == 0 ? d.qoff : d.doff;
-  /* this thread's record of the first chunk (idle lanes shadow the chunk's last record); role 0 needs the quality
-   * offsets, role 1 the DNA and title offsets */
-  u32 n_te, n_se, n_kx, n_off, n_cbase, n_rs = 0, n_toff = 0, n_fl = 0, n_tblk = 0;
-  {
-    const u32 i = min(c0 * CH + tid, R - 1), r = P.first_rec + i;
-    n_te = d.te[r]; n_se = d.se[r]; n_kx = d.kx[r]; n_off = off_p[r]; n_cbase = cbase_p[c0];
-    if (tit) { n_rs = d.rstart[r]; n_toff = d.toff[r]; n_fl = flag_p[i / 32]; n_tblk = tbase_p[c0] + blkloc_p[c0 * (CH / 32) + w]; }
-  }
-  if (c0 == 0) {
+  if (blockIdx.x == 0) {
     /* fixed part of the info stream (phyNGSC.cpp:719-730) and the three staged headers.  Bytes are OR-ed
      * into the zeroed payload word-atomically because a header may end inside a word whose other bytes
      * belong to a bit stream written by another thread. */
@@ -1440,35 +1445,54 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
       for (u32 i = 0; i < INFO_FIXED; ++i) or_byte(out, i, fx[i]);
     }
     const u8 *hs = (const u8 *)(arena + C.stage_off);
-    for (u32 i = threadIdx.x; i < C.thdr_len; i += EMIT_THREADS) or_byte(out, o_title + i, hs[i]);
-    for (u32 i = threadIdx.x; i < C.qhdr_len; i += EMIT_THREADS) or_byte(out, o_qual + i, hs[C.thdr_cap + i]);
-    for (u32 i = threadIdx.x; i < C.dhdr_len; i += EMIT_THREADS) or_byte(out, o_dna + i, hs[C.thdr_cap + C.qhdr_cap + i]);
+    for (u32 i = threadIdx.x; i < C.thdr_len; i += EW * 32) or_byte(out, o_title + i, hs[i]);
+    for (u32 i = threadIdx.x; i < C.qhdr_len; i += EW * 32) or_byte(out, o_qual + i, hs[C.thdr_cap + i]);
+    for (u32 i = threadIdx.x; i < C.dhdr_len; i += EW * 32) or_byte(out, o_dna + i, hs[C.thdr_cap + C.qhdr_cap + i]);
   }
-  for (u32 c = c0; c < c1; ++c) {
-    const u32 nrec = min((u32)CH, R - c * CH);
-    const bool active = tid < nrec;
-    const u32 i_sb = c * CH + (active ? tid : nrec - 1); /* record index inside the subblock */
-    const u32 te = n_te, se = n_se, kx = n_kx, my_off = n_off, cbase = n_cbase, rs_r = n_rs, my_toff = n_toff, flags = n_fl, tblk = n_tblk;
+  if (g0 >= g1) return;
+  if (role == 0 && lane == 0) stage.request(d.in, g_lo[w][0], g_lo[w][1]); /* k_lengths has checked that every block fits its stage */
+  /* bit positions of the three bodies inside d.out; per 32-record block: base of its quality bits, DNA bits, title bytes */
+  const u64 q_bit0 = (obase + o_qual + C.qhdr_len) * 8, d_bit0 = (obase + o_dna + C.dhdr_len) * 8, t_byte0 = obase + o_title + C.thdr_len;
+  const u32 *qbase_p = arena + C.blk3_off, *dbase_p = qbase_p + nblk, *tbase_p = dbase_p + nblk, *flag_p = arena + C.flagbits_off;
+  /* this lane's record of the first block (idle lanes shadow the block's last record) */
+  const bool tit = do_d && nnc;
+  u32 n_te, n_se, n_kx, n_qoff = 0, n_doff = 0, n_qb = 0, n_db = 0, n_rs = 0, n_toff = 0, n_fl = 0, n_tb = 0;
+  {
+    const u32 i = min(g0 * 32 + lane, R - 1), r = P.first_rec + i;
+    n_te = d.te[r]; n_se = d.se[r]; n_kx = d.kx[r];
+    if (PAIR) { n_qoff = (role ? d.doff : d.qoff)[r]; n_qb = (role ? dbase_p : qbase_p)[g0]; } /* the role's own stream */
+    else { n_qoff = d.qoff[r]; n_qb = qbase_p[g0]; n_doff = d.doff[r]; n_db = dbase_p[g0]; }
+    if (tit) { n_rs = d.rstart[r]; n_toff = d.toff[r]; n_fl = flag_p[g0]; n_tb = tbase_p[g0]; }
+  }
+  for (u32 g = g0; g < g1; ++g) {
+    const u32 nrec = min(32u, R - g * 32);
+    const bool active = lane < nrec;
+    const u32 i_sb = g * 32 + (active ? lane : nrec - 1); /* record index inside the subblock */
+    const u32 te = n_te, se = n_se, kx = n_kx, qoff = n_qoff, qb = n_qb, doff = PAIR ? n_qoff : n_doff, db = PAIR ? n_qb : n_db;
+    const u32 rs_r = n_rs, my_toff = n_toff, flags = n_fl, tblk = n_tb;
     const u32 L = se - te - 1;
-    if (c + 1 < c1) { /* next chunk's record, in flight while this chunk is encoded */
-      const u32 i = min((c + 1) * CH + tid, R - 1), rn = P.first_rec + i;
-      n_te = d.te[rn]; n_se = d.se[rn]; n_kx = d.kx[rn]; n_off = off_p[rn]; n_cbase = cbase_p[c + 1];
-      if (tit) { n_rs = d.rstart[rn]; n_toff = d.toff[rn]; n_fl = flag_p[i / 32]; n_tblk = tbase_p[c + 1] + blkloc_p[(c + 1) * (CH / 32) + w]; }
+    if (g + 1 < g1) { /* next block's record, in flight while this block is encoded */
+      const u32 i = min((g + 1) * 32 + lane, R - 1), rn = P.first_rec + i;
+      n_te = d.te[rn]; n_se = d.se[rn]; n_kx = d.kx[rn];
+      if (PAIR) { n_qoff = (role ? d.doff : d.qoff)[rn]; n_qb = (role ? dbase_p : qbase_p)[g + 1]; }
+      else { n_qoff = d.qoff[rn]; n_qb = qbase_p[g + 1]; n_doff = d.doff[rn]; n_db = dbase_p[g + 1]; }
+      if (tit) { n_rs = d.rstart[rn]; n_toff = d.toff[rn]; n_fl = flag_p[g + 1]; n_tb = tbase_p[g + 1]; }
     }
-    const u8 *b = stage.wait(c_lo[c - c0]);
+    const u8 *b = stage.wait(g_lo[w][g - g0]);
     const bool xfer = kx >> 15;
-    if (role == 0) {
+    if (do_q) {
       if (active) { /* per-record length bits of the info stream (phyNGSC.cpp:732-742; always present) */
         OrSink k; k.init(outw, (obase + INFO_FIXED) * 8 + (u64)i_sb * nb_len);
         k.put(L, nb_len); k.finish();
       }
-      /* idle lanes of the last chunk walk the chunk's last record without storing */
-      OrSink q; q.init(outw, q_bit0 + cbase + my_off, active);
+      /* idle lanes of the last block walk the block's last record without storing */
+      OrSink q; q.init(outw, q_bit0 + qb + qoff, active);
       quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
       q.finish();
-    } else {
+    }
+    if (do_d) {
       {
-        OrSink dn; dn.init(outw, d_bit0 + cbase + my_off, active);
+        OrSink dn; dn.init(outw, d_bit0 + db + doff, active);
         dna_walk(b + te + 1, L, xfer, T, dn);
         dn.finish();
       }
@@ -1485,8 +1509,10 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_CTAS) k_emit(Dev d) {
         t.finish();
       }
     }
-    __syncthreads(); /* every thread has left the stage buffer */
-    if (threadIdx.x == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
+    if (g + 1 < g1) { /* every warp that reads the stage has left it */
+      if (PAIR) pair_sync(w); else __syncwarp();
+      if (role == 0 && lane == 0) stage.request(d.in, g_lo[w][g + 1 - g0], g_lo[w][g + 2 - g0]);
+    }
   }
 }
 
