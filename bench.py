@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--shape", default="36bp", choices=sorted(WORKLOADS))
     ap.add_argument("--mb", type=int, default=1000, help="shard size per GPU in MB (10^6 bytes)")
     ap.add_argument("--cpu-sample-mb", type=int, default=256)
-    ap.add_argument("--e2e-batch-mb", type=int, default=256, help="batch size (MiB) of the pipelined end-to-end run")
+    ap.add_argument("--e2e-batch-mb", type=int, default=64, help="batch size (MiB) of the pipelined end-to-end run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
   if (H->status || st.done || st.status) { if (lane == 0) { H->S = 0; H->next_pos = (u64)st.bytes_read; } return; }
   const u32 NR = H->NR, NL = H->NL;
   u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0, max_qchunks = 0;
-  i64 avg_n = 1, avg_b = 128;
+  i64 avg_n = 1;
+  float dens = 1.0f / 128.0f;
   while (!st.done && S < d.max_sb) {
     i64 ws = st.bytes_read - d.batch_base; /* batch-relative window start */
     if (!d.batch_is_final && ws + st.rsize + (i64)d.slack > (i64)d.len) break;
@@ -269,22 +270,48 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     i64 target = ws + st.rsize - st.overlap, size_lim = ws + lim;
     u32 last = F, rs_next = 0xFFFFFFFFu; /* rs_next: rstart[last + 1] when the probe already holds it */
     bool capped = false;
-    /* One round trip in the common case: the title newline of the second record, and a 32-wide probe of the
-     * record table around the interpolated position of the last record, are loaded together. */
-    const i64 guess = (i64)F + (target - (ws + st.rec_start)) * avg_n / avg_b; /* records-per-byte of the previous window */
+    /* One round trip in the common case: the title newline of the second record, and a 128-wide probe (four table
+     * entries per lane) of the record table around the interpolated position of the last record, are loaded together. */
+    const i64 guess = (i64)F + (i64)((float)(target - (ws + st.rec_start)) * dens); /* records per byte of the previous window; the probe absorbs the rounding */
     u32 pbase;
-    { i64 gb = guess - 16; pbase = gb < (i64)F + 2 ? F + 2 : (u32)gb; }
-    const u32 pidx = pbase + lane;
+    { i64 gb = guess - 64; pbase = gb < (i64)F + 2 ? F + 2 : (u32)gb; pbase = (pbase + 3u) & ~3u; }
+    const u32 pidx = pbase + 4 * lane;
+    /* the probe regions of the next two windows are predictable: bring them into L2 while this window is resolved */
+#pragma unroll
+    for (u32 a = 1; a <= 2; ++a) {
+      const u64 nidx = (u64)pidx + a * (u64)avg_n;
+      if (S > 0 && nidx + 3 <= (u64)d.maxrec) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.rstart + nidx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.te + nidx));
+      }
+    }
     const u32 te_f1 = 4ull * (F + 1) < NL ? d.te[F + 1] : 0xFFFFFFFFu;
-    const u32 prs = pidx <= NR ? d.rstart[pidx] : 0xFFFFFFFFu;
-    const u32 pte = pidx >= 1 && 4ull * (pidx - 1) < NL ? d.te[pidx - 1] : 0xFFFFFFFFu; /* title newline of record pidx-1 */
+    uint4 prs = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), pte = prs;
+    if (pidx <= NR) { /* the tables have four entries of slack behind the last record */
+      prs = *(const uint4 *)(d.rstart + pidx); pte = *(const uint4 *)(d.te + pidx);
+      if (pidx + 1 > NR) prs.y = 0xFFFFFFFFu;
+      if (pidx + 2 > NR) prs.z = 0xFFFFFFFFu;
+      if (pidx + 3 > NR) prs.w = 0xFFFFFFFFu;
+    }
     if ((i64)te_f1 < size_lim) {
       u32 m;
-      u32 bal = __ballot_sync(0xFFFFFFFFu, (i64)prs >= target);
-      u32 k = bal ? __ffs(bal) - 1 : 32;
-      bool hit = bal != 0 && (k > 0 || pbase == F + 2) && pbase + k <= NR;
+      const u32 kl = (i64)prs.x >= target ? 0u : (i64)prs.y >= target ? 1u : (i64)prs.z >= target ? 2u : (i64)prs.w >= target ? 3u : 4u;
+      const u32 bal = __ballot_sync(0xFFFFFFFFu, kl < 4u);
+      const u32 hl = bal ? __ffs(bal) - 1 : 0u;
+      const u32 hk = __shfl_sync(0xFFFFFFFFu, kl, hl);
+      const u32 cand = pbase + 4 * hl + hk;
+      const bool hit = bal != 0 && (cand > pbase || pbase == F + 2) && cand <= NR;
       u32 te_last = 0xFFFFFFFFu;
-      if (hit) { m = pbase + k; te_last = __shfl_sync(0xFFFFFFFFu, pte, k); rs_next = __shfl_sync(0xFFFFFFFFu, prs, k); }
+      if (hit) {
+        m = cand;
+        const u32 rsel = hk == 0 ? prs.x : hk == 1 ? prs.y : hk == 2 ? prs.z : prs.w;
+        rs_next = __shfl_sync(0xFFFFFFFFu, rsel, hl);
+        if (m > pbase) { /* te[m - 1] sits in the probe as well */
+          const u32 q = m - 1 - pbase, ql = q >> 2, qk = q & 3u;
+          const u32 tsel = qk == 0 ? pte.x : qk == 1 ? pte.y : qk == 2 ? pte.z : pte.w;
+          te_last = 4ull * (m - 1) < NL ? __shfl_sync(0xFFFFFFFFu, tsel, ql) : 0xFFFFFFFFu;
+        } else te_last = te_f1; /* m == F + 2 */
+      }
       else m = warp_lower_bound(d.rstart, F + 2, NR + 1, target, guess);
       last = m - 1;
       if (last > F + st.record_cap) { last = F + st.record_cap; capped = true; te_last = 0xFFFFFFFFu; rs_next = 0xFFFFFFFFu; }
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     chunk_base += nch;
     max_chunks = max(max_chunks, nch);
     max_qchunks = max(max_qchunks, (P.n_records + QCH - 1) / QCH);
-    avg_n = (i64)P.n_records; avg_b = max((i64)1, (i64)P.bytes_consumed);
+    avg_n = (i64)P.n_records; dens = (float)P.n_records / (float)max((i64)1, (i64)P.bytes_consumed); /* the previous window predicts best: record sizes drift along a file */
     ++S; F = last + 1;
     /* phyNGSC.cpp:745-755 */
     st.bytes_read += (i64)P.bytes_consumed;
