@@ -429,6 +429,20 @@ struct ChunkStage {
   __device__ __forceinline__ const u8 *wait(u32 lo) { mbar_wait(bar_a, phase); phase ^= 1u; return buf - (lo & ~15u); } /* p[pos] valid for the chunk's positions */
 };
 
+/* four bytes at any shared-memory address (may read up to three bytes past them) */
+__device__ __forceinline__ u32 ld4u(const u8 *p) {
+  const u32 a = (u32)(size_t)p & 3u;
+  const u32 *w = (const u32 *)(p - a);
+  return __funnelshift_r(w[0], w[1], 8 * a);
+}
+/* n >= 1 bytes equal?  Both sides in shared memory, any alignment. */
+__device__ __forceinline__ bool eq_bytes(const u8 *x, const u8 *y, u32 n) {
+  u32 diff = 0, p = 0;
+  for (; p + 4 <= n; p += 4) diff |= ld4u(x + p) ^ ld4u(y + p);
+  if (p < n) diff |= (ld4u(x + p) ^ ld4u(y + p)) & (0xFFFFFFFFu >> (8 * (4 - (n - p))));
+  return diff == 0;
+}
+
 /* ---- stat1 ---------------------------------------------------------------------------------------------- */
 struct Stat1S {
   u32 facc[MAXF][8];
@@ -441,6 +455,9 @@ struct Stat1S {
   u32 off0[MAXF], len0[MAXF];
   u32 v0[MAXF];     /* numeric value / is_num of record 0's tokens */
   u8 num0[MAXF];
+  u32 touched, chunk_touched; /* fields some warp found to differ from record 0: so far in this CTA / in the current chunk */
+  u16 run_bytes[MAXF];        /* bytes (tokens and separators) of the run of untouched fields that starts at a field */
+  u8 run_end[MAXF];           /* first field behind that run; == field for a touched one */
   u8 r0[R0_MAX];
 };
 
@@ -575,26 +592,44 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way.
    * Most tokens repeat record 0's: a token whose bytes AND separator equal record 0's is that token, so a warp
    * whose 32 records all pass this comparison neither tokenises the field nor reduces anything -- record 0's own
-   * length and value are folded into the accumulators once per CTA instead. */
+   * length and value are folded into the accumulators once per CTA instead.  Fields that no warp of the CTA has seen
+   * differ so far are compared as whole runs of consecutive fields, four bytes per step (S.run_end / run_bytes are
+   * rebuilt between chunks from the S.touched mask; they steer only how the comparison is done, not its result). */
+  if (tid == 0) {
+    S.chunk_touched = 0;
+    const u32 tm = S.touched;
+    for (u32 f = nf; f-- > 0;) {
+      if ((tm >> f) & 1u) { S.run_end[f] = (u8)f; S.run_bytes[f] = 0; continue; }
+      const bool ext = f + 1 < nf && !((tm >> (f + 1)) & 1u);
+      S.run_end[f] = ext ? S.run_end[f + 1] : (u8)(f + 1);
+      S.run_bytes[f] = (u16)(S.len0[f] + 1 + (ext ? S.run_bytes[f + 1] : 0u));
+    }
+  }
+  __syncthreads();
   const bool walk = active && !err && seed_ok;
   bool fields_ok = true;
+  u32 my_done = 0; /* fields this warp tokenised in this chunk (their values are in the table) */
   TitleCursor cur; cur.init(b, ts, te, lut);
-  for (u32 f = 0; f < nf && seed_ok; ++f) {
+  for (u32 f = 0; f < nf && seed_ok;) {
+    u32 fe = f + 1;
+    if (S.run_end[f] > f) { /* a run of fields that have matched record 0 everywhere so far */
+      fe = S.run_end[f];
+      const u32 rl = S.run_bytes[f];
+      const bool ok = walk && fields_ok;
+      const bool same = ok && cur.pos + rl - 1 <= te && eq_bytes(b + cur.pos, S.r0 + S.off0[f], rl);
+      if (__all_sync(0xFFFFFFFFu, same || !ok)) { if (same) cur.pos += rl; f = fe; continue; }
+    }
+    for (; f < fe; ++f) {
     const u32 len0 = S.len0[f];
     const u8 *d0 = S.r0 + S.off0[f];
     bool ok = walk && fields_ok;
-    bool same = ok && cur.pos + len0 <= te;
-    if (same) {
-      const u8 *dp = b + cur.pos;
-      u32 diff = 0;
-      for (u32 p = 0; p <= len0; ++p) diff |= (u32)(dp[p] ^ d0[p]);
-      same = diff == 0;
-    }
+    const bool same = ok && cur.pos + len0 <= te && eq_bytes(b + cur.pos, d0, len0 + 1);
     if (__all_sync(0xFFFFFFFFu, same || !ok)) {
-      vals[f * CH + tid] = S.v0[f];
       if (same) cur.pos += len0 + 1;
       continue;
     }
+    my_done |= 1u << f;
+    if (lane == 0 && !((S.chunk_touched >> f) & 1u)) { atomicOr(&S.chunk_touched, 1u << f); atomicOr(&S.touched, 1u << f); }
     Tok t; t.start = t.end = 0; t.v = 0; t.num = true;
     u32 len = 0;
     if (ok && !cur.next(t)) { fields_ok = false; ok = false; t.start = t.end = 0; t.v = 0; t.num = true; }
@@ -626,17 +661,25 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       if (nn) S.facc[f][2] = 1;
       atomicMax(&S.facc[f][3], kmax); atomicMax(&S.facc[f][4], kinv);
     }
+    }
   }
   if (walk && (!fields_ok || cur.pos <= cur.lim)) err = E_FIELDS; /* fewer or more separators than record 0 */
+  __syncthreads();
+  /* fields that some warp of the chunk tokenised need every record's value: the other warps fill in record 0's */
+  const u32 ct = seed_ok ? S.chunk_touched : 0u;
+  for (u32 m = ct & ~my_done; m; m &= m - 1) { const u32 f = __ffs(m) - 1; vals[f * CH + tid] = S.v0[f]; }
   __syncthreads();
   /* deltas inside the chunk; the delta across the chunk boundary is folded in by k_xdelta from the values of
    * the chunk's first / last record, so that no thread has to parse the neighbouring chunk's record */
   if (seed_ok && tid < nf) {
     const size_t row = ((size_t)P.chunk_base + c) * MAXF + tid;
-    d.chunk_first[row] = vals[tid * CH];
-    d.chunk_last[row] = vals[tid * CH + nrec - 1];
+    const bool in_table = (ct >> tid) & 1u;
+    d.chunk_first[row] = in_table ? vals[tid * CH] : S.v0[tid];
+    d.chunk_last[row] = in_table ? vals[tid * CH + nrec - 1] : S.v0[tid];
+    if (!in_table && nrec >= 2) { atomicMax(&S.facc[tid][5], key_of(0)); atomicMax(&S.facc[tid][6], ~key_of(0)); } /* every delta inside the chunk is 0 */
   }
-  for (u32 f = 0; f < nf && seed_ok; ++f) {
+  for (u32 m = ct; m; m &= m - 1) {
+    const u32 f = __ffs(m) - 1;
     const bool hasd = walk && tid > 0;
     u32 pv = tid > 0 ? vals[f * CH + tid - 1] : 0u;
     u32 kd = key_of((i32)(vals[f * CH + tid] - pv));

@@ -4,14 +4,18 @@ import csv
 import sys
 
 
-def main(path, title):
+def main(path, title, first=None):
     lines = open(path).read().splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
     rows = list(csv.DictReader(lines[start:]))
     agg = collections.OrderedDict()
+    seen = 0
     for r in rows:
         if r["Metric Name"] != "gpu__time_duration.sum":
             continue
+        seen += 1
+        if first is not None and seen > first:
+            break
         scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[r["Metric Unit"]]
         agg.setdefault(r["Kernel Name"].split("(")[0], []).append(float(r["Metric Value"].replace(",", "")) * scale)
     tot = sum(sum(v) for v in agg.values())
@@ -23,4 +27,5 @@ def main(path, title):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1])
+    # optional third argument: only the first N launches (bench.py's kernel-only region: (warmup + steps) x launches per step)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], int(sys.argv[3]) if len(sys.argv) > 3 else None)
