@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   if (Lp == 0) return;
   u32 *raw = raw_table(d, s);
   const u32 RP = Lp < d.qh_rows ? Lp : d.qh_rows;  /* rows (read positions) per pass */
-  const u32 slots = RP < 256 ? 256 / RP : 1u;      /* records the CTA counts side by side */
+  const u32 slots = RP < 256 ? min(256 / RP, 64u / QU) : 1u; /* records the CTA counts side by side (the list padding holds QU * slots dummies) */
   u32 *hist = (u32 *)dyn_smem;
   const u32 nbuf = d.qh_nbuf;
   const u32 hist_a = (u32)__cvta_generic_to_shared(hist), buf_a0 = hist_a + ((d.qh_rows * (QR_ROWW * 4) + 15u) & ~15u), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);

@@ -73,12 +73,51 @@ CASES = [  # (name, shape, seed, bytes, np, window_bytes)
     ("36bp_full_window", "36bp", 31, 20_000_000, 2, 1 << 23),
     ("100bp_full_window", "100bp", 32, 20_000_000, 2, 1 << 23),
     ("mixed_amb_record_cap", "mixed_amb", 33, 12_000_000, 2, 1 << 23),
+    ("long300_two_position_passes", "py:long300", 34, 3_000_000, 2, 1 << 20),
+    ("odd_quality_bytes", "py:odd_qual", 35, 1_500_000, 2, 512 * 1024),
+    ("tiny_reads", "py:tiny", 36, 600_000, 2, 128 * 1024),
 ]
+
+
+def py_fastq(kind, seed, nbytes):
+    """Inputs the C generator has no shape for (each exercises one path of the CUDA kernels):
+    long300    300 bp reads: more read positions than the 256 rows of k_qhist's private table (second pass over the
+               positions), records beyond the reference's 500-byte overlap
+    odd_qual   quality bytes outside 33..127 (>= 128, < 33) in records without ambiguity codes: k_qhist's exact recount
+    tiny       reads of 1..6 bases: tails of the four-bases-per-step loops, blocks with very few payload bits
+    """
+    rng = np.random.default_rng(seed)
+    out = []
+    n = 0
+    i = 0
+    while n < nbytes:
+        i += 1
+        if kind == "long300":
+            L = 300
+            title = f"@LR{seed}.{i} run:{i % 7}:{(i * 37) % 1000} len={L}"
+        elif kind == "tiny":
+            L = int(rng.integers(1, 7))
+            title = f"@T.{i} {i % 3}/1"
+        else:
+            L = 36
+            title = f"@OQ.{i} x_{(i * 13) % 500:03d}:{i % 2047}/2"
+        seq = rng.choice(np.frombuffer(b"ACGT", np.uint8), L)
+        qual = rng.choice(np.arange(35, 74, dtype=np.uint8), L, p=None)
+        if kind == "odd_qual" and rng.random() < 0.02:
+            k = int(rng.integers(0, L))
+            qual[k] = int(rng.choice([200, 255, 128, 31, 9, 127]))
+        if kind == "long300" and rng.random() < 0.03:
+            k = int(rng.integers(0, L))
+            seq[k] = ord("N"); qual[k] = 35
+        rec = title.encode() + b"\n" + seq.tobytes() + b"\n+\n" + qual.tobytes() + b"\n"
+        out.append(rec)
+        n += len(rec)
+    return np.frombuffer(b"".join(out), np.uint8).copy()
 
 
 def run_case(ctx, case):
     name, shape, seed, nbytes, npr, win = case
-    data = synth.fastq(shape, seed, target_bytes=nbytes + 131)
+    data = py_fastq(shape[3:], seed, nbytes) if shape.startswith("py:") else synth.fastq(shape, seed, target_bytes=nbytes + 131)
     probs = []
     for r in range(npr):
         probs += compare_rank(ctx, data, npr, r, window_bytes=win)
