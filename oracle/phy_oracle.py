@@ -170,8 +170,21 @@ def ref_kat():
         K.ref_huffman.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         K.ref_bitstream.restype = C.c_int
         K.ref_bitstream.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        if hasattr(K, "ref_decode_subblock"):
+            K.ref_decode_subblock.restype = C.c_longlong
+            K.ref_decode_subblock.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_ulonglong]
         _kat = K
     return _kat
+
+
+def ref_decode_subblock(payload, cap):
+    """FASTQ text of one subblock payload, decoded by the reference's own Fetch* functions (oracle/ref_kat.cpp)."""
+    p = np.ascontiguousarray(np.frombuffer(payload, np.uint8) if not isinstance(payload, np.ndarray) else payload)
+    out = np.empty(int(cap), np.uint8)
+    n = ref_kat().ref_decode_subblock(p.ctypes.data, p.size, out.ctypes.data, out.size)
+    if n < 0:
+        raise RuntimeError(f"ref_decode_subblock rc={n}")
+    return out[:n]
 
 
 def ref_huffman(freq, compact=True):

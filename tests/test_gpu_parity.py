@@ -107,3 +107,22 @@ def test_roundtrip_properties_at_full_window_size(ctx):
         assert int.from_bytes(p[0:4], "big") == x.n_records and int.from_bytes(p[4:8], "big") == 150
         assert x.out_len == sum(x.sec_len)
     assert sum(x.n_records for x in d) == int((data == 10).sum()) // 4
+
+
+@pytest.mark.parametrize("shape,mb", [("36bp", 256), ("100bp", 128)])
+def test_full_size_round_trip_through_the_reference_decoder(shape, mb, ctx):
+    """Encode on the GPU -> decode with the reference's own Fetch* functions (oracle/_ref/libphyref_kat.so) -> the
+    input FASTQ, byte for byte, at a size the oracle encoder would need minutes for: every 8 MiB subblock of a
+    multi-batch region call is decoded (one at a time: the reference's Huffman loader keeps function-static scratch)."""
+    from oracle import phy_oracle as O
+    if not (os.path.exists(O.REF_KAT) and hasattr(O.ref_kat(), "ref_decode_subblock")):
+        pytest.skip("oracle/_ref/libphyref_kat.so without the decode hook")
+    data = synth.fastq(shape, 45, target_bytes=mb * 1_000_000)
+    d, out, res = ctx.compress_region(data, api.region_params(data.size, 1, 0))
+    assert res.n_batches > 1 and res.bytes_in == data.size
+    bad = []
+    for i, x in enumerate(d):
+        dec = O.ref_decode_subblock(out[x.out_off:x.out_off + x.out_len], x.bytes_consumed + 4096)
+        if dec.size != x.bytes_consumed or not np.array_equal(dec, data[x.win_off:x.win_off + x.bytes_consumed]):
+            bad.append(i)
+    assert not bad, f"subblocks that do not decode to their input: {bad[:10]}"
