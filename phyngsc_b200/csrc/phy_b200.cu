@@ -179,7 +179,8 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SPAN_MAX + MAXF * CH * 4)));
   CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_DYN_MAX));
-  CK(cudaFuncSetAttribute(k_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
+  CK(cudaFuncSetAttribute(k_lengths<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
+  CK(cudaFuncSetAttribute(k_lengths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
@@ -311,19 +312,22 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     u32 es = (H.max_span32 + 16 + 255) & ~255u;
     d.enc_stage = es > ENC_STAGE_MAX ? ENC_STAGE_MAX : es; /* wider blocks fail their subblock with PHY_ERR_UNSUPPORTED */
   }
-  const dim3 ge((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), S);
-  const u32 enc_dyn = d.pk_bytes + EW * d.enc_stage;
-  k_lengths<<<ge, EW * 32, enc_dyn, st>>>(d); PMARK();
+  /* one warp per 32-record block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
+  static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
+  const u32 solo_dyn = d.pk_bytes + EW * d.enc_stage, pair_dyn = d.pk_bytes + EP * d.enc_stage;
+  const bool pair = pair_env >= 0 ? pair_env != 0 : (solo_dyn + 7 * 1024) * 4 > 227u * 1024;
+  const dim3 ge_solo((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), S), ge_pair((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), S);
+  /* reads of very different lengths: the quality warp of a pair would wait for its longest record while the title warp idles */
+  const bool varlen = H.max_len > 0 && (u64)(H.max_len - ~H.inv_min_len) * 4 > H.max_len;
+  if (pair && !varlen) k_lengths<true><<<ge_pair, EW * 32, pair_dyn, st>>>(d);
+  else k_lengths<false><<<ge_solo, EW * 32, solo_dyn, st>>>(d);
+  PMARK();
   k_layout<<<S, 256, 0, st>>>(d); PMARK();
   k_outscan<<<1, 256, 0, st>>>(d); PMARK();
   k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
-  { /* one warp per block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
-    static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
-    const bool pair = pair_env >= 0 ? pair_env != 0 : (enc_dyn + 7 * 1024) * 4 > 227u * 1024;
-    if (pair) k_emit<true><<<dim3((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), S), EW * 32, d.pk_bytes + EP * d.enc_stage, st>>>(d);
-    else k_emit<false><<<ge, EW * 32, enc_dyn, st>>>(d);
-    PMARK();
-  }
+  if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, st>>>(d);
+  else k_emit<false><<<ge_solo, EW * 32, solo_dyn, st>>>(d);
+  PMARK();
   ctx->launches += 13;
   CK(cudaGetLastError());
   if (ctx->profile) {

@@ -51,6 +51,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
   u32 max_len;         /* longest sequence line of the batch's subblocks */
+  u32 inv_min_len;     /* ~(shortest sequence line) */
   u32 max_span64, max_span32; /* widest 64- / 32-record span (k_qhist may stage smaller groups than the 128-record chunk) */
 };
 
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->inv_min_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
   if (s >= d.hdr->S) return; /* launched for the context's capacity: the host learns S only afterwards */
   const SbPlan P = d.plans[s];
   if (P.status) return;
-  u32 mx = 0, m64 = 0, m32 = 0, ml = 0;
+  u32 mx = 0, m64 = 0, m32 = 0, ml = 0, il = 0;
   for (u32 g = blockIdx.x * 256 + threadIdx.x; g * 32 < P.n_records; g += gridDim.x * 256) { /* 32-record groups */
     const u32 i = g * 32, r0 = P.first_rec + i, n = P.n_records;
     const u32 lo = d.rstart[r0] & ~15u;
@@ -364,13 +365,14 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
     if ((g & 1u) == 0) m64 = max(m64, d.rstart[P.first_rec + min(i + 64, n)] - lo);
     if ((g & 3u) == 0) mx = max(mx, d.rstart[P.first_rec + min(i + CH, n)] - lo);
   }
-  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) ml = max(ml, d.se[P.first_rec + i] - d.te[P.first_rec + i] - 1);
+  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) { const u32 L = d.se[P.first_rec + i] - d.te[P.first_rec + i] - 1; ml = max(ml, L); il = max(il, ~L); }
   mx = __reduce_max_sync(0xFFFFFFFFu, mx); m64 = __reduce_max_sync(0xFFFFFFFFu, m64); m32 = __reduce_max_sync(0xFFFFFFFFu, m32);
-  ml = __reduce_max_sync(0xFFFFFFFFu, ml);
+  ml = __reduce_max_sync(0xFFFFFFFFu, ml); il = __reduce_max_sync(0xFFFFFFFFu, il);
   if ((threadIdx.x & 31) == 0 && mx) atomicMax(&d.hdr->max_span, mx);
   if ((threadIdx.x & 31) == 0 && m64) atomicMax(&d.hdr->max_span64, m64);
   if ((threadIdx.x & 31) == 0 && m32) atomicMax(&d.hdr->max_span32, m32);
   if ((threadIdx.x & 31) == 0 && ml) atomicMax(&d.hdr->max_len, ml);
+  if ((threadIdx.x & 31) == 0 && il) atomicMax(&d.hdr->inv_min_len, il);
   if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&d.hdr->max_nf, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
 }
 
@@ -1277,30 +1279,42 @@ struct WarpStage {
   __device__ __forceinline__ const u8 *wait(u32 lo) { mbar_wait(bar_a, phase); phase ^= 1u; return buf - (lo & ~15u); }
 };
 
+constexpr int EP = EW / 2; /* warp pairs (= stages) per CTA of the paired encoder kernels */
+__device__ __forceinline__ void pair_sync(u32 pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+/* k_lengths<false>: one warp per 32-record block counts all three streams.  k_lengths<true>: two warps share a block's
+ * stage -- the even warp counts the quality bits, the odd warp the DNA bits and the title bits; each scans and stores
+ * its own offsets, so the pair only meets at its named barrier before the next block is requested (long records:
+ * twice the warps per staged byte). */
+template <bool PAIR>
 __global__ void __launch_bounds__(EW * 32) k_lengths(Dev d) {
+  constexpr u32 NST = PAIR ? EP : EW; /* stages per CTA */
   extern __shared__ uint4 dyn_smem[];
   __shared__ TitleTabs TT;
   __shared__ __align__(16) u8 codes[512];
   __shared__ __align__(16) u8 xq[256];
   __shared__ __align__(16) u8 lut[256];
-  __shared__ __align__(8) u64 bars[EW];
-  __shared__ u32 g_lo[EW][EGW + 1];
-  const u32 s = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ __align__(8) u64 bars[NST];
+  __shared__ u32 g_lo[NST][EGW + 1];
+  const u32 s = blockIdx.y, lane = threadIdx.x & 31, w = PAIR ? threadIdx.x >> 6 : threadIdx.x >> 5; /* w: stage */
+  const u32 role = PAIR ? (threadIdx.x >> 5) & 1u : 0u;
+  const bool do_q = !PAIR || role == 0, do_d = !PAIR || role == 1;
   SbClass &C = d.cls[s];
   if (C.status) return;
   const u32 nblk = C.nblk;
-  if (blockIdx.x * (EW * EGW) >= nblk) return;
-  const u32 g0 = min((blockIdx.x * EW + w) * EGW, nblk), g1 = min(g0 + EGW, nblk);
+  if (blockIdx.x * (NST * EGW) >= nblk) return;
+  const u32 g0 = min((blockIdx.x * NST + w) * EGW, nblk), g1 = min(g0 + EGW, nblk);
   const SbPlan P = d.plans[s];
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   const TableDesc *td = (const TableDesc *)(arena + C.tabdesc_off);
   const u32 R = C.R, nnc = C.nnc, plain = C.plain, flagbits_off = C.flagbits_off, blk3_off = C.blk3_off;
+  const bool tit = do_d && nnc;
   WalkTabs T;
   load_walk_tabs(d, C, arena, td, codes, xq, (u16 *)dyn_smem, T);
   load_lut(lut);
   load_title_tabs(C, TT);
-  if (lane <= g1 - g0) g_lo[w][lane] = d.rstart[P.first_rec + min((g0 + lane) * 32, R)];
-  WarpStage stage; stage.init((u8 *)dyn_smem + d.pk_bytes + w * d.enc_stage, &bars[w], lane == 0);
+  if (role == 0 && lane <= g1 - g0) g_lo[w][lane] = d.rstart[P.first_rec + min((g0 + lane) * 32, R)];
+  WarpStage stage; stage.init((u8 *)dyn_smem + d.pk_bytes + w * d.enc_stage, &bars[w], role == 0 && lane == 0);
   __syncthreads();
   if (g0 >= g1) return;
   {
@@ -1308,13 +1322,13 @@ __global__ void __launch_bounds__(EW * 32) k_lengths(Dev d) {
     for (u32 k = 0; k < g1 - g0; ++k) fits = fits && g_lo[w][k + 1] - (g_lo[w][k] & ~15u) + 16 <= d.enc_stage;
     if (!fits) { if (lane == 0) atomicMin(&C.status, (i32)E_UNSUPPORTED); return; } /* records far beyond the reference's 500-byte domain */
   }
-  if (lane == 0) stage.request(d.in, g_lo[w][0], g_lo[w][1]);
+  if (role == 0 && lane == 0) stage.request(d.in, g_lo[w][0], g_lo[w][1]);
   /* this lane's record of the first block (idle lanes shadow the block's last record so that the warp stays converged) */
-  u32 n_te, n_se, n_rs, n_kx, n_fl = 0;
+  u32 n_te, n_se, n_rs = 0, n_kx, n_fl = 0;
   {
     const u32 i = min(g0 * 32 + lane, R - 1), r = P.first_rec + i;
-    n_te = d.te[r]; n_se = d.se[r]; n_rs = d.rstart[r]; n_kx = d.kx[r];
-    if (nnc) n_fl = arena[flagbits_off + g0];
+    n_te = d.te[r]; n_se = d.se[r]; n_kx = d.kx[r];
+    if (tit) { n_rs = d.rstart[r]; n_fl = arena[flagbits_off + g0]; }
   }
   for (u32 g = g0; g < g1; ++g) {
     const u32 nrec = min(32u, R - g * 32);
@@ -1323,16 +1337,18 @@ __global__ void __launch_bounds__(EW * 32) k_lengths(Dev d) {
     const u32 te = n_te, se = n_se, rs_r = n_rs, kx = n_kx, myflags = n_fl, L = se - te - 1;
     if (g + 1 < g1) { /* next block's record, in flight while this block is walked */
       const u32 i = min((g + 1) * 32 + lane, R - 1), rn = P.first_rec + i;
-      n_te = d.te[rn]; n_se = d.se[rn]; n_rs = d.rstart[rn]; n_kx = d.kx[rn];
-      if (nnc) n_fl = arena[flagbits_off + g + 1];
+      n_te = d.te[rn]; n_se = d.se[rn]; n_kx = d.kx[rn];
+      if (tit) { n_rs = d.rstart[rn]; n_fl = arena[flagbits_off + g + 1]; }
     }
     const u8 *b = stage.wait(g_lo[w][g - g0]);
-    u32 qbits = 0, dbits = 0;
-    {
-      const bool xfer = kx >> 15;
+    const bool xfer = kx >> 15;
+    u32 qbits = 0, dbits = 0, tb = 0;
+    if (do_q) {
       CountSink q; q.init();
       quality_walk(b + se + 3, b + te + 1, L, xfer, T, q);
       qbits = active ? (u32)q.bits : 0u;
+    }
+    if (do_d) {
       if (plain) dbits = 2 * (kx & 0x7FFFu);
       else {
         CountSink dn; dn.init();
@@ -1340,31 +1356,40 @@ __global__ void __launch_bounds__(EW * 32) k_lengths(Dev d) {
         dbits = (u32)dn.bits;
       }
       if (!active) dbits = 0;
+      if (nnc) {
+        __syncwarp();
+        CountSink t; t.init();
+        title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, myflags, lane == 0, PrevShfl(), t);
+        tb = active ? (u32)t.bits : 0u;
+      }
     }
-    u32 tb = 0, tx = 0;
-    if (nnc) {
-      __syncwarp();
-      CountSink t; t.init();
-      title_record(b, lut, rs_r, te, C, TT.fc, TT.ncf, TT.ncskip, arena, myflags, lane == 0, PrevShfl(), t);
-      tb = active ? (u32)t.bits : 0u; tx = tb;
+    if (g + 1 < g1) { /* every warp that reads the stage has left it */
+      if (PAIR) pair_sync(w); else __syncwarp();
+      if (role == 0 && lane == 0) stage.request(d.in, g_lo[w][g + 1 - g0], g_lo[w][g + 2 - g0]);
     }
-    __syncwarp(); /* every lane has left the stage */
-    if (lane == 0 && g + 1 < g1) stage.request(d.in, g_lo[w][g + 1 - g0], g_lo[w][g + 2 - g0]);
     /* offsets inside the block */
-    u32 qx = qbits, dx = dbits;
+    if (do_q) {
+      u32 qx = qbits;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 yq = __shfl_up_sync(0xFFFFFFFFu, qx, o), yd = __shfl_up_sync(0xFFFFFFFFu, dx, o), yt = __shfl_up_sync(0xFFFFFFFFu, tx, o);
-      if (lane >= (u32)o) { qx += yq; dx += yd; tx += yt; }
+      for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, qx, o); if (lane >= (u32)o) qx += y; }
+      if (active) d.qoff[r] = qx - qbits;
+      if (lane == 31) arena[blk3_off + g] = qx;
     }
-    if (active) {
-      d.qoff[r] = qx - qbits; d.doff[r] = dx - dbits;
-      if (nnc) d.toff[r] = tx - tb; /* bits of the block's earlier records (the flag bits come on top) */
-    }
-    if (lane == 31) {
-      arena[blk3_off + g] = qx;
-      arena[blk3_off + nblk + g] = dx;
-      arena[blk3_off + 2 * nblk + g] = nnc ? (nnc + tx + 7) / 8 : 0u;
+    if (do_d) {
+      u32 dx = dbits, tx = tb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 yd = __shfl_up_sync(0xFFFFFFFFu, dx, o), yt = __shfl_up_sync(0xFFFFFFFFu, tx, o);
+        if (lane >= (u32)o) { dx += yd; tx += yt; }
+      }
+      if (active) {
+        d.doff[r] = dx - dbits;
+        if (nnc) d.toff[r] = tx - tb; /* bits of the block's earlier records (the flag bits come on top) */
+      }
+      if (lane == 31) {
+        arena[blk3_off + nblk + g] = dx;
+        arena[blk3_off + 2 * nblk + g] = nnc ? (nnc + tx + 7) / 8 : 0u;
+      }
     }
   }
 }
@@ -1467,8 +1492,6 @@ __device__ __forceinline__ void or_byte(u8 *base, u32 pos, u8 v) {
  * odd warp the DNA and the title tokens.  The streams are independent, the pair shares one stage (twice the warps per
  * staged byte -- what long records need to keep an SM busy) and meets only at its own named barrier before the next
  * block is requested. */
-constexpr int EP = EW / 2; /* warp pairs (= stages) per k_emit<true> CTA */
-__device__ __forceinline__ void pair_sync(u32 pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
 
 template <bool PAIR>
 __global__ void __launch_bounds__(EW * 32, PAIR ? 5 : 4) k_emit(Dev d) {
