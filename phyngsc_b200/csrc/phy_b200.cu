@@ -15,13 +15,16 @@
 using namespace phy;
 
 #define NKERN 16
+#define GROUPS_MAX 4
 
 static_assert(sizeof(phy_subblock_desc) == 72, "phy_subblock_desc layout is part of the ABI");
 
 struct phy_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t s_rb = nullptr; cudaEvent_t ev_cls = nullptr; BatchHdr *h_hdr2 = nullptr; /* mid-pipeline header readback, overlapped with the statistics kernels */
+  /* subblock groups of a batch: own stream, header (device + pinned mirror) and events */
+  cudaStream_t gstream[GROUPS_MAX] = {}; cudaEvent_t ev_rb[GROUPS_MAX] = {}, ev_scan[GROUPS_MAX] = {}, ev_done[GROUPS_MAX] = {};
+  BatchHdr *hdr_g = nullptr, *h_hdr_g = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   u64 max_batch = 0; u32 max_sb = 0; u32 maxrec = 0; u32 arena_words = 0; u64 out_cap = 0; u32 slack = 0;
   u32 max_tiles = 0;
@@ -116,9 +119,13 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->pev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->s_rb) cudaStreamDestroy(ctx->s_rb);
-  if (ctx->ev_cls) cudaEventDestroy(ctx->ev_cls);
-  if (ctx->h_hdr2) cudaFreeHost(ctx->h_hdr2);
+  for (int g = 0; g < GROUPS_MAX; ++g) {
+    if (ctx->gstream[g]) cudaStreamDestroy(ctx->gstream[g]);
+    cudaEvent_t evs[] = {ctx->ev_rb[g], ctx->ev_scan[g], ctx->ev_done[g]};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+  }
+  if (ctx->hdr_g) cudaFree(ctx->hdr_g);
+  if (ctx->h_hdr_g) cudaFreeHost(ctx->h_hdr_g);
   delete ctx;
 }
 
@@ -137,9 +144,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   ctx->slack = 64 * 1024;
   ctx->max_tiles = (u32)((ctx->max_batch + TILE - 1) / TILE) + 1;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx->s_rb, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&ctx->ev_cls, cudaEventDisableTiming));
-  CK(cudaHostAlloc(&ctx->h_hdr2, sizeof(BatchHdr), cudaHostAllocDefault));
+  CK(cudaMalloc(&ctx->hdr_g, sizeof(BatchHdr) * GROUPS_MAX));
+  CK(cudaHostAlloc(&ctx->h_hdr_g, sizeof(BatchHdr) * GROUPS_MAX, cudaHostAllocDefault));
+  CK(cudaEventCreateWithFlags(&ctx->ev_rb[0], cudaEventDisableTiming));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   CK(cudaMalloc(&ctx->in, ctx->max_batch + 4096));
   CK(cudaMemset(ctx->in, 0, ctx->max_batch + 4096));
@@ -266,12 +273,8 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
-  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(SbAcc) * S, st));
-  dim3 gc(H.max_chunks, S);
+  /* launch geometry shared by all subblock groups of the batch */
   u32 qh_dyn = 0;
-  PMARK();
-  k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, S), CH, span_v, st>>>(d);
-  k_xdelta<<<S, 128, 0, st>>>(d); PMARK();
   { /* k_qhist: private table of min(longest read, 256) rows beside two stage buffers.  Long records are staged in
      * groups of 64 or 32 instead of 128 so that two CTAs still fit an SM (fewer, larger groups beat more CTAs: the
      * per-group barriers and list building are what a CTA spends its time on besides counting). */
@@ -287,56 +290,103 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     d.qh_nbuf = nb;
     qh_dyn = hb + d.qh_nbuf * d.qh_stage;
   }
-  k_qhist<<<dim3(H.max_qchunks, S), 256, qh_dyn, st>>>(d); PMARK();
-  k_classify<<<S, 32, 0, st>>>(d); PMARK();
-  /* the batch header now holds the exact size of the packed quality tables: fetch it on a side stream while the
-   * statistics kernels run, so that the encoder kernels get exactly the shared memory they need */
-  CK(cudaEventRecord(ctx->ev_cls, st));
-  CK(cudaStreamWaitEvent(ctx->s_rb, ctx->ev_cls, 0));
-  CK(cudaMemcpyAsync(ctx->h_hdr2, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, ctx->s_rb));
-  k_zero_hist<<<dim3(8, S), 256, 0, st>>>(d);
-  k_dnacount<<<dim3(16, S), 256, 0, st>>>(d); PMARK();
   {
     static const int nbuf_env = getenv("PHY_S2_NBUF") ? atoi(getenv("PHY_S2_NBUF")) : 1;
     d.s2_nbuf = (nbuf_env == 2 && 2 * span + d.max_nf * CH * 4 <= 200u * 1024) ? 2u : 1u;
-    const u32 dyn = d.s2_nbuf * span + d.max_nf * CH * 4;
-    k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, S), CH, dyn, st>>>(d); PMARK();
   }
-  CK(cudaStreamSynchronize(ctx->s_rb)); /* classify is long done: stat2 keeps the GPU busy meanwhile */
-  {
-    const u32 pk = (ctx->h_hdr2->max_pk_bytes + 15u) & ~15u;
-    d.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
-  }
-  k_huff<<<dim3(16, S), 128, 4 * sizeof(HuffScratch), st>>>(d); PMARK();
+  const u32 s2_dyn = d.s2_nbuf * span + d.max_nf * CH * 4;
   {
     u32 es = (H.max_span32 + 16 + 255) & ~255u;
     d.enc_stage = es > ENC_STAGE_MAX ? ENC_STAGE_MAX : es; /* wider blocks fail their subblock with PHY_ERR_UNSUPPORTED */
   }
-  /* one warp per 32-record block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
+  /* Subblock groups: the subblocks of the batch are split into G consecutive groups that run the rest of the pipeline on
+   * their own streams.  Several of its stages are latency-bound (one warp per subblock in k_classify, one warp per table
+   * in k_huff, one CTA per subblock in k_layout): while one group sits in such a stage the other keeps the SMs busy.
+   * A group sees its own slice of the per-subblock arrays (shifted base pointers) and its own header; the payloads of all
+   * groups still lie back to back because a group's output scan starts at the previous group's end. */
+  static const int groups_env = getenv("PHY_GROUPS") ? atoi(getenv("PHY_GROUPS")) : 3; /* measured on 1 GB: 3.25 / 3.13 / 3.01 / 3.05 ms for 1..4 groups */
+  u32 G = (ctx->profile || dbg_sync || S < 16) ? 1u : (u32)(groups_env < 1 ? 1 : groups_env > GROUPS_MAX ? GROUPS_MAX : groups_env);
+  if (G > 1 && !ctx->gstream[1]) {
+    for (int g = 1; g < GROUPS_MAX; ++g) CK(cudaStreamCreateWithFlags(&ctx->gstream[g], cudaStreamNonBlocking));
+    for (int g = 0; g < GROUPS_MAX; ++g) {
+      if (g) CK(cudaEventCreateWithFlags(&ctx->ev_rb[g], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ctx->ev_scan[g], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done[g], cudaEventDisableTiming));
+    }
+  }
+  Dev dg[GROUPS_MAX];
+  u32 s0[GROUPS_MAX + 1];
+  for (u32 g = 0; g <= G; ++g) s0[g] = (u32)((u64)S * g / G);
+  for (u32 g = 0; g < G; ++g) {
+    Dev &e = dg[g];
+    e = d;
+    const u32 b = s0[g];
+    e.plans += b; e.acc += b; e.cls += b; e.sbout += b; e.arena += (size_t)b * ctx->arena_words;
+    e.hdr = ctx->hdr_g + g;
+    e.prev_total = g ? &ctx->hdr_g[g - 1].total_out : nullptr;
+    BatchHdr hg = H; /* device-side consumers read S and status; max_pk_bytes / total_out are produced per group */
+    hg.S = s0[g + 1] - s0[g]; hg.max_pk_bytes = 0; hg.total_out = 0; hg.out_begin = 0;
+    ctx->h_hdr_g[g] = hg;
+  }
+  /* phase 1 (statistics) of every group, then phase 2 (coding) once the group's packed-table size is known on the host */
+  for (u32 g = 0; g < G; ++g) {
+    const Dev &e = dg[g];
+    const u32 Sg = s0[g + 1] - s0[g];
+    cudaStream_t gs = g ? ctx->gstream[g] : st;
+#define GMARK() do { if (G == 1) PMARK(); } while (0)
+    CK(cudaMemcpyAsync(ctx->hdr_g + g, ctx->h_hdr_g + g, sizeof(BatchHdr), cudaMemcpyHostToDevice, gs));
+    CK(cudaMemsetAsync(e.acc, 0, sizeof(SbAcc) * Sg, gs));
+    GMARK();
+    k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, Sg), CH, span_v, gs>>>(e);
+    k_xdelta<<<Sg, 128, 0, gs>>>(e); GMARK();
+    k_qhist<<<dim3(H.max_qchunks, Sg), 256, qh_dyn, gs>>>(e); GMARK();
+    k_classify<<<Sg, 32, 0, gs>>>(e); GMARK();
+    /* the group header now holds the exact size of the packed quality tables: the copy is ordered before the
+     * statistics kernels that follow, so the host gets it while they keep the GPU busy */
+    CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs));
+    CK(cudaEventRecord(ctx->ev_rb[g], gs));
+    k_zero_hist<<<dim3(8, Sg), 256, 0, gs>>>(e);
+    k_dnacount<<<dim3(16, Sg), 256, 0, gs>>>(e); GMARK();
+    k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, s2_dyn, gs>>>(e); GMARK();
+  }
   static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
-  const u32 solo_dyn = d.pk_bytes + EW * d.enc_stage, pair_dyn = d.pk_bytes + EP * d.enc_stage;
-  const bool pair = pair_env >= 0 ? pair_env != 0 : (solo_dyn + 7 * 1024) * 4 > 227u * 1024;
-  const dim3 ge_solo((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), S), ge_pair((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), S);
   /* reads of very different lengths: the quality warp of a pair would wait for its longest record while the title warp idles */
   const bool varlen = H.max_len > 0 && (u64)(H.max_len - ~H.inv_min_len) * 4 > H.max_len;
-  if (pair && !varlen) k_lengths<true><<<ge_pair, EW * 32, pair_dyn, st>>>(d);
-  else k_lengths<false><<<ge_solo, EW * 32, solo_dyn, st>>>(d);
-  PMARK();
-  k_layout<<<S, 256, 0, st>>>(d); PMARK();
-  k_outscan<<<1, 256, 0, st>>>(d); PMARK();
-  k_zero_out<<<148 * 4, 256, 0, st>>>(d); PMARK();
-  if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, st>>>(d);
-  else k_emit<false><<<ge_solo, EW * 32, solo_dyn, st>>>(d);
-  PMARK();
-  ctx->launches += 13;
+  for (u32 g = 0; g < G; ++g) {
+    Dev &e = dg[g];
+    const u32 Sg = s0[g + 1] - s0[g];
+    cudaStream_t gs = g ? ctx->gstream[g] : st;
+    CK(cudaEventSynchronize(ctx->ev_rb[g]));
+    {
+      const u32 pk = (ctx->h_hdr_g[g].max_pk_bytes + 15u) & ~15u;
+      e.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
+    }
+    k_huff<<<dim3(16, Sg), 128, 4 * sizeof(HuffScratch), gs>>>(e); GMARK();
+    /* one warp per 32-record block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
+    const u32 solo_dyn = e.pk_bytes + EW * e.enc_stage, pair_dyn = e.pk_bytes + EP * e.enc_stage;
+    const bool pair = pair_env >= 0 ? pair_env != 0 : (solo_dyn + 7 * 1024) * 4 > 227u * 1024;
+    const dim3 ge_solo((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), Sg), ge_pair((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), Sg);
+    if (pair && !varlen) k_lengths<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
+    else k_lengths<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
+    GMARK();
+    k_layout<<<Sg, 256, 0, gs>>>(e); GMARK();
+    if (g) CK(cudaStreamWaitEvent(gs, ctx->ev_scan[g - 1], 0)); /* the previous group's end of output */
+    k_outscan<<<1, 256, 0, gs>>>(e); GMARK();
+    if (G > 1) CK(cudaEventRecord(ctx->ev_scan[g], gs));
+    k_zero_out<<<148 * 4, 256, 0, gs>>>(e); GMARK();
+    if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
+    else k_emit<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
+    GMARK();
+    ctx->launches += 13;
+    CK(cudaMemcpyAsync(ctx->h_sbout + s0[g], e.sbout, sizeof(SbOut) * Sg, cudaMemcpyDeviceToHost, gs));
+    if (g == G - 1) CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* total_out = the end of the last group */
+    if (g) { CK(cudaEventRecord(ctx->ev_done[g], gs)); CK(cudaStreamWaitEvent(st, ctx->ev_done[g], 0)); } /* the caller waits on the main stream */
+  }
   CK(cudaGetLastError());
   if (ctx->profile) {
     CK(cudaStreamSynchronize(st));
     for (int i = 0; i < NKERN && i + 1 < pi; ++i) { float t = 0; cudaEventElapsedTime(&t, ctx->pev[i], ctx->pev[i + 1]); ctx->pms[i] += t; }
     ctx->pcount++;
   }
-  CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ctx->h_sbout, ctx->sbout, sizeof(SbOut) * S, cudaMemcpyDeviceToHost, st));
   return PHY_OK;
 }
 

@@ -33,7 +33,10 @@ namespace phy {
 constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
 constexpr int TILE = 16384;        /* bytes per newline-index tile (256 threads x 64 bytes)                */
 constexpr int SUPER = 64;          /* tiles per supertile: the single-CTA scan runs over supertiles         */
-constexpr int QCH = 2048;          /* records per quality-histogram work item (16 chunks)                  */
+#ifndef PHY_QCH
+#define PHY_QCH 2048
+#endif
+constexpr int QCH = PHY_QCH;          /* records per quality-histogram work item (16 chunks)                  */
 constexpr u32 QR_ROWW = 97;        /* words per row of k_qhist's private table (odd: neighbouring rows start in different banks) */
 constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
@@ -45,7 +48,8 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_chunks;      /* max over subblocks of ceil(n_records / CH)                            */
   u32 max_span;        /* widest 128-record span (16-byte aligned start, one record of halo)     */
   i32 status;          /* batch-level error (capacity ...)                                      */
-  u64 total_out;       /* bytes of output used                                                  */
+  u64 total_out;       /* end of the output used (byte offset in d.out)                          */
+  u64 out_begin;       /* where this group's payloads start (= the previous group's total_out)   */
   u64 next_pos;        /* region-relative position where the next window starts                 */
   u32 max_qchunks;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
@@ -71,6 +75,7 @@ struct Dev {
   SbAcc *acc; SbClass *cls; SbOut *sbout;
   u32 *arena; u32 arena_words;
   u8 *out; u64 out_cap;
+  const u64 *prev_total;      /* total_out of the subblock group before this one (nullptr: this is the first) */
   i64 batch_base, region_len; i32 batch_is_final; u32 slack;
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
@@ -463,7 +468,10 @@ struct Stat1S {
   u8 r0[R0_MAX];
 };
 
-constexpr int S1G = 8; /* 128-record chunks per k_stat1 CTA */
+#ifndef PHY_S1G
+#define PHY_S1G 8
+#endif
+constexpr int S1G = PHY_S1G; /* 128-record chunks per k_stat1 CTA */
 
 /* A CTA walks S1G consecutive chunks of one subblock (bulk-copy staging, ChunkStage); record 0 is tokenised and the
  * shared-memory accumulators are flushed to the subblock's once per CTA.
@@ -985,7 +993,10 @@ __device__ __forceinline__ bool span_issue(const u8 *in, u32 lo, u32 hi, u8 *sme
 }
 
 constexpr int CSLOTS = 8; /* per-position char tables whose histogram a CTA keeps in shared memory */
-constexpr int S2G = 8;    /* 128-record chunks per k_stat2 CTA */
+#ifndef PHY_S2G
+#define PHY_S2G 8
+#endif
+constexpr int S2G = PHY_S2G;    /* 128-record chunks per k_stat2 CTA */
 
 /* field classes and the list of non-constant fields of a subblock, copied to shared memory once per CTA */
 struct TitleTabs { FieldClass fc[MAXF]; u16 ncskip[MAXF]; u8 ncf[MAXF]; };
@@ -1266,7 +1277,10 @@ __device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, c
  * loop, so a warp with long or ambiguous records does not hold the others up.
  * dynamic shared memory: [pk_bytes packed quality tables][EW stages of enc_stage bytes] */
 constexpr int EW = 8;   /* warps per encoder CTA */
-constexpr int EGW = 8;  /* 32-record blocks per warp */
+#ifndef PHY_EGW
+#define PHY_EGW 8
+#endif
+constexpr int EGW = PHY_EGW;  /* 32-record blocks per warp */
 
 struct WarpStage {
   u32 buf_a, bar_a, phase;
@@ -1450,7 +1464,8 @@ __global__ void __launch_bounds__(256) k_layout(Dev d) {
 __global__ void __launch_bounds__(256) k_outscan(Dev d) {
   __shared__ u32 ws[8];
   const u32 S = d.hdr->S;
-  u64 carry = 0;
+  const u64 begin = d.prev_total ? *d.prev_total : 0ull; /* payloads of all groups lie back to back */
+  u64 carry = begin;
   for (u32 base = 0; base < S; base += 256) {
     const u32 s = base + threadIdx.x;
     u32 len = 0, pad = 0;
@@ -1472,13 +1487,13 @@ __global__ void __launch_bounds__(256) k_outscan(Dev d) {
     }
     carry += (u64)tot << 4;
   }
-  if (threadIdx.x == 0) d.hdr->total_out = carry < d.out_cap ? carry : d.out_cap;
+  if (threadIdx.x == 0) { d.hdr->out_begin = begin < d.out_cap ? begin : d.out_cap; d.hdr->total_out = carry < d.out_cap ? carry : d.out_cap; }
 }
 
 __global__ void __launch_bounds__(256) k_zero_out(Dev d) {
-  u64 n16 = (d.hdr->total_out + 15) / 16;
+  const u64 b16 = d.hdr->out_begin / 16, e16 = (d.hdr->total_out + 15) / 16; /* payloads are 16-byte aligned */
   uint4 z = make_uint4(0, 0, 0, 0);
-  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n16; i += (u64)gridDim.x * 256) ((uint4 *)d.out)[i] = z;
+  for (u64 i = b16 + (u64)blockIdx.x * 256 + threadIdx.x; i < e16; i += (u64)gridDim.x * 256) ((uint4 *)d.out)[i] = z;
 }
 
 /* ---- emit ------------------------------------------------------------------------------------------------------------ */
