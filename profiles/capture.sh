@@ -12,5 +12,6 @@ timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
 timeout 300 python tests/gpu_prof_target.py 36bp 256 2 > $O/${TAG}_plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(stat1|stat2|qhist|lengths|emit|nl_emit|nl_count)' -s 7 -c 7 -f -o $O/${TAG}_full \
+# one subblock group, so that every launch covers the whole 256 MB shard (the traffic figures in ncu_traffic.json are per shard)
+PHY_GROUPS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(stat1|stat2|qhist|lengths|emit|nl_emit|nl_count)' -s 7 -c 7 -f -o $O/${TAG}_full \
   python tests/gpu_prof_target.py 36bp 256 2 > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"

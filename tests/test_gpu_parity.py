@@ -37,17 +37,23 @@ def test_payloads_bit_exact_against_reference_goldens(case, ctx):
 
 
 def test_multi_batch_equals_single_batch(oracle):
+    """One batch of 24 subblocks (>= 16: the subblock groups of run_batch run on three streams) against many small
+    batches (one group each) and against the oracle."""
     data = synth.fastq("100bp", 41, target_bytes=6_000_000)
-    prm = api.region_params(data.size, 1, 0, window_bytes=512 * 1024)
+    win = 256 * 1024
+    prm = api.region_params(data.size, 1, 0, window_bytes=win)
     big = api.Context(0, max_batch_bytes=32 << 20, max_subblocks=64)
-    small = api.Context(0, max_batch_bytes=(3 << 20) // 2, max_subblocks=64)
+    small = api.Context(0, max_batch_bytes=1 << 20, max_subblocks=64)
     try:
         d1, o1, r1 = big.compress_region(data, prm)
         d2, o2, r2 = small.compress_region(data, prm)
-        assert r1.n_batches == 1 and r2.n_batches > 2
+        assert r1.n_batches == 1 and r2.n_batches > 2 and len(d1) >= 16
+        assert r1.kernel_launches > 30  # three groups x 13 launches + the splitter
         assert api.payloads(d1, o1) == api.payloads(d2, o2)
         assert [(d.win_off, d.win_len, d.n_records) for d in d1] == [(d.win_off, d.win_len, d.n_records) for d in d2]
-        assert api.payloads(d1, o1) == oracle.compress_rank(data, 1, 0, window_bytes=512 * 1024)["subblocks"]
+        assert api.payloads(d1, o1) == oracle.compress_rank(data, 1, 0, window_bytes=win)["subblocks"]
+        # payloads of all groups lie back to back in the output
+        assert all(a.out_off + ((a.out_len + 15) & ~15) == b.out_off for a, b in zip(d1, d1[1:]))
     finally:
         big.close(); small.close()
 
