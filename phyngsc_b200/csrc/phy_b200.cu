@@ -275,6 +275,8 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   /* launch geometry shared by all subblock groups of the batch */
   u32 qh_dyn = 0;
+  static const int qh_nt_env = getenv("PHY_QH_NT") ? atoi(getenv("PHY_QH_NT")) : 0;
+  const u32 qh_threads = qh_nt_env ? (u32)qh_nt_env : (H.max_len > 192 ? 512u : 256u); /* very long reads (one record slot per 256 threads): a second slot on the same private table */
   { /* k_qhist: private table of min(longest read, 256) rows beside two stage buffers.  Long records are staged in
      * groups of 64 or 32 instead of 128 so that two CTAs still fit an SM (fewer, larger groups beat more CTAs: the
      * per-group barriers and list building are what a CTA spends its time on besides counting). */
@@ -338,7 +340,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     GMARK();
     k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, Sg), CH, span_v, gs>>>(e);
     k_xdelta<<<Sg, 128, 0, gs>>>(e); GMARK();
-    k_qhist<<<dim3(H.max_qchunks, Sg), 256, qh_dyn, gs>>>(e); GMARK();
+    k_qhist<<<dim3(H.max_qchunks, Sg), qh_threads, qh_dyn, gs>>>(e); GMARK();
     k_classify<<<Sg, 32, 0, gs>>>(e); GMARK();
     /* the group header now holds the exact size of the packed quality tables: the copy is ordered before the
      * statistics kernels that follow, so the host gets it while they keep the GPU busy */

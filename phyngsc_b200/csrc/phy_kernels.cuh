@@ -834,14 +834,14 @@ constexpr int QU = 8;          /* records in flight per thread */
 __device__ __forceinline__ u32 lds_u8(u32 addr) { u16 v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sm_red_inc(u32 addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
 /* dynamic shared memory: [qh_rows * QR_ROWW words: the CTA's private table][qh_nbuf span buffers] */
-__global__ void __launch_bounds__(256) k_qhist(Dev d) {
+__global__ void __launch_bounds__(512) k_qhist(Dev d) { /* 256 threads for short reads, 512 for long ones (more record slots per private table) */
   extern __shared__ uint4 dyn_smem[];
   __shared__ __align__(8) u64 bars[8];
   __shared__ u32 m_qs[CH + 64];  /* shared-memory address of the quality line: plain records from the front (padded with */
   __shared__ u16 m_len[CH + 64]; /* dummies), records with an ambiguity transfer from the back                           */
   __shared__ u32 n_plain, n_x;
   __shared__ u32 c_lo[QCH / 32 + 1]; /* first byte of each of the CTA's record groups (and the end of the last) */
-  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const SbPlan P = d.plans[s];
   if (P.status || d.acc[s].status) return;
   const u32 QS = d.qh_recs; /* records per pipeline stage */
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   if (Lp == 0) return;
   u32 *raw = raw_table(d, s);
   const u32 RP = Lp < d.qh_rows ? Lp : d.qh_rows;  /* rows (read positions) per pass */
-  const u32 slots = RP < 256 ? min(256 / RP, 64u / QU) : 1u; /* records the CTA counts side by side (the list padding holds QU * slots dummies) */
+  const u32 slots = RP < NT ? min(NT / RP, 64u / QU) : 1u; /* records the CTA counts side by side (the list padding holds QU * slots dummies) */
   u32 *hist = (u32 *)dyn_smem;
   const u32 nbuf = d.qh_nbuf;
   const u32 hist_a = (u32)__cvta_generic_to_shared(hist), buf_a0 = hist_a + ((d.qh_rows * (QR_ROWW * 4) + 15u) & ~15u), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
   /* row p of the private table: counters 0..94 = bytes 33..127, 95 = "some other byte" (those go to the global table one
    * by one), 96 = no symbol.  Rows are QR_ROWW = 97 words apart, so the 32 positions a warp works on fall into 32 banks. */
   for (u32 p0 = 0; p0 < Lp; p0 += RP) {
-    for (u32 i = tid; i < RP * QR_ROWW; i += 256) hist[i] = 0;
+    for (u32 i = tid; i < RP * QR_ROWW; i += NT) hist[i] = 0;
     __syncthreads(); /* also: barriers initialised, c_lo filled, previous pass has left the buffers */
     if (tid == 0) for (u32 c = c0; c < c1 && c < c0 + (nbuf > 1 ? nbuf - 1 : 1u); ++c) request(c); /* fill the pipeline */
     /* this thread's record of the first chunk */
@@ -905,11 +905,11 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
       const bool uniform = __syncthreads_and(covers);
       const u32 np = n_plain, nx = n_x;
       const u32 np_pad = (np + QU * slots - 1) / (QU * slots) * (QU * slots);
-      for (u32 i = np + tid; i < np_pad; i += 256) { m_qs[i] = buf_b; m_len[i] = 0; } /* dummies: a valid address, no symbols */
+      for (u32 i = np + tid; i < np_pad; i += NT) { m_qs[i] = buf_b; m_len[i] = 0; } /* dummies: a valid address, no symbols */
       mbar_wait(bar_b, (phases >> b) & 1u); phases ^= 1u << b;
       __syncthreads();
       if (owner)
-        for (u32 pr = p; pr < RP; pr += 256) { /* more than 256 rows per pass: a thread takes several positions */
+        for (u32 pr = p; pr < RP; pr += NT) { /* more rows per pass than threads: a thread takes several positions */
           const u32 pos = p0 + pr, row_a = hist_a + pr * (QR_ROWW * 4);
           if (uniform) { /* every plain record covers this row range: no per-symbol length test */
             const u32 full = np / (QU * slots) * (QU * slots);
@@ -949,10 +949,10 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
     const u32 rows = min(RP, Lp - p0);
     { /* bytes outside 33..127 in plain records (counter 95 of a row): rare; recount them exactly from global memory */
       bool any = false;
-      for (u32 pr = tid; pr < rows; pr += 256) any = any || hist[pr * QR_ROWW + 95] != 0;
+      for (u32 pr = tid; pr < rows; pr += NT) any = any || hist[pr * QR_ROWW + 95] != 0;
       if (__syncthreads_or(any)) {
         const u32 i_end = min(c1 * QS, P.n_records);
-        for (u32 i = c0 * QS + tid; i < i_end; i += 256) {
+        for (u32 i = c0 * QS + tid; i < i_end; i += NT) {
           const u32 r = P.first_rec + i;
           if (d.kx[r] & 0x8000u) continue;
           const u32 tei = d.te[r], sei = d.se[r], L = sei - tei - 1;
@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(256) k_qhist(Dev d) {
         }
       }
     }
-    for (u32 i = tid; i < rows * 95; i += 256) {
+    for (u32 i = tid; i < rows * 95; i += NT) {
       const u32 pr = i / 95, c = i % 95, v = hist[pr * QR_ROWW + c];
       if (v) atomicAdd(raw + (p0 + pr + 1) * 256 + 33 + c, v);
     }
