@@ -5,27 +5,29 @@
  *   in[len + slack]            the FASTQ bytes, batch-relative positions are uint32
  *   te[r], se[r], rstart[r]    record table: newline ending the title line / the sequence line, first byte
  *   kx[r]                      kept DNA length | transfer flag << 15          (phyNGSC.cpp:549-588)
- *   qoff[r], doff[r], toff[r]  bit offset of the record inside its 128-record chunk of the quality / DNA body,
- *                              and inside its 32-record title block
+ *   qoff[r], doff[r], toff[r]  bit offset of the record inside its 32-record block of the quality / DNA / title body
  *   plans[s], acc[s], cls[s]   per-subblock window, reduced statistics, coding decisions (phy_core.cuh)
- *   arena[s][ARENA_WORDS]      per-subblock histograms, Huffman tables, tree blobs, header staging
+ *   arena[s][arena_words]      per-subblock histograms, Huffman tables, tree blobs, header staging, per-block totals;
+ *                              its last RAW_WORDS words are the raw per-position quality table of k_qhist
  *   out[]                      payloads info|title|quality|dna, 16-byte aligned per subblock
  *
- * Stages (one launch each, every launch covers all subblocks of the batch):
+ * Stages (every launch covers all subblocks of the batch, or of one subblock group -- see run_batch in phy_b200.cu):
  *   nl_count -> nl_scan -> nl_emit      record splitter            (phyNGSC.cpp:254-331)
- *   plan                                window chaining            (phyNGSC.cpp:168-250, 744-755)
- *   stat1                               validation, ambiguity transfer, DNA/quality alphabets, title field
- *                                       reductions                 (phyNGSC.cpp:383-423, 462-653; tasks.cpp:22-223)
- *   classify, zero                      coding decisions + arena   (tasks.cpp:196-257)
- *   qhist, stat2                        per-position quality histogram, numeric/char histograms,
- *                                       32-record block descriptors (tasks.cpp:64-93,127-182,260-286)
+ *   plan, spanmax                       window chaining, shared-memory sizing (phyNGSC.cpp:168-250, 744-755)
+ *   stat1, xdelta                       validation, ambiguity transfer, DNA alphabet, title field reductions
+ *                                                                  (phyNGSC.cpp:383-423, 462-653; tasks.cpp:22-223)
+ *   qhist                               raw per-position quality histogram (tasks.cpp:260-286)
+ *   classify, zero_hist, dnacount       coding decisions, arena layout, coded quality tables (tasks.cpp:196-257)
+ *   stat2                               numeric / char histograms, 32-record block descriptors (tasks.cpp:64-93,127-182)
  *   huff                                one warp per table         (huffman.cpp:18-118)
  *   lengths -> layout -> outscan        bit lengths, scans, header assembly, payload offsets
  *   zero_out -> emit                    BitStream emission         (tasks.cpp:393-509,544-557,609-619)
+ *
+ * The kernels that read record bytes (stat1, qhist, stat2, lengths, emit) stream them into shared memory with the
+ * bulk-copy engine (cp.async.bulk + mbarrier): span_request / ChunkStage / WarpStage below.
  */
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_pipeline.h>
 #include "phy_core.cuh"
 
 namespace phy {
@@ -379,19 +381,6 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
   if ((threadIdx.x & 31) == 0 && ml) atomicMax(&d.hdr->max_len, ml);
   if ((threadIdx.x & 31) == 0 && il) atomicMax(&d.hdr->inv_min_len, il);
   if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&d.hdr->max_nf, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
-}
-
-/* ---- record spans in shared memory ------------------------------------------------------------------- */
-/* Copies bytes [lo, hi) of the batch (16-byte granules) into shared memory and returns a pointer p with
- * p[pos] valid for batch positions pos in [lo, hi), or nullptr when the span does not fit (records far
- * beyond the reference's 500-byte domain).  All threads of the CTA must call it. */
-__device__ __forceinline__ const u8 *stage_span(const u8 *in, u32 lo, u32 hi, u8 *smem, u32 smem_bytes) {
-  u32 alo = lo & ~15u;
-  u32 n = hi - alo;
-  if (n > smem_bytes) return nullptr;
-  for (u32 i = threadIdx.x * 16; i < n; i += blockDim.x * 16) *(uint4 *)(smem + i) = __ldg((const uint4 *)(in + alo + i));
-  __syncthreads();
-  return smem - alo;
 }
 
 /* Dynamic shared memory of the per-record kernels: [span_bytes: staged records][vals: nf x CH numeric values] */
@@ -981,15 +970,6 @@ __device__ __forceinline__ void warp_hist_add(u32 *hist, u32 idx, bool on) {
   u32 key = on ? idx : 0xFFFFFFFFu;
   u32 m = __match_any_sync(0xFFFFFFFFu, key);
   if (on && (u32)(__ffs(m) - 1) == (threadIdx.x & 31)) atomicAdd(hist + idx, (u32)__popc(m));
-}
-
-/* Issues the asynchronous copy (cp.async, 16 bytes per request) of batch bytes [lo, hi) into `smem`; the caller
- * commits / waits.  Returns false when the span does not fit. */
-__device__ __forceinline__ bool span_issue(const u8 *in, u32 lo, u32 hi, u8 *smem, u32 smem_bytes) {
-  u32 alo = lo & ~15u, n = hi - alo;
-  if (n > smem_bytes) return false;
-  for (u32 i = threadIdx.x * 16; i < n; i += blockDim.x * 16) __pipeline_memcpy_async(smem + i, in + alo + i, 16);
-  return true;
 }
 
 constexpr int CSLOTS = 8; /* per-position char tables whose histogram a CTA keeps in shared memory */
