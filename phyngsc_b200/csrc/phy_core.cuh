@@ -227,7 +227,8 @@ struct SbClass {
   u32 ntab, tabdesc_off, tq0, tdna, tchr0, qstat_off, dnastat_off, zero_begin, zero_end;
   u32 chr_cl_off;              /* code array of char table tchr0; table tchr0 + k follows 512 * k words later */
   u32 chr_freq_off;            /* frequency array of char table tchr0; table tchr0 + k follows 256 * k words later */
-  u32 qpk_off, qpk_bad;        /* quality tables packed to 16 bits (len << 12 | code); qpk_bad != 0 when a code is longer than 12 bits */
+  u32 qpk_esc;                 /* some packed entry is the escape (set by the Huffman stage) */
+  u32 qpk_off, qpk_bad;        /* quality tables packed to 16 bits (len << 12 | code, escape for longer codes); qpk_bad != 0 when a table failed to build */
   u32 nblk, flagbits_off;
   u32 nchunk;                  /* 128-record chunks (work items of the statistics kernels) */
   u32 blk3_off;                /* per 32-record block: [3][nblk] totals -> bases of quality bits, dna bits, title bytes */
@@ -463,7 +464,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   C.zero_end = al.used;
   while (al.used & 3u) al.take(1); /* 16-byte alignment: the packed tables are copied to shared memory as vectors */
   C.qpk_off = al.take(((C.max_qlen + 1) * nq + 1) / 2 + 4);
-  C.qpk_bad = 0;
+  C.qpk_bad = 0; C.qpk_esc = 0;
   /* table directory: quality (max_qlen+1), dna (0/1), numeric, char */
   u32 ntab = (C.max_qlen + 1) + (C.plain ? 0 : 1) + ntab_num + ntab_chr;
   C.ntab = ntab;

@@ -42,6 +42,7 @@ constexpr int QCH = PHY_QCH;          /* records per quality-histogram work item
 constexpr u32 QR_ROWW = 97;        /* words per row of k_qhist's private table (odd: neighbouring rows start in different banks) */
 constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
+constexpr u32 PK_ESC = 0xF000u;   /* packed quality entries at or above this value: code longer than 12 bits, read the 64-bit entry */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
@@ -1120,12 +1121,13 @@ __global__ void __launch_bounds__(128) k_huff(Dev d) {
     u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS[w], lane, 32u, WarpSync());
     if (lane == 0) td[t].tree_len = blob;
     __syncwarp();
-    if (t - C.tq0 <= C.max_qlen) { /* quality table: 16-bit copy (len << 12 | code) for the shared-memory walkers */
+    if (t - C.tq0 <= C.max_qlen) { /* quality table: 16-bit copy (len << 12 | code, PK_ESC for the rare codes beyond 12 bits) for the shared-memory walkers */
       u16 *pk = (u16 *)(arena + C.qpk_off) + (size_t)(t - C.tq0) * D.n;
       const u64 *cl = (const u64 *)(arena + D.cl_off);
-      bool bad = blob == 0;
-      for (u32 i = lane; i < D.n && blob; i += 32) { u16 e; if (!qpack_entry(cl[i], e)) bad = true; pk[i] = e; }
-      if (bad) atomicOr(&C.qpk_bad, 1u);
+      bool esc = false;
+      for (u32 i = lane; i < D.n && blob; i += 32) { u16 e; if (!qpack_entry(cl[i], e)) { e = (u16)PK_ESC; esc = true; } pk[i] = e; } /* longer than 12 bits: escape to the 64-bit entry */
+      if (blob == 0) atomicOr(&C.qpk_bad, 1u);
+      if (esc) atomicOr(&C.qpk_esc, 1u);
     }
   }
 }
@@ -1136,6 +1138,7 @@ __global__ void __launch_bounds__(128) k_huff(Dev d) {
 struct WalkTabs {
   const u8 *qmap, *smap, *xq;  /* qua_code[256], sym_code[256], g_xq_lut */
   const u16 *pk; u32 nq;       /* packed quality tables (nullptr: read the 64-bit entries from the arena) */
+  bool has_esc;                /* some packed entry is the escape */
   const u64 *qcl;              /* 64-bit quality entries, table-major */
   u32 dna_mode;                /* 0 Huffman, 1 two bits per base through smap, 2 two bits per base, alphabet exactly ACGT */
   const u64 *dcl;              /* DNA code table (Huffman mode) */
@@ -1153,43 +1156,63 @@ template <class Sink> __device__ __forceinline__ void put_pk2(Sink &s, u32 e0, u
  * symbol codes and table entries are loaded together (independent shared-memory loads), then appended pairwise.
  * The ambiguity transfer (phyNGSC.cpp:575-580) costs two more loads per symbol and is only compiled into the loop
  * of warps that hold such a record. */
-template <class Sink>
-__device__ __forceinline__ void quality_walk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
+/* one symbol whose packed entry may be the escape: its code then comes from the 64-bit table in the arena */
+template <class Sink> __device__ __forceinline__ void put_pk_esc(Sink &s, u32 e, const u64 *full) {
+  if (e >= PK_ESC) { const u64 f = *full; s.put((u32)f, (u32)(f >> 32)); }
+  else put_pk(s, e);
+}
+/* ESC: the subblock has packed entries with the escape (a code longer than 12 bits somewhere); compiled separately so
+ * that the common case carries neither the test nor its registers */
+template <bool ESC, class Sink>
+__device__ __forceinline__ void quality_walk_pk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
   const bool wx = __any_sync(__activemask(), xfer);
   const u32 xm = xfer ? 0xFFu : 0u;
   const u32 nq = T.nq;
-  if (T.pk) {
-    const u16 *row = T.pk + nq;
-    u32 j = 0;
-    if (!wx) {
-      for (; j + 4 <= L; j += 4, row += 4 * nq) {
-        const u32 q0 = qp[j], q1 = qp[j + 1], q2 = qp[j + 2], q3 = qp[j + 3];
-        const u32 c0 = T.qmap[q0], c1 = T.qmap[q1], c2 = T.qmap[q2], c3 = T.qmap[q3];
-        const u32 e0 = row[c0], e1 = row[nq + c1], e2 = row[2 * nq + c2], e3 = row[3 * nq + c3];
-        put_pk2(s, e0, e1); put_pk2(s, e2, e3);
-      }
-    } else {
-      for (; j + 4 <= L; j += 4, row += 4 * nq) {
-        const u32 q0 = qp[j] + (T.xq[sp[j]] & xm), q1 = qp[j + 1] + (T.xq[sp[j + 1]] & xm);
-        const u32 q2 = qp[j + 2] + (T.xq[sp[j + 2]] & xm), q3 = qp[j + 3] + (T.xq[sp[j + 3]] & xm);
-        const u32 c0 = T.qmap[q0], c1 = T.qmap[q1], c2 = T.qmap[q2], c3 = T.qmap[q3];
-        const u32 e0 = row[c0], e1 = row[nq + c1], e2 = row[2 * nq + c2], e3 = row[3 * nq + c3];
-        put_pk2(s, e0, e1); put_pk2(s, e2, e3);
-      }
+  const u16 *row = T.pk + nq;
+  const u64 *frow = T.qcl + nq; /* the same position in the 64-bit tables */
+  u32 j = 0;
+#define PHY_Q4_BODY                                                                                                          \
+  const u32 c0 = T.qmap[q0], c1 = T.qmap[q1], c2 = T.qmap[q2], c3 = T.qmap[q3];                                            \
+  const u32 e0 = row[c0], e1 = row[nq + c1], e2 = row[2 * nq + c2], e3 = row[3 * nq + c3];                                 \
+  if (ESC && max(max(e0, e1), max(e2, e3)) >= PK_ESC) { /* rare: a code longer than 12 bits among the four */               \
+    const u64 *f = frow + (size_t)j * nq;                                                                                   \
+    put_pk_esc(s, e0, f + c0); put_pk_esc(s, e1, f + nq + c1); put_pk_esc(s, e2, f + 2 * nq + c2); put_pk_esc(s, e3, f + 3 * nq + c3); \
+  } else {                                                                                                                  \
+    put_pk2(s, e0, e1); put_pk2(s, e2, e3);                                                                                 \
+  }
+  if (!wx) {
+    for (; j + 4 <= L; j += 4, row += 4 * nq) {
+      const u32 q0 = qp[j], q1 = qp[j + 1], q2 = qp[j + 2], q3 = qp[j + 3];
+      PHY_Q4_BODY
     }
-    for (; j < L; ++j, row += nq) put_pk(s, (u32)row[T.qmap[qp[j] + (T.xq[sp[j]] & xm)]]);
+  } else {
+    for (; j + 4 <= L; j += 4, row += 4 * nq) {
+      const u32 q0 = qp[j] + (T.xq[sp[j]] & xm), q1 = qp[j + 1] + (T.xq[sp[j + 1]] & xm);
+      const u32 q2 = qp[j + 2] + (T.xq[sp[j + 2]] & xm), q3 = qp[j + 3] + (T.xq[sp[j + 3]] & xm);
+      PHY_Q4_BODY
+    }
+  }
+#undef PHY_Q4_BODY
+  for (; j < L; ++j, row += nq) {
+    const u32 c = T.qmap[qp[j] + (T.xq[sp[j]] & xm)], e = row[c];
+    if (ESC) put_pk_esc(s, e, frow + (size_t)j * nq + c); else put_pk(s, e);
+  }
+}
+template <class Sink>
+__device__ __forceinline__ void quality_walk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
+  if (T.pk) {
+    if (T.has_esc) quality_walk_pk<true>(qp, sp, L, xfer, T, s);
+    else quality_walk_pk<false>(qp, sp, L, xfer, T, s);
     return;
   }
+  const u32 xm = xfer ? 0xFFu : 0u;
+  const u32 nq = T.nq;
   const u64 *row = T.qcl + nq;
   for (u32 j = 0; j < L; ++j, row += nq) {
     const u64 e = row[T.qmap[qp[j] + (T.xq[sp[j]] & xm)]];
     s.put((u32)e, (u32)(e >> 32));
   }
 }
-
-/* DNA codes of one record (tasks.cpp:544-557).  With the alphabet exactly ACGT and no ambiguity transfer in the warp,
- * four bases are turned into eight bits with a handful of word operations: ((c >> 1) & 3) ^ ((c >> 2) & 1) maps
- * A,C,G,T to 0,1,2,3 and a multiply gathers the four 2-bit fields. */
 template <class Sink>
 __device__ __forceinline__ void dna_walk(const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
   const bool wx = __any_sync(__activemask(), xfer);
@@ -1237,7 +1260,7 @@ __device__ __forceinline__ void load_walk_tabs(const Dev &d, const SbClass &C, c
   T.qmap = codes; T.smap = codes + 256; T.xq = xq; T.nq = C.nq;
   T.qcl = (const u64 *)(arena + td[C.tq0].cl_off);
   const u32 pk_bytes = (C.max_qlen + 1) * C.nq * 2u;
-  T.pk = nullptr;
+  T.pk = nullptr; T.has_esc = C.qpk_esc != 0;
   if (!C.qpk_bad && pk_bytes <= d.pk_bytes) {
     const uint4 *src = (const uint4 *)(arena + C.qpk_off);
     for (u32 i = threadIdx.x; i < (pk_bytes + 15) / 16; i += blockDim.x) ((uint4 *)pk_smem)[i] = src[i];
