@@ -351,8 +351,6 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, s2_dyn, gs>>>(e); GMARK();
   }
   static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
-  /* reads of very different lengths: the quality warp of a pair would wait for its longest record while the title warp idles */
-  const bool varlen = H.max_len > 0 && (u64)(H.max_len - ~H.inv_min_len) * 4 > H.max_len;
   for (u32 g = 0; g < G; ++g) {
     Dev &e = dg[g];
     const u32 Sg = s0[g + 1] - s0[g];
@@ -367,7 +365,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     const u32 solo_dyn = e.pk_bytes + EW * e.enc_stage, pair_dyn = e.pk_bytes + EP * e.enc_stage;
     const bool pair = pair_env >= 0 ? pair_env != 0 : (solo_dyn + 7 * 1024) * 4 > 227u * 1024;
     const dim3 ge_solo((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), Sg), ge_pair((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), Sg);
-    if (pair && !varlen) k_lengths<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
+    if (pair) k_lengths<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
     else k_lengths<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
     GMARK();
     k_layout<<<Sg, 256, 0, gs>>>(e); GMARK();

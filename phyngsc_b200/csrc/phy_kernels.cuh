@@ -58,7 +58,6 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
   u32 max_len;         /* longest sequence line of the batch's subblocks */
-  u32 inv_min_len;     /* ~(shortest sequence line) */
   u32 max_span64, max_span32; /* widest 64- / 32-record span (k_qhist may stage smaller groups than the 128-record chunk) */
 };
 
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->inv_min_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -365,7 +364,7 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
   if (s >= d.hdr->S) return; /* launched for the context's capacity: the host learns S only afterwards */
   const SbPlan P = d.plans[s];
   if (P.status) return;
-  u32 mx = 0, m64 = 0, m32 = 0, ml = 0, il = 0;
+  u32 mx = 0, m64 = 0, m32 = 0, ml = 0;
   for (u32 g = blockIdx.x * 256 + threadIdx.x; g * 32 < P.n_records; g += gridDim.x * 256) { /* 32-record groups */
     const u32 i = g * 32, r0 = P.first_rec + i, n = P.n_records;
     const u32 lo = d.rstart[r0] & ~15u;
@@ -373,14 +372,13 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
     if ((g & 1u) == 0) m64 = max(m64, d.rstart[P.first_rec + min(i + 64, n)] - lo);
     if ((g & 3u) == 0) mx = max(mx, d.rstart[P.first_rec + min(i + CH, n)] - lo);
   }
-  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) { const u32 L = d.se[P.first_rec + i] - d.te[P.first_rec + i] - 1; ml = max(ml, L); il = max(il, ~L); }
+  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) ml = max(ml, d.se[P.first_rec + i] - d.te[P.first_rec + i] - 1);
   mx = __reduce_max_sync(0xFFFFFFFFu, mx); m64 = __reduce_max_sync(0xFFFFFFFFu, m64); m32 = __reduce_max_sync(0xFFFFFFFFu, m32);
-  ml = __reduce_max_sync(0xFFFFFFFFu, ml); il = __reduce_max_sync(0xFFFFFFFFu, il);
+  ml = __reduce_max_sync(0xFFFFFFFFu, ml);
   if ((threadIdx.x & 31) == 0 && mx) atomicMax(&d.hdr->max_span, mx);
   if ((threadIdx.x & 31) == 0 && m64) atomicMax(&d.hdr->max_span64, m64);
   if ((threadIdx.x & 31) == 0 && m32) atomicMax(&d.hdr->max_span32, m32);
   if ((threadIdx.x & 31) == 0 && ml) atomicMax(&d.hdr->max_len, ml);
-  if ((threadIdx.x & 31) == 0 && il) atomicMax(&d.hdr->inv_min_len, il);
   if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&d.hdr->max_nf, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
 }
 
