@@ -346,8 +346,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
      * statistics kernels that follow, so the host gets it while they keep the GPU busy */
     CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs));
     CK(cudaEventRecord(ctx->ev_rb[g], gs));
-    k_zero_hist<<<dim3(8, Sg), 256, 0, gs>>>(e);
-    k_dnacount<<<dim3(16, Sg), 256, 0, gs>>>(e); GMARK();
+    k_zero_hist<<<dim3(8, Sg), 256, 0, gs>>>(e); GMARK();
     k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, s2_dyn, gs>>>(e); GMARK();
   }
   static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
@@ -376,7 +375,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
     else k_emit<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
     GMARK();
-    ctx->launches += 13;
+    ctx->launches += 12;
     CK(cudaMemcpyAsync(ctx->h_sbout + s0[g], e.sbout, sizeof(SbOut) * Sg, cudaMemcpyDeviceToHost, gs));
     if (g == G - 1) CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* total_out = the end of the last group */
     if (g) { CK(cudaEventRecord(ctx->ev_done[g], gs)); CK(cudaStreamWaitEvent(st, ctx->ev_done[g], 0)); } /* the caller waits on the main stream */

@@ -17,8 +17,9 @@
  *   stat1, xdelta                       validation, ambiguity transfer, DNA alphabet, title field reductions
  *                                                                  (phyNGSC.cpp:383-423, 462-653; tasks.cpp:22-223)
  *   qhist                               raw per-position quality histogram (tasks.cpp:260-286)
- *   classify, zero_hist, dnacount       coding decisions, arena layout, coded quality tables (tasks.cpp:196-257)
- *   stat2                               numeric / char histograms, 32-record block descriptors (tasks.cpp:64-93,127-182)
+ *   classify, zero_hist                 coding decisions, arena layout, coded quality tables (tasks.cpp:196-257)
+ *   stat2                               numeric / char histograms, 32-record block descriptors (tasks.cpp:64-93,127-182),
+ *                                       exact DNA symbol counts when the DNA is Huffman coded (tasks.cpp:233-236)
  *   huff                                one warp per table         (huffman.cpp:18-118)
  *   lengths -> layout -> outscan        bit lengths, scans, header assembly, payload offsets
  *   zero_out -> emit                    BitStream emission         (tasks.cpp:393-509,544-557,609-619)
@@ -430,11 +431,22 @@ __device__ __forceinline__ u32 ld4u(const u8 *p) {
   const u32 *w = (const u32 *)(p - a);
   return __funnelshift_r(w[0], w[1], 8 * a);
 }
-/* n >= 1 bytes equal?  Both sides in shared memory, any alignment. */
+/* n >= 1 bytes equal?  Both sides in shared memory, any alignment (may read up to three bytes past either side).
+ * Each side keeps the previous aligned word, so a step of four bytes is two loads, two funnel shifts and one LOP3. */
 __device__ __forceinline__ bool eq_bytes(const u8 *x, const u8 *y, u32 n) {
-  u32 diff = 0, p = 0;
-  for (; p + 4 <= n; p += 4) diff |= ld4u(x + p) ^ ld4u(y + p);
-  if (p < n) diff |= (ld4u(x + p) ^ ld4u(y + p)) & (0xFFFFFFFFu >> (8 * (4 - (n - p))));
+  const u32 ax = (u32)(size_t)x & 3u, ay = (u32)(size_t)y & 3u;
+  const u32 *wx = (const u32 *)(x - ax), *wy = (const u32 *)(y - ay);
+  const u32 sx = 8 * ax, sy = 8 * ay;
+  u32 x0 = *wx, y0 = *wy, diff = 0;
+  for (; n >= 4; n -= 4) {
+    const u32 x1 = *++wx, y1 = *++wy;
+    diff |= __funnelshift_r(x0, x1, sx) ^ __funnelshift_r(y0, y1, sy);
+    x0 = x1; y0 = y1;
+  }
+  if (n) {
+    const u32 x1 = wx[1], y1 = wy[1];
+    diff |= (__funnelshift_r(x0, x1, sx) ^ __funnelshift_r(y0, y1, sy)) & (0xFFFFFFFFu >> (8 * (4 - n)));
+  }
   return diff == 0;
 }
 
@@ -536,7 +548,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
    * about three instructions per base and its quality line is not touched at all -- the quality alphabet comes from
    * k_qhist's raw histogram.  Only records that hold another byte walk their bases and qualities one by one.
    * Only the PRESENCE of A/C/G/T is recorded here (that decides plain 2-bit coding); exact symbol counts are taken
-   * by k_dnacount in the rare Huffman-DNA case. */
+   * by k_stat2 in the rare Huffman-DNA case. */
   u32 kept = 0, pres = 0, myL = 0;
   if (active && !err) {
     const u8 *sp = b + te + 1, *qp = b + qs;
@@ -567,7 +579,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
         else { ++namb; nul = nul || c == 0; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; }
       }
       xfer = (namb && ok) ? 1u : 0u;
-      if (!xfer) for (j = 0; j < L; ++j) { const u8 c = sp[j]; if (!dlut[c]) atomicAdd(&S.dna[c], 1u); }
+      if (!xfer) for (j = 0; j < L; ++j) { const u8 c = sp[j]; if (!dlut[c]) S.dna[c] = 1; } /* the byte stays in the DNA; presence is all that is needed here */
       if (nul) err = E_UNSUPPORTED;
     }
     ph |= ph >> 16; ph |= ph >> 8;
@@ -784,30 +796,6 @@ __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
   }
 }
 
-/* Exact DNA symbol counts (sym_stats, tasks.cpp:233-236), needed only when more than four symbols force
- * Huffman-coded DNA; plain subblocks leave immediately. */
-__global__ void __launch_bounds__(256) k_dnacount(Dev d) {
-  __shared__ u32 h[256];
-  const u32 s = blockIdx.y;
-  const SbClass &C = d.cls[s];
-  if (C.status || C.plain) return;
-  const SbPlan P = d.plans[s];
-  for (u32 i = threadIdx.x; i < 256; i += 256) h[i] = 0;
-  __syncthreads();
-  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < C.R; i += gridDim.x * 256) {
-    u32 r = P.first_rec + i, te = d.te[r], se = d.se[r];
-    bool xfer = d.kx[r] >> 15;
-    for (u32 j = te + 1; j < se; ++j) {
-      u8 c = d.in[j];
-      if (xfer && !is_acgt(c)) continue;
-      atomicAdd(&h[C.sym_code[c]], 1u);
-    }
-  }
-  __syncthreads();
-  u32 *dst = d.arena + (size_t)s * d.arena_words + C.dnastat_off;
-  for (u32 i = threadIdx.x; i < C.nsym; i += 256) if (h[i]) atomicAdd(dst + i, h[i]);
-}
-
 /* ---- per-position quality histogram (tasks.cpp:260-286) ----------------------------------------------------- */
 /* Runs BEFORE the classification: it counts raw quality bytes (after the ambiguity transfer, phyNGSC.cpp:575-580)
  * per read position into the subblock's raw table raw[position + 1][byte] (row 0 = totals); the quality alphabet
@@ -998,9 +986,11 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   __shared__ u32 c_lo[S2G + 1];
   __shared__ __align__(16) u8 lut[256];
   __shared__ u32 chist[CSLOTS * 256];
+  __shared__ u32 dnah[256]; /* exact DNA symbol counts by symbol code (Huffman-coded DNA only) */
   const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const SbClass &C = d.cls[s];
-  if (C.status || C.nnc == 0) return; /* every field constant: no histogram, no block flag is ever read */
+  const bool count_dna = !C.plain; /* sym_stats (tasks.cpp:233-236) are needed only when more than four symbols force Huffman-coded DNA */
+  if (C.status || (C.nnc == 0 && !count_dna)) return; /* every field constant: no histogram, no block flag is ever read */
   const u32 c0 = blockIdx.x * S2G, c1 = min(c0 + S2G, C.nchunk);
   if (c0 >= C.nchunk) return;
   const SbPlan P = d.plans[s];
@@ -1013,6 +1003,7 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   /* char histograms of the first CSLOTS per-position tables are privatised in shared memory */
   const u32 ncs = min(C.ntab - C.tchr0, (u32)CSLOTS);
   for (u32 i = tid; i < ncs * 256; i += CH) chist[i] = 0;
+  if (count_dna) for (u32 i = tid; i < 256; i += CH) dnah[i] = 0;
   load_title_tabs(C, T);
   const u32 buf_a0 = (u32)__cvta_generic_to_shared(dyn_smem), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);
   if (tid == 0) { mbar_init(bar_a0, 1); mbar_init(bar_a0 + 8, 1); mbar_fence_init(); }
@@ -1021,8 +1012,8 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
   auto request = [&](u32 c) { const u32 st = (c - c0) % nbuf; span_request(d.in, c_lo[c - c0], c_lo[c - c0 + 1], buf_a0 + st * d.span_bytes, bar_a0 + 8 * st); };
   if (tid == 0) request(c0);
   u32 phases = 0;
-  u32 ts = 0, te = 0;
-  { const u32 i = c0 * CH + tid; if (i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; } }
+  u32 ts = 0, te = 0, se = 0, kx = 0;
+  { const u32 i = c0 * CH + tid; if (i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; if (count_dna) { se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; } } }
   for (u32 c = c0; c < c1; ++c) {
     const u32 st = (c - c0) % nbuf, pb = (c - c0) & 1u;
     const u32 nrec = min((u32)CH, R - c * CH);
@@ -1030,10 +1021,49 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
     const u32 r = P.first_rec + c * CH + (active ? tid : 0);
     const u32 wbase = tid & ~31u;
     if (nbuf == 2 && tid == 0 && c + 1 < c1) request(c + 1);
-    const u32 my_ts = ts, my_te = te;
-    { const u32 i = (c + 1) * CH + tid; if (c + 1 < c1 && i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; } } /* next chunk's record */
+    const u32 my_ts = ts, my_te = te, my_se = se, my_kx = kx;
+    { const u32 i = (c + 1) * CH + tid; if (c + 1 < c1 && i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; if (count_dna) { se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; } } } /* next chunk's record */
     mbar_wait(bar_a0 + 8 * st, (phases >> st) & 1u); phases ^= 1u << st;
     const u8 *b = (const u8 *)dyn_smem + st * d.span_bytes - (c_lo[c - c0] & ~15u);
+    if (count_dna) { /* exact counts of the kept bases: four per step like k_stat1, A/C/G/T by popcount of their one-hot bytes */
+      u32 nA = 0, nC = 0, nT = 0, nG = 0;
+      if (active) {
+        const u8 *sp = b + my_te + 1;
+        const u32 L = my_se - my_te - 1;
+        const bool xfer = my_kx >> 15;
+        const u32 a = (u32)(size_t)sp & 3u;
+        const u32 *wp = (const u32 *)(sp - a);
+        u32 w0 = wp[0], j = 0;
+        for (; j + 4 <= L; j += 4) {
+          const u32 w1 = *++wp;
+          const u32 v = __funnelshift_r(w0, w1, a * 8);
+          w0 = w1;
+          const u32 z = (v >> 1) & 0x03030303u;
+          const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
+          u32 oh = __byte_perm(0x08040201u, 0, sel);
+          const u32 bad = __byte_perm(0x47544341u, 0, sel) ^ v;
+          if (bad) { /* some of the four is not A/C/G/T: it counts under its own symbol unless the record's codes were transferred */
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if ((bad >> (8 * q)) & 0xFFu) { oh &= ~(0xFFu << (8 * q)); if (!xfer) atomicAdd(&dnah[C.sym_code[(v >> (8 * q)) & 0xFFu]], 1u); }
+          }
+          nA += __popc(oh & 0x01010101u); nC += __popc(oh & 0x02020202u); nT += __popc(oh & 0x04040404u); nG += __popc(oh & 0x08080808u);
+        }
+        for (; j < L; ++j) {
+          const u8 ch = sp[j];
+          if (ch == 'A') ++nA; else if (ch == 'C') ++nC; else if (ch == 'T') ++nT; else if (ch == 'G') ++nG;
+          else if (!xfer) atomicAdd(&dnah[C.sym_code[ch]], 1u);
+        }
+      }
+      nA = __reduce_add_sync(0xFFFFFFFFu, nA); nC = __reduce_add_sync(0xFFFFFFFFu, nC);
+      nT = __reduce_add_sync(0xFFFFFFFFu, nT); nG = __reduce_add_sync(0xFFFFFFFFu, nG);
+      if (lane == 0) {
+        if (nA) atomicAdd(&dnah[C.sym_code['A']], nA);
+        if (nC) atomicAdd(&dnah[C.sym_code['C']], nC);
+        if (nT) atomicAdd(&dnah[C.sym_code['T']], nT);
+        if (nG) atomicAdd(&dnah[C.sym_code['G']], nG);
+      }
+    }
     u32 flags = 0;
     /* one walk: string fields are finished here, numeric values are parked in shared memory */
     TitleCursor cur; cur.init(b, my_ts, my_te, lut);
@@ -1097,6 +1127,7 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
     __syncthreads(); /* the stage buffer and the value table are free again */
     if (nbuf == 1 && tid == 0 && c + 1 < c1) request(c + 1);
   }
+  if (count_dna) for (u32 i = tid; i < C.nsym; i += CH) if (dnah[i]) atomicAdd(arena + C.dnastat_off + i, dnah[i]);
   for (u32 i = tid; i < ncs * 256; i += CH) {
     u32 v = chist[i];
     if (v) atomicAdd(arena + C.chr_freq_off + i, v);
