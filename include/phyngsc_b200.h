@@ -133,6 +133,12 @@ int64_t phy_debug_read(phy_ctx *ctx, const char *name, uint64_t offset, void *ds
 int phy_profile(phy_ctx *ctx, int enable);
 int phy_profile_read(phy_ctx *ctx, const char **names, float *ms, int cap);
 
+/* Decoder of one subblock payload (info | title | quality | dna) back to FASTQ text: the inverse of the path above
+ * (host code, phyngsc_b200/host/phy_decode.hpp; replaces the Fetch* chain of tasks.cpp:625-1101, whose driver
+ * phyNGSD.cpp the reference does not ship).  Needs no device and no context; reentrant.  Returns the number of bytes
+ * written to `out`, PHY_ERR_CAPACITY if `cap` is too small, PHY_ERR_MALFORMED for a payload that is not a subblock. */
+int64_t phy_decode_subblock(const uint8_t *payload, uint64_t len, uint8_t *out, uint64_t cap);
+
 const char *phy_strerror(int code);
 const char *phy_last_error(phy_ctx *ctx); /* detail of the last failure on ctx (may be "") */
 int phy_abi_version(void);

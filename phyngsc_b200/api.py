@@ -33,7 +33,7 @@ class RegionResult(C.Structure):
 
 EXPORTS = ["phy_device_count", "phy_ctx_create", "phy_ctx_destroy", "phy_compress_region", "phy_upload", "phy_compress_resident", "phy_download",
            "phy_find_first_record", "phy_device_input", "phy_device_output", "phy_host_alloc", "phy_host_free",
-           "phy_make_block_header", "phy_make_footer", "phy_debug_read", "phy_profile", "phy_profile_read", "phy_strerror", "phy_last_error", "phy_abi_version"]
+           "phy_make_block_header", "phy_make_footer", "phy_debug_read", "phy_profile", "phy_profile_read", "phy_strerror", "phy_last_error", "phy_abi_version", "phy_decode_subblock"]
 
 _lib = None
 
@@ -90,6 +90,8 @@ def lib():
         L.phy_last_error.restype = C.c_char_p
         L.phy_last_error.argtypes = [C.c_void_p]
         L.phy_abi_version.restype = C.c_int
+        L.phy_decode_subblock.restype = C.c_int64
+        L.phy_decode_subblock.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -231,3 +233,18 @@ def make_footer(np_ranks, fastq_size, n_blocks, n_subblocks, overlaps, block_ord
     if k < 0:
         raise PhyError(k, lib().phy_strerror(k).decode())
     return buf[:k].tobytes()
+
+
+def decode_subblock(payload, cap=None):
+    """FASTQ text (uint8 array) of one subblock payload, decoded by phy_decode_subblock (host code, no device needed)."""
+    p = np.ascontiguousarray(np.frombuffer(payload, np.uint8) if not isinstance(payload, np.ndarray) else payload)
+    cap = int(cap) if cap else 16 * p.size + 4096
+    while True:
+        out = np.empty(cap, np.uint8)
+        n = lib().phy_decode_subblock(p.ctypes.data, p.size, out.ctypes.data, out.size)
+        if n == -5 and cap < (1 << 31):  # PHY_ERR_CAPACITY
+            cap *= 4
+            continue
+        if n < 0:
+            raise PhyError(int(n), "phy_decode_subblock")
+        return out[:n]

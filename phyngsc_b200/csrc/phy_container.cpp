@@ -73,3 +73,22 @@ extern "C" int32_t phy_make_footer(int32_t np, uint64_t fastq_size, uint32_t n_b
   if (w.over) return PHY_ERR_CAPACITY;
   return (int32_t)w.bytes();
 }
+
+/* ---- subblock decoder (host/phy_decode.hpp) behind the C ABI ------------------------------------------------- */
+#include "../host/phy_decode.hpp"
+
+extern "C" int64_t phy_decode_subblock(const uint8_t *payload, uint64_t len, uint8_t *out, uint64_t cap) {
+  if (!payload || !out) return PHY_ERR_ARG;
+  try {
+    std::string text;
+    text.reserve((size_t)len * 6);
+    phydec::decode_subblock(payload, (size_t)len, text);
+    if (text.size() > cap) return PHY_ERR_CAPACITY;
+    memcpy(out, text.data(), text.size());
+    return (int64_t)text.size();
+  } catch (const phydec::Error &) {
+    return PHY_ERR_MALFORMED;
+  } catch (...) {
+    return PHY_ERR_MALFORMED;
+  }
+}

@@ -132,3 +132,21 @@ def test_full_size_round_trip_through_the_reference_decoder(shape, mb, ctx):
         if dec.size != x.bytes_consumed or not np.array_equal(dec, data[x.win_off:x.win_off + x.bytes_consumed]):
             bad.append(i)
     assert not bad, f"subblocks that do not decode to their input: {bad[:10]}"
+
+
+@pytest.mark.parametrize("shape,mb", [("36bp", 1000), ("100bp", 512), ("150bp_paired", 512), ("var50_205", 512)])
+def test_baseline_size_round_trip_through_the_decoder(shape, mb, ctx):
+    """Encode on the GPU -> phy_decode_subblock (host/phy_decode.hpp) -> the input FASTQ, byte for byte, at BASELINE.json
+    sizes (configs[1] in full, 512 MB slices of the shapes of configs[2..4]), every subblock of a 17-batch region call."""
+    from concurrent.futures import ThreadPoolExecutor
+    data = synth.fastq(shape, 46, target_bytes=mb * 1_000_000)
+    d, out, res = ctx.compress_region(data, api.region_params(data.size, 1, 0))
+    assert res.bytes_in == data.size and sum(x.bytes_consumed for x in d) == data.size
+
+    def check(x):
+        dec = api.decode_subblock(out[x.out_off:x.out_off + x.out_len], x.bytes_consumed + 4096)
+        return dec.size == x.bytes_consumed and np.array_equal(dec, data[x.win_off:x.win_off + x.bytes_consumed])
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        ok = list(ex.map(check, d))
+    assert all(ok), f"subblocks that do not decode to their input: {[i for i, v in enumerate(ok) if not v][:10]}"
