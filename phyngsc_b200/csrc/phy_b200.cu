@@ -30,7 +30,7 @@ struct phy_ctx {
   u32 max_tiles = 0;
   /* device buffers */
   u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr, *chunk_first = nullptr, *chunk_last = nullptr;
-  u32 *tile_cnt = nullptr, *tile_off = nullptr;
+  u32 *tile_cnt = nullptr, *tile_off = nullptr; uint2 *nl_mask = nullptr;
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
   /* second input / output buffers and copy streams of the pipelined region call (allocated on first use) */
@@ -105,7 +105,7 @@ extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->plan_state,
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl};
@@ -164,6 +164,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   }
   CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
+  CK(cudaMalloc(&ctx->nl_mask, (size_t)ctx->max_tiles * 256 * sizeof(uint2)));
   CK(cudaMalloc(&ctx->plan_state, sizeof(PlanState)));
   CK(cudaMalloc(&ctx->plans, sizeof(SbPlan) * ctx->max_sb));
   CK(cudaMalloc(&ctx->hdr, sizeof(BatchHdr)));
@@ -224,7 +225,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.in = in; d.len = len; d.start_pos = start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
   d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff; d.chunk_first = ctx->chunk_first; d.chunk_last = ctx->chunk_last;
-  d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.ntiles = (len + TILE - 1) / TILE;
+  d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
   d.out = out; d.out_cap = ctx->out_cap;

@@ -73,6 +73,7 @@ struct Dev {
   u16 *kx; u32 *qoff, *doff, *toff;
   u32 *chunk_first, *chunk_last; /* numeric token values of the first / last record of every 128-record chunk, [chunk][MAXF] */
   u32 *tile_cnt, *tile_off; u32 ntiles;
+  uint2 *nl_mask;             /* newline bit mask of the batch, 64 input bytes per element */
   PlanState *plan_state; SbPlan *plans; u32 max_sb;
   BatchHdr *hdr;
   SbAcc *acc; SbClass *cls; SbOut *sbout;
@@ -104,25 +105,6 @@ __device__ __forceinline__ void load_xq(u8 *xq) {
 }
 
 /* ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ u32 nl_count16(uint4 v) {
-  const u32 NL4 = 0x0A0A0A0Au;
-  return (__popc(__vcmpeq4(v.x, NL4)) + __popc(__vcmpeq4(v.y, NL4)) + __popc(__vcmpeq4(v.z, NL4)) + __popc(__vcmpeq4(v.w, NL4))) >> 3;
-}
-
-/* newlines in this thread's 64 bytes [p, p+64) restricted to [lo, hi) */
-__device__ __forceinline__ u32 nl_count64(const u8 *in, u32 p, u32 lo, u32 hi) {
-  if (p >= hi || p + 64 <= lo) return 0;
-  u32 n = 0;
-  if (p >= lo && p + 64 <= hi) {
-    const uint4 *q = (const uint4 *)(in + p);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) n += nl_count16(__ldg(q + k));
-  } else {
-    for (u32 i = (p < lo ? lo : p); i < p + 64 && i < hi; ++i) n += in[i] == '\n';
-  }
-  return n;
-}
-
 template <int NW>
 __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *warp_sums /*[NW]*/, u32 &total) {
   u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -140,12 +122,38 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *warp_sums /*[NW]*/, u
 }
 __device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warp_sums /*[8]*/, u32 &total) { return block_excl_scan<8>(v, warp_sums, total); }
 
-/* (a) record splitter, pass 1: newline count per 16 KiB tile */
+__device__ __forceinline__ u32 nl_nibble(u32 w) {
+  const u32 x = w ^ 0x0A0A0A0Au;
+  const u32 t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); /* bit 7 of a byte set iff the byte was '\n' */
+  return (t * 0x00204081u) >> 28;
+}
+/* 64-bit newline mask (bit i = byte p + i is '\n') of this thread's 64 bytes [p, p+64) restricted to [lo, hi) */
+__device__ __forceinline__ uint2 nl_mask64(const u8 *in, u32 p, u32 lo, u32 hi) {
+  uint2 m = make_uint2(0u, 0u);
+  if (p >= hi || p + 64 <= lo) return m;
+  if (p >= lo && p + 64 <= hi) {
+    const uint4 *q = (const uint4 *)(in + p);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+    m.x = nl_nibble(v0.x) | nl_nibble(v0.y) << 4 | nl_nibble(v0.z) << 8 | nl_nibble(v0.w) << 12 | nl_nibble(v1.x) << 16 | nl_nibble(v1.y) << 20 |
+          nl_nibble(v1.z) << 24 | nl_nibble(v1.w) << 28;
+    m.y = nl_nibble(v2.x) | nl_nibble(v2.y) << 4 | nl_nibble(v2.z) << 8 | nl_nibble(v2.w) << 12 | nl_nibble(v3.x) << 16 | nl_nibble(v3.y) << 20 |
+          nl_nibble(v3.z) << 24 | nl_nibble(v3.w) << 28;
+  } else {
+    for (u32 i = (p < lo ? lo : p); i < p + 64 && i < hi; ++i)
+      if (in[i] == '\n') { if (i - p < 32) m.x |= 1u << (i - p); else m.y |= 1u << (i - p - 32); }
+  }
+  return m;
+}
+
+/* (a) record splitter, pass 1: newline mask of every 64-byte piece (kept for pass 2: one bit per input byte instead
+ * of a second read of the input) and the newline count per 16 KiB tile */
 __global__ void __launch_bounds__(256) k_nl_count(Dev d) {
   __shared__ u32 ws[8];
   u32 t = blockIdx.x;
   u32 p = t * TILE + threadIdx.x * 64;
-  u32 n = nl_count64(d.in, p, d.start_pos, d.len);
+  const uint2 m = nl_mask64(d.in, p, d.start_pos, d.len);
+  d.nl_mask[(size_t)t * 256 + threadIdx.x] = m;
+  u32 n = __popc(m.x) + __popc(m.y);
   n = __reduce_add_sync(0xFFFFFFFFu, n);
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = n;
   __syncthreads();
@@ -181,11 +189,6 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
  * Each thread owns 64 bytes.  It first builds the 64-bit mask of its newline bytes with word operations (exact
  * zero-byte test of w ^ 0x0A0A0A0A, the four flag bits gathered by a multiply), all lanes converged; only then are
  * the set bits visited -- as many iterations as the thread has newlines, two on average. */
-__device__ __forceinline__ u32 nl_nibble(u32 w) {
-  const u32 x = w ^ 0x0A0A0A0Au;
-  const u32 t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); /* bit 7 of a byte set iff the byte was '\n' */
-  return (t * 0x00204081u) >> 28;
-}
 __device__ __forceinline__ void nl_put(const Dev &d, u32 l, u32 pos) {
   const u32 r = l >> 2, k = l & 3;
   u32 *dst = k == 0 ? d.te + r : k == 1 ? d.se + r : d.rstart + r + 1;
@@ -197,19 +200,9 @@ __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   if (d.hdr->status) return;
   const u32 t = blockIdx.x;
   const u32 p = t * TILE + threadIdx.x * 64;
-  const bool whole = p >= d.start_pos && p + 64 <= d.len;
-  u32 mlo = 0, mhi = 0, n = 0;
-  if (whole) {
-    const uint4 *q = (const uint4 *)(d.in + p);
-    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
-    mlo = nl_nibble(v0.x) | nl_nibble(v0.y) << 4 | nl_nibble(v0.z) << 8 | nl_nibble(v0.w) << 12 | nl_nibble(v1.x) << 16 | nl_nibble(v1.y) << 20 |
-          nl_nibble(v1.z) << 24 | nl_nibble(v1.w) << 28;
-    mhi = nl_nibble(v2.x) | nl_nibble(v2.y) << 4 | nl_nibble(v2.z) << 8 | nl_nibble(v2.w) << 12 | nl_nibble(v3.x) << 16 | nl_nibble(v3.y) << 20 |
-          nl_nibble(v3.z) << 24 | nl_nibble(v3.w) << 28;
-    n = __popc(mlo) + __popc(mhi);
-  } else {
-    n = nl_count64(d.in, p, d.start_pos, d.len);
-  }
+  const uint2 m = d.nl_mask[(size_t)t * 256 + threadIdx.x]; /* pass 1 left it there */
+  u32 mlo = m.x, mhi = m.y;
+  const u32 n = __popc(mlo) + __popc(mhi);
   if (threadIdx.x < 32) { /* newlines before this tile: supertile base + the earlier tiles of the supertile */
     const u32 t0 = t & ~(u32)(SUPER - 1);
     u32 a = 0;
@@ -220,14 +213,8 @@ __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
   u32 tot;
   u32 l = block_excl_scan_256(n, ws, tot); /* its barriers also publish tile_base */
   l += tile_base;
-  if (!n) return;
-  if (whole) {
-    while (mlo) { const u32 bit = __ffs(mlo) - 1; mlo &= mlo - 1; nl_put(d, l++, p + bit); }
-    while (mhi) { const u32 bit = __ffs(mhi) - 1; mhi &= mhi - 1; nl_put(d, l++, p + 32 + bit); }
-  } else {
-    u32 lo = max(p, d.start_pos), hi = min(p + 64, d.len);
-    for (u32 i = lo; i < hi; ++i) if (d.in[i] == '\n') nl_put(d, l++, i);
-  }
+  while (mlo) { const u32 bit = __ffs(mlo) - 1; mlo &= mlo - 1; nl_put(d, l++, p + bit); }
+  while (mhi) { const u32 bit = __ffs(mhi) - 1; mhi &= mhi - 1; nl_put(d, l++, p + 32 + bit); }
 }
 
 /* ---- window chaining: one warp walks the rank's windows (phyNGSC.cpp:168-250, 744-755) -------------- */
