@@ -1,3 +1,4 @@
+# one ncu --set full capture of the kernels matching $1 (regex) on shape $2: bash profiles/ncu_kernel.sh "k_(emit|stat1)" 36bp <skip> <count>
 set -e
 K=${1:-'k_(lengths|emit)'}
 SHAPE=${2:-36bp}
