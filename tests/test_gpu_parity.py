@@ -37,8 +37,7 @@ def test_payloads_bit_exact_against_reference_goldens(case, ctx):
 
 
 def test_multi_batch_equals_single_batch(oracle):
-    """One batch of 24 subblocks (>= 16: the subblock groups of run_batch run on three streams) against many small
-    batches (one group each) and against the oracle."""
+    """One batch of 24 subblocks against many small batches and against the oracle."""
     data = synth.fastq("100bp", 41, target_bytes=6_000_000)
     win = 256 * 1024
     prm = api.region_params(data.size, 1, 0, window_bytes=win)
@@ -48,14 +47,33 @@ def test_multi_batch_equals_single_batch(oracle):
         d1, o1, r1 = big.compress_region(data, prm)
         d2, o2, r2 = small.compress_region(data, prm)
         assert r1.n_batches == 1 and r2.n_batches > 2 and len(d1) >= 16
-        assert r1.kernel_launches > 30  # three groups x 13 launches + the splitter
         assert api.payloads(d1, o1) == api.payloads(d2, o2)
         assert [(d.win_off, d.win_len, d.n_records) for d in d1] == [(d.win_off, d.win_len, d.n_records) for d in d2]
         assert api.payloads(d1, o1) == oracle.compress_rank(data, 1, 0, window_bytes=win)["subblocks"]
-        # payloads of all groups lie back to back in the output
-        assert all(a.out_off + ((a.out_len + 15) & ~15) == b.out_off for a, b in zip(d1, d1[1:]))
     finally:
         big.close(); small.close()
+
+
+def test_groups_of_a_large_batch_equal_one_group_batches(ctx):
+    """A 200 MB batch runs as three groups (own streams, record table and window plan of the later groups overlapping
+    the statistics of the earlier ones); the same data through 64 MiB batches runs one group per batch.  Same windows,
+    same payloads, payloads of all groups back to back, and every payload decodes to its input."""
+    data = synth.fastq("100bp", 47, target_bytes=200_000_000)
+    prm = api.region_params(data.size, 1, 0)
+    big = api.Context(0, max_batch_bytes=256 << 20, max_subblocks=64)
+    try:
+        d1, o1, r1 = big.compress_region(data, prm)
+        d2, o2, r2 = ctx.compress_region(data, prm)
+        assert r1.n_batches == 1 and r2.n_batches > 2
+        assert r1.kernel_launches > 2 + 3 * 3 + 12 * 2  # more than two groups' worth of launches
+        assert [(d.win_off, d.win_len, d.n_records, d.bytes_consumed) for d in d1] == [(d.win_off, d.win_len, d.n_records, d.bytes_consumed) for d in d2]
+        assert api.payloads(d1, o1) == api.payloads(d2, o2)
+        assert all(a.out_off + ((a.out_len + 15) & ~15) == b.out_off for a, b in zip(d1, d1[1:]))
+        for x in d1[::5]:
+            dec = api.decode_subblock(o1[x.out_off:x.out_off + x.out_len], x.bytes_consumed + 4096)
+            assert np.array_equal(dec, data[x.win_off:x.win_off + x.bytes_consumed])
+    finally:
+        big.close()
 
 
 def test_resident_legs_match_region_call(ctx):
