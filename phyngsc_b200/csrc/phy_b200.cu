@@ -164,7 +164,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   }
   CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
-  CK(cudaMalloc(&ctx->nl_mask, (size_t)ctx->max_tiles * 256 * sizeof(uint2)));
+  CK(cudaMalloc(&ctx->nl_mask, (size_t)ctx->max_tiles * NLT * sizeof(uint2)));
   CK(cudaMalloc(&ctx->plan_state, sizeof(PlanState)));
   CK(cudaMalloc(&ctx->plans, sizeof(SbPlan) * ctx->max_sb));
   CK(cudaMalloc(&ctx->hdr, sizeof(BatchHdr)));
@@ -254,9 +254,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   } while (0)
   PMARK();
   CK(cudaMemsetAsync(ctx->tile_off, 0, (size_t)((d.ntiles + SUPER - 1) / SUPER) * 4, st));
-  k_nl_count<<<d.ntiles, 256, 0, st>>>(d); PMARK();
+  k_nl_count<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
   k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
-  k_nl_emit<<<d.ntiles, 256, 0, st>>>(d); PMARK();
+  k_nl_emit<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
   k_plan<<<1, 32, 0, st>>>(d);
   k_spanmax<<<dim3(8, ctx->max_sb), 256, 0, st>>>(d); PMARK();
   ctx->launches += 5;

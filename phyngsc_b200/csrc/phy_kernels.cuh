@@ -34,7 +34,11 @@
 namespace phy {
 
 constexpr int CH = 128;            /* records per work item (4 warps; one warp = one 32-record title block) */
-constexpr int TILE = 16384;        /* bytes per newline-index tile (256 threads x 64 bytes)                */
+#ifndef PHY_NLT
+#define PHY_NLT 256
+#endif
+constexpr int NLT = PHY_NLT;        /* threads per CTA of the record splitter                               */
+constexpr int TILE = NLT * 64;     /* bytes per newline-index tile (NLT threads x 64 bytes)                */
 constexpr int SUPER = 64;          /* tiles per supertile: the single-CTA scan runs over supertiles         */
 #ifndef PHY_QCH
 #define PHY_QCH 2048
@@ -147,18 +151,18 @@ __device__ __forceinline__ uint2 nl_mask64(const u8 *in, u32 p, u32 lo, u32 hi) 
 
 /* (a) record splitter, pass 1: newline mask of every 64-byte piece (kept for pass 2: one bit per input byte instead
  * of a second read of the input) and the newline count per 16 KiB tile */
-__global__ void __launch_bounds__(256) k_nl_count(Dev d) {
-  __shared__ u32 ws[8];
+__global__ void __launch_bounds__(NLT) k_nl_count(Dev d) {
+  __shared__ u32 ws[NLT / 32];
   u32 t = blockIdx.x;
   u32 p = t * TILE + threadIdx.x * 64;
   const uint2 m = nl_mask64(d.in, p, d.start_pos, d.len);
-  d.nl_mask[(size_t)t * 256 + threadIdx.x] = m;
+  d.nl_mask[(size_t)t * NLT + threadIdx.x] = m;
   u32 n = __popc(m.x) + __popc(m.y);
   n = __reduce_add_sync(0xFFFFFFFFu, n);
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = n;
   __syncthreads();
   if (threadIdx.x < 32) {
-    n = __reduce_add_sync(0xFFFFFFFFu, threadIdx.x < 8 ? ws[threadIdx.x] : 0u);
+    n = __reduce_add_sync(0xFFFFFFFFu, threadIdx.x < NLT / 32 ? ws[threadIdx.x] : 0u);
     if (threadIdx.x == 0) { d.tile_cnt[t] = n; if (n) atomicAdd(&d.tile_off[t / SUPER], n); } /* tile_off: supertile totals, zeroed by the host */
   }
 }
@@ -194,13 +198,13 @@ __device__ __forceinline__ void nl_put(const Dev &d, u32 l, u32 pos) {
   u32 *dst = k == 0 ? d.te + r : k == 1 ? d.se + r : d.rstart + r + 1;
   if (k != 2) *dst = pos + (k == 3 ? 1u : 0u);
 }
-__global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
-  __shared__ u32 ws[8];
+__global__ void __launch_bounds__(NLT) k_nl_emit(Dev d) {
+  __shared__ u32 ws[NLT / 32];
   __shared__ u32 tile_base;
   if (d.hdr->status) return;
   const u32 t = blockIdx.x;
   const u32 p = t * TILE + threadIdx.x * 64;
-  const uint2 m = d.nl_mask[(size_t)t * 256 + threadIdx.x]; /* pass 1 left it there */
+  const uint2 m = d.nl_mask[(size_t)t * NLT + threadIdx.x]; /* pass 1 left it there */
   u32 mlo = m.x, mhi = m.y;
   const u32 n = __popc(mlo) + __popc(mhi);
   if (threadIdx.x < 32) { /* newlines before this tile: supertile base + the earlier tiles of the supertile */
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(256) k_nl_emit(Dev d) {
     if (threadIdx.x == 0) tile_base = d.tile_off[t / SUPER] + a;
   }
   u32 tot;
-  u32 l = block_excl_scan_256(n, ws, tot); /* its barriers also publish tile_base */
+  u32 l = block_excl_scan<NLT / 32>(n, ws, tot); /* its barriers also publish tile_base */
   l += tile_base;
   while (mlo) { const u32 bit = __ffs(mlo) - 1; mlo &= mlo - 1; nl_put(d, l++, p + bit); }
   while (mhi) { const u32 bit = __ffs(mhi) - 1; mhi &= mhi - 1; nl_put(d, l++, p + 32 + bit); }
