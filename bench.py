@@ -289,7 +289,7 @@ def main():
     if rank == 0:
         nrec, title_b, seq_b = shard_stats(data[: int(bytes_in)])
         # algorithmic bytes per launch of each stage: what it must read + must write
-        alg = {"nl_count": bytes_in, "nl_emit": bytes_in + 12 * nrec, "stat1": bytes_in + 2 * nrec, "qhist": seq_b + 10 * nrec,
+        alg = {"nl_count": bytes_in + bytes_in // 8, "nl_emit": bytes_in // 8 + 12 * nrec, "stat1": bytes_in + 2 * nrec, "qhist": seq_b + 10 * nrec,
                "stat2": title_b + 8 * nrec, "lengths": bytes_in + 8 * nrec, "layout": 16 * nrec, "emit": bytes_in + bytes_out}
         dom = max((k for k in stages if k in alg), key=lambda k: stages[k])
         ach = alg[dom] / (stages[dom] * 1e-3) / 1e9
