@@ -44,6 +44,7 @@ struct phy_ctx {
   u32 launches = 0;
   u64 resident_len = 0, resident_out = 0;
   u32 last_S = 0;
+  u32 nq_hint = 0, prev_groups = 0, prev_max_len = 0; /* quality alphabet size seen by the previous batch (sizes the packed tables' shared memory without a readback) */
   /* per-kernel timing (phy_profile): one event after every launch of run_batch */
   bool profile = false;
   cudaEvent_t pev[NKERN + 1] = {};
@@ -235,6 +236,12 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   u32 tune = tune_env >= 0 ? (u32)tune_env : 0u;
   d.tune = tune;
   cudaStream_t st = ctx->stream;
+  if (ctx->prev_groups) { /* the previous batch is complete (the callers synchronise): its alphabet is the hint for this one */
+    u32 mx = 0;
+    for (u32 g = 0; g < ctx->prev_groups; ++g) mx = ctx->h_hdr_g[g].max_pk_bytes > mx ? ctx->h_hdr_g[g].max_pk_bytes : mx;
+    if (ctx->prev_max_len) ctx->nq_hint = mx / 2 / (ctx->prev_max_len + 1);
+    ctx->prev_groups = 0;
+  }
   ctx->last_S = 0;
   if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
   int pi = 0;
@@ -344,22 +351,28 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     k_qhist<<<dim3(H.max_qchunks, Sg), qh_threads, qh_dyn, gs>>>(e); GMARK();
     k_classify<<<Sg, 32, 0, gs>>>(e); GMARK();
     /* the group header now holds the exact size of the packed quality tables: the copy is ordered before the
-     * statistics kernels that follow, so the host gets it while they keep the GPU busy */
+     * statistics kernels that follow, so the host gets it while they keep the GPU busy (only waited for when the
+     * previous batch left no hint, see below) */
     CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs));
     CK(cudaEventRecord(ctx->ev_rb[g], gs));
     k_zero_hist<<<dim3(8, Sg), 256, 0, gs>>>(e); GMARK();
     k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, s2_dyn, gs>>>(e); GMARK();
   }
   static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
+  static const bool pk_exact = getenv("PHY_PK_EXACT") != nullptr;
+  const u32 nq_hint = pk_exact ? 0u : ctx->nq_hint; /* quality alphabet of the previous batch of this context (0: none yet) */
   for (u32 g = 0; g < G; ++g) {
     Dev &e = dg[g];
     const u32 Sg = s0[g + 1] - s0[g];
     cudaStream_t gs = g ? ctx->gstream[g] : st;
-    CK(cudaEventSynchronize(ctx->ev_rb[g]));
-    {
-      const u32 pk = (ctx->h_hdr_g[g].max_pk_bytes + 15u) & ~15u;
-      e.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
-    }
+    /* Shared memory for the packed quality tables: (longest read + 1) x alphabet x 2 bytes.  The alphabet size is known
+     * on the device only; the first batch of a context waits for the readback, later batches reserve room for the
+     * alphabet the previous batch had plus eight symbols, so the GPU never waits for the host here (a subblock whose
+     * tables outgrow the reservation reads them from global memory instead -- slower, same bytes). */
+    u32 pk;
+    if (nq_hint) pk = ((H.max_len + 1) * (nq_hint + 8 > 256 ? 256u : nq_hint + 8) * 2u + 15u) & ~15u;
+    else { CK(cudaEventSynchronize(ctx->ev_rb[g])); pk = (ctx->h_hdr_g[g].max_pk_bytes + 15u) & ~15u; }
+    e.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
     k_huff<<<dim3(16, Sg), 128, 4 * sizeof(HuffScratch), gs>>>(e); GMARK();
     /* one warp per 32-record block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
     const u32 solo_dyn = e.pk_bytes + EW * e.enc_stage, pair_dyn = e.pk_bytes + EP * e.enc_stage;
@@ -378,9 +391,11 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     GMARK();
     ctx->launches += 12;
     CK(cudaMemcpyAsync(ctx->h_sbout + s0[g], e.sbout, sizeof(SbOut) * Sg, cudaMemcpyDeviceToHost, gs));
+    CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* max_pk_bytes: the next batch's hint */
     if (g == G - 1) CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* total_out = the end of the last group */
     if (g) { CK(cudaEventRecord(ctx->ev_done[g], gs)); CK(cudaStreamWaitEvent(st, ctx->ev_done[g], 0)); } /* the caller waits on the main stream */
   }
+  ctx->prev_groups = G; ctx->prev_max_len = H.max_len;
   CK(cudaGetLastError());
   if (ctx->profile) {
     CK(cudaStreamSynchronize(st));
