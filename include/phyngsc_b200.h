@@ -95,6 +95,15 @@ int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len
                         uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
                         phy_region_result *result);
 
+/* Streamed variant for callers that are still filling `region` (a reader thread pulling the rank's byte range from
+ * the file, phyNGSC.cpp:128/:249 done ahead of the GPU): before the library touches region[0, upto) it calls
+ * wait(user, upto), which returns once those bytes are in place.  Batches are uploaded in order, so the file read of
+ * batch b+1 overlaps the upload and the kernels of batch b.  Everything else is phy_compress_region. */
+typedef void (*phy_wait_fn)(void *user, uint64_t upto);
+int phy_compress_region_streamed(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
+                                 phy_wait_fn wait, void *user, uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs,
+                                 uint32_t *inout_n_descs, phy_region_result *result);
+
 /* The same work split into its three legs, for callers that keep data resident (and for kernel-only
  * timing): upload copies host bytes into the ctx input buffer; compress_resident runs the kernels over
  * what is resident (single batch: region_len <= max_batch_bytes) leaving payloads in device memory

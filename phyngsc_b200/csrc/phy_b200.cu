@@ -540,12 +540,15 @@ static int pipeline_init(phy_ctx *ctx) {
  * the payloads of batch b-1 stream device -> host on a third (double-buffered input and output).  The start of
  * batch b+1 does not depend on batch b's result: it is placed one window + slack before the end of batch b, which
  * is never past the point where the window chain stops in batch b. */
-extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
-                                   uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
-                                   phy_region_result *result) {
+static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
+                                phy_wait_fn wait, void *wait_user, uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs,
+                                uint32_t *inout_n_descs, phy_region_result *result) {
   if (!ctx || !region || !out || !descs || !inout_n_descs || region_len == 0) return PHY_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  /* `wait` (streamed variant): region[0, upto) is only valid after wait(user, upto) has returned */
+  auto need = [&](u64 upto) { if (wait) wait(wait_user, upto < region_len ? upto : region_len); };
   PlanState st;
+  if (params && params->rank != 0) need(1u << 20); /* the '@' heuristic looks at the head of the region */
   int rc = init_plan(ctx, region, region_len, params, 0, false, st);
   if (rc) return rc;
   const u32 first = st.rec_start;
@@ -573,7 +576,7 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
   float k_ms = 0, h2d_ms = 0, d2h_ms = 0;
   u64 h2d_bytes = 0;
   int worst = 0;
-  const bool patch_nl = st.is_last && region[region_len - 1] != '\n';
+  bool patch_nl = false; /* decided when the final batch is uploaded (the region's last byte must be there) */
 
   /* enqueue the upload of the batch that starts at `base` into buffer `slot` (stream s_in).  Bytes that the
    * previous upload already brought to the device (the tail of the other buffer: consecutive batches overlap by one
@@ -591,6 +594,8 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
       if (carry > blen) carry = blen;
       CK(cudaMemcpyAsync(inb[slot], inb[up_slot] + (base - up_base), carry, cudaMemcpyDeviceToDevice, ctx->s_in));
     }
+    need(base + blen);
+    if (final) patch_nl = st.is_last && region[region_len - 1] != '\n';
     if (blen > carry) CK(cudaMemcpyAsync(inb[slot] + carry, region + base + carry, blen - carry, cudaMemcpyHostToDevice, ctx->s_in));
     h2d_bytes += blen - carry;
     if (final && patch_nl) { /* virtual trailing newline, see patch_trailing_newline */
@@ -682,6 +687,18 @@ extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t
   for (u32 i = 0; i < nd; ++i) if (descs[i].status < worst) worst = descs[i].status;
   if (worst) ctx->err = std::string("a subblock failed: ") + phy_strerror(worst);
   return worst;
+}
+
+extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
+                                   uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs, uint32_t *inout_n_descs,
+                                   phy_region_result *result) {
+  return compress_region_impl(ctx, region, region_len, params, nullptr, nullptr, out, out_cap, descs, inout_n_descs, result);
+}
+
+extern "C" int phy_compress_region_streamed(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
+                                            phy_wait_fn wait, void *user, uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs,
+                                            uint32_t *inout_n_descs, phy_region_result *result) {
+  return compress_region_impl(ctx, region, region_len, params, wait, user, out, out_cap, descs, inout_n_descs, result);
 }
 
 extern "C" int phy_profile(phy_ctx *ctx, int enable) {

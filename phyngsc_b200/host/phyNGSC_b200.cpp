@@ -24,6 +24,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "phyngsc_b200.h"
@@ -41,6 +48,17 @@ static void die(int rank, int code, const char *msg, const char *detail) {
   MPI_Abort(MPI_COMM_WORLD, code);
   exit(code);
 }
+
+/* how much of the rank's region the reader thread has delivered */
+struct Watermark {
+  std::mutex m; std::condition_variable cv; uint64_t have = 0; bool failed = false;
+  void publish(uint64_t upto, bool fail) { { std::lock_guard<std::mutex> g(m); if (upto > have) have = upto; failed = failed || fail; } cv.notify_all(); }
+  static void wait_cb(void *self, uint64_t upto) {
+    Watermark *w = (Watermark *)self;
+    std::unique_lock<std::mutex> g(w->m);
+    w->cv.wait(g, [&] { return w->have >= upto || w->failed; });
+  }
+};
 
 /* Block assembly of one rank, phyNGSC.cpp:842-928: appends the finished blocks to `file_bytes`. */
 struct BlockAssembler {
@@ -133,13 +151,41 @@ int main(int argc, char **argv) {
   if (end > size) end = size;
   const uint64_t region_len = end - start;
 
-  uint8_t *in = (uint8_t *)phy_host_alloc(region_len + 64);
+  /* Pinned buffers (the copies of the pipelined region call are asynchronous only from pinned memory).  Pinning costs
+   * about 0.6 s per GB on this box -- most of a one-shot run's wall time; PHY_DRIVER_PINNED=0 uses pageable memory
+   * instead (measured 2.1-5.4 s against 2.9 s on a 2 GB file: first-touch faults and synchronous staged copies). */
+  const bool pinned = !(getenv("PHY_DRIVER_PINNED") && atoi(getenv("PHY_DRIVER_PINNED")) == 0);
+  uint8_t *in = (uint8_t *)(pinned ? phy_host_alloc(region_len + 64) : malloc(region_len + 64));
   uint64_t out_cap = region_len / 2 + (1u << 20);
-  uint8_t *out = (uint8_t *)phy_host_alloc(out_cap);
-  if (!in || !out) die(rank, 3, "cannot allocate pinned host buffers", nullptr);
-  for (uint64_t o = 0; o < region_len; o += 1u << 30) { /* MPI counts are ints */
-    uint64_t n = region_len - o < (1u << 30) ? region_len - o : (1u << 30);
-    MPI_File_read_at(fin, (MPI_Offset)(start + o), in + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
+  uint8_t *out = (uint8_t *)(pinned ? phy_host_alloc(out_cap) : malloc(out_cap));
+  if (!in || !out) die(rank, 3, "cannot allocate host buffers", nullptr);
+  /* The rank's byte range is read by a helper thread in 32 MiB pieces while the GPU path already works on what has
+   * arrived (phy_compress_region_streamed waits on the watermark before it touches a byte).  The helper uses pread on
+   * the input path, not MPI-IO: MPI stays on the main thread (MPI_THREAD_FUNNELED, phyNGSC.cpp:57).
+   * PHY_DRIVER_STREAM=0 reads everything first with MPI_File_read_at, like the reference. */
+  const bool streamed = !(getenv("PHY_DRIVER_STREAM") && atoi(getenv("PHY_DRIVER_STREAM")) == 0);
+  Watermark wm;
+  std::thread reader;
+  if (streamed) {
+    reader = std::thread([&wm, in, start, region_len, path = std::string(argv[1])]() {
+      int fd = open(path.c_str(), O_RDONLY);
+      uint64_t o = 0;
+      while (fd >= 0 && o < region_len) {
+        uint64_t n = region_len - o < (32u << 20) ? region_len - o : (32u << 20);
+        ssize_t got = pread(fd, in + o, n, (off_t)(start + o));
+        if (got <= 0) break;
+        o += (uint64_t)got;
+        wm.publish(o, false);
+      }
+      if (fd >= 0) close(fd);
+      wm.publish(o, o < region_len); /* short read: wake the waiters up with the failure flag */
+    });
+  } else {
+    for (uint64_t o = 0; o < region_len; o += 1u << 30) { /* MPI counts are ints */
+      uint64_t n = region_len - o < (1u << 30) ? region_len - o : (1u << 30);
+      MPI_File_read_at(fin, (MPI_Offset)(start + o), in + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
+    }
+    wm.publish(region_len, false);
   }
   const double t_read = MPI_Wtime();
 
@@ -159,7 +205,9 @@ int main(int argc, char **argv) {
   std::vector<phy_subblock_desc> descs((size_t)(region_len / (READ_BUFFER_SIZE / 2)) + 64);
   uint32_t nd_ = (uint32_t)descs.size();
   phy_region_result res;
-  rc = phy_compress_region(ctx, in, region_len, &prm, out, out_cap, descs.data(), &nd_, &res);
+  rc = phy_compress_region_streamed(ctx, in, region_len, &prm, &Watermark::wait_cb, &wm, out, out_cap, descs.data(), &nd_, &res);
+  if (reader.joinable()) reader.join();
+  if (wm.failed) die(rank, 3, "cannot read the input", argv[1]);
   if (rc) die(rank, 4, phy_strerror(rc), phy_last_error(ctx));
   const double t_comp = MPI_Wtime();
   for (uint32_t i = 0; i < nd_; ++i)
@@ -208,7 +256,7 @@ int main(int argc, char **argv) {
     if (r == rank) {
       if (rank == 0) printf("RANK\tCOMP_TIME\tN_BLOCK\tN_SUBBLOCKS\n");
       printf("%d\t%f\t%u\t%u\n", rank, t1 - t0, ba.n_blocks, nd_);
-      printf("[I] rank %d: read %.3fs, gpu path %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), assemble+write %.3fs, %llu -> %lld bytes\n",
+      printf("[I] rank %d: read (issued) %.3fs, read + gpu path %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), assemble+write %.3fs, %llu -> %lld bytes\n",
              rank, t_read - t0, t_comp - t_read, res.h2d_ms, res.kernel_ms, res.d2h_ms, res.kernel_launches, t1 - t_comp,
              (unsigned long long)res.bytes_in, mine);
       fflush(stdout);
@@ -216,7 +264,7 @@ int main(int argc, char **argv) {
   }
   MPI_Barrier(MPI_COMM_WORLD);
   phy_ctx_destroy(ctx);
-  phy_host_free(in); phy_host_free(out);
+  if (pinned) { phy_host_free(in); phy_host_free(out); } else { free(in); free(out); }
   MPI_File_close(&fin); MPI_File_close(&fout);
   MPI_Finalize();
   return 0;
