@@ -56,3 +56,21 @@ def test_driver_blocks_match_reference_goldens_keyed_by_rank(case, tmp_path):
         assert [b["raw"] for b in mine["per_rank_blocks"][r]] == [b["raw"] for b in ref["per_rank_blocks"][r]]
     assert mine["footer"]["overlaps"] == ref["footer"]["overlaps"]
     assert mine["footer"]["n_subblocks"] == ref["footer"]["n_subblocks"]
+
+
+@pytest.mark.parametrize("shape,mb,npr,stream", [("var50_205", 400, 3, "1"), ("36bp", 150, 2, "0")])
+def test_compress_then_decompress_gives_the_file_back(shape, mb, npr, stream, tmp_path):
+    """The whole tool chain on a file: driver (reader thread + streamed region call, or everything read first) -> .ngsc
+    with several blocks per rank and subblocks split across blocks -> phyngsc_b200.decompress -> the input, byte for byte."""
+    from phyngsc_b200 import decompress
+    data = synth.fastq(shape, 600 + mb, target_bytes=mb * 1_000_000 + 311)
+    src, dst, back = tmp_path / "in.fastq", tmp_path / "out.ngsc", tmp_path / "back.fastq"
+    data.tofile(src)
+    os.environ["PHY_DRIVER_STREAM"] = stream
+    try:
+        run_driver(src, dst, npr)
+    finally:
+        del os.environ["PHY_DRIVER_STREAM"]
+    n, k = decompress.decompress(str(dst), str(back), threads=8)
+    assert n == data.size and k >= npr
+    assert open(back, "rb").read() == data.tobytes()
