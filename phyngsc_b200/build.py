@@ -4,6 +4,7 @@
   csrc/libphysynth.so       synthetic FASTQ generator (plain C)
   host/phyNGSC_b200         drop-in host driver (C++/MPI; built against the fork-based mpi.h stand-in
                             when no MPI is installed)
+  host/phyNGSD_b200         decompressor (plain C++)
 """
 import os
 import shutil
@@ -14,6 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(CSRC, "libphyngsc_b200.so")
 DRIVER = os.path.join(HOST, "phyNGSC_b200")
+DECOMP = os.path.join(HOST, "phyNGSD_b200")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -50,11 +52,20 @@ def build_driver(force=False):
     return DRIVER
 
 
+def build_decompressor(force=False):
+    """host/phyNGSD_b200: plain C++ (no CUDA, no MPI)."""
+    src = [os.path.join(HOST, "phyNGSD_b200.cpp"), os.path.join(HOST, "phy_decode.hpp")]
+    if force or _newer(DECOMP, src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", DECOMP, src[0], "-lpthread"])
+    return DECOMP
+
+
 def build_all(force=False):
     from . import synth
     synth.build(force)
     build_lib(force)
     build_driver(force)
+    build_decompressor(force)
 
 
 if __name__ == "__main__":

@@ -36,6 +36,21 @@ def test_reference_ngsc_files_decompress_to_their_input(case, tmp_path):
     assert hashlib.sha256(got).hexdigest() == case["input_sha256"]
 
 
+@pytest.mark.parametrize("case", json.load(open(os.path.join(GOLD, "manifest.json")))[::3], ids=lambda c: c["file"])
+def test_cpp_decompressor_binary(case, tmp_path):
+    """host/phyNGSD_b200 (the C++ program a user runs) on reference-minted files."""
+    import subprocess
+    from phyngsc_b200 import build
+    exe = build.build_decompressor()
+    out = tmp_path / "out.fastq"
+    p = subprocess.run([exe, os.path.join(GOLD, case["file"]), str(out), "3"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == case["input_sha256"]
+    bad = tmp_path / "bad.ngsc"
+    bad.write_bytes(open(os.path.join(GOLD, case["file"]), "rb").read()[:-7])
+    assert subprocess.run([exe, str(bad), str(out)], capture_output=True, timeout=120).returncode != 0
+
+
 def test_garbage_is_an_error_not_a_crash():
     rng = np.random.default_rng(5)
     for n in (0, 3, 19, 200, 5000):
