@@ -58,7 +58,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -79,7 +79,7 @@ class ClockSampler:
     def summary(self, t0=None, t1=None):
         if self.proc is not None:
             self.proc.terminate()
-        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0 - 0.06) and (t1 is None or t <= t1 + 0.06)] or [r for _, r in self.rows]
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0 - 0.11) and (t1 is None or t <= t1 + 0.11)] or [r for _, r in self.rows]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
