@@ -168,3 +168,25 @@ def test_baseline_size_round_trip_through_the_decoder(shape, mb, ctx):
     with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
         ok = list(ex.map(check, d))
     assert all(ok), f"subblocks that do not decode to their input: {[i for i, v in enumerate(ok) if not v][:10]}"
+
+
+def test_a_bad_record_fails_only_its_subblock_in_a_grouped_batch():
+    """200 MB in one batch (three groups): a '+' line damaged in the middle fails exactly the subblock that holds it
+    (PHY_ERR_MALFORMED); every other subblock of every group is written and decodes to its input."""
+    data = synth.fastq("36bp", 48, target_bytes=200_000_000).copy()
+    mid = data.size // 2
+    plus = data[mid:mid + 4096].tobytes().find(b"\n+\n") + 1
+    data[mid + plus] = ord("-")
+    big = api.Context(0, max_batch_bytes=256 << 20, max_subblocks=64)
+    try:
+        d, out, res = big.compress_region(data, api.region_params(data.size, 1, 0), check=False)
+        assert res.n_batches == 1 and len(d) >= 16
+        bad = [i for i, x in enumerate(d) if x.status]
+        assert len(bad) == 1 and d[bad[0]].status == -1
+        assert d[bad[0]].win_off <= mid + plus < d[bad[0]].win_off + d[bad[0]].bytes_consumed
+        for i in (0, bad[0] - 1, bad[0] + 1, len(d) - 1):
+            x = d[i]
+            dec = api.decode_subblock(out[x.out_off:x.out_off + x.out_len], x.bytes_consumed + 4096)
+            assert np.array_equal(dec, data[x.win_off:x.win_off + x.bytes_consumed])
+    finally:
+        big.close()
