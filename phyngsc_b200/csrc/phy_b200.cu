@@ -232,9 +232,6 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.out = out; d.out_cap = ctx->out_cap;
   d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
   d.span_bytes = 0;
-  static const int tune_env = getenv("PHY_TUNE") ? atoi(getenv("PHY_TUNE")) : -1;
-  u32 tune = tune_env >= 0 ? (u32)tune_env : 0u;
-  d.tune = tune;
   cudaStream_t st = ctx->stream;
   if (ctx->prev_groups) { /* the previous batch is complete (the callers synchronise): its alphabet is the hint for this one */
     u32 mx = 0;

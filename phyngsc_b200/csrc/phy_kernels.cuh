@@ -93,7 +93,6 @@ struct Dev {
   u32 qh_rows;                /* rows of a k_qhist CTA's private table */
   u32 enc_stage;              /* bytes of one warp's stage buffer in the encoder kernels (a 32-record block) */
   u32 qh_recs, qh_stage;      /* records per pipeline stage of k_qhist (128, 64 or 32) and the bytes of a stage buffer */
-  u32 tune;                   /* experiment switches (PHY_TUNE) */
 };
 
 /* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
