@@ -205,7 +205,6 @@ def main():
         print("bench.py: no CUDA device -- the product path has no CPU fallback", file=sys.stderr)
         return 2
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("PHY_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

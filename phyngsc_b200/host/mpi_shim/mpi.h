@@ -18,6 +18,7 @@
 
 #include <fcntl.h>
 #include <pthread.h>
+#include <signal.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -68,12 +69,17 @@ struct phy_shim_arena {
   pthread_barrier_t barrier;
   pthread_mutex_t lock;
   long long shared_off[PHY_SHIM_MAX_FILES];
+  volatile int abort_code;                 /* set by MPI_Abort before it signals the other ranks */
+  volatile pid_t pids[PHY_SHIM_MAX_RANKS]; /* every rank's process id (written by the rank itself) */
   unsigned char slots[PHY_SHIM_MAX_RANKS][PHY_SHIM_SLOT_BYTES];
 };
 
 static struct phy_shim_arena *phy_shim_arena_p = 0;
 static int phy_shim_rank = 0, phy_shim_np = 1, phy_shim_files_open = 0;
 static pid_t phy_shim_kids[PHY_SHIM_MAX_RANKS];
+
+/* MPI_Abort ends every rank: the aborting rank signals the others, which leave with the same exit code */
+static void phy_shim_on_term(int sig) { (void)sig; _exit(phy_shim_arena_p && phy_shim_arena_p->abort_code ? phy_shim_arena_p->abort_code : 143); }
 
 static inline int MPI_Init_thread(int *argc, char ***argv, int required, int *provided) {
   (void)argc; (void)argv;
@@ -101,6 +107,8 @@ static inline int MPI_Init_thread(int *argc, char ***argv, int required, int *pr
     if (k == 0) { phy_shim_rank = r; break; }
     phy_shim_kids[r] = k;
   }
+  phy_shim_arena_p->pids[phy_shim_rank] = getpid();
+  signal(SIGTERM, phy_shim_on_term);
   if (provided) *provided = required;
   return MPI_SUCCESS;
 }
@@ -116,11 +124,24 @@ static inline double MPI_Wtime(void) {
 static inline int MPI_Finalize(void) {
   fflush(stdout); fflush(stderr);
   if (phy_shim_rank == 0) {
-    for (int r = 1; r < phy_shim_np; ++r) { int st; waitpid(phy_shim_kids[r], &st, 0); }
+    int worst = 0;
+    for (int r = 1; r < phy_shim_np; ++r) {
+      int st = 0;
+      if (waitpid(phy_shim_kids[r], &st, 0) > 0 && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) worst = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
+    }
+    if (worst) _exit(worst); /* a rank that failed after its last collective still fails the run */
   }
   return 0;
 }
-static inline int MPI_Abort(MPI_Comm c, int code) { (void)c; fflush(stdout); fflush(stderr); _exit(code); return 0; }
+static inline int MPI_Abort(MPI_Comm c, int code) {
+  (void)c; fflush(stdout); fflush(stderr);
+  if (phy_shim_arena_p) {
+    phy_shim_arena_p->abort_code = code ? code : 1;
+    for (int r = 0; r < phy_shim_np; ++r) { const pid_t p = phy_shim_arena_p->pids[r]; if (r != phy_shim_rank && p > 0) kill(p, SIGTERM); }
+  }
+  _exit(code);
+  return 0;
+}
 
 /* ---- MPI-IO ------------------------------------------------------------ */
 static inline int MPI_File_open(MPI_Comm c, const char *name, int amode, MPI_Info info, MPI_File *fh) {

@@ -15,7 +15,8 @@
  * to the reference's.
  *
  * Differences kept on purpose: np = 1 is accepted (the reference refuses np < 2, :91-97; WRID then takes 0 bits);
- * `threads` only selects the per-thread record cap of :51 for threads = 1 semantics (the GPU path has no thread count).
+ * `threads` is accepted and checked like the reference does but changes nothing: the reference's output is thread-count
+ * independent and the GPU path has no thread count.
  * Built against a real <mpi.h> when mpicxx exists, otherwise against host/mpi_shim/mpi.h (PHY_SHIM_NP=<n> ./phyNGSC_b200 ...).
  */
 #include <mpi.h>
@@ -201,7 +202,13 @@ int main(int argc, char **argv) {
 
   phy_region_params prm;
   prm.file_size = size; prm.np = np; prm.rank = rank; prm.window_bytes = READ_BUFFER_SIZE; prm.overlap = OVERLAP;
-  prm.record_cap = 100000u / (uint32_t)threads; /* records_per_th, phyNGSC.cpp:51,82 */
+  /* Record cap.  The reference gives each of its `threads` byte slices of a window room for 100000/threads + 1 records
+   * (phyNGSC.cpp:51,82,261-266,321-326) and its output does not depend on `threads` as long as no slice runs out of room
+   * (when one does, the reference silently drops the rest of that slice).  A subblock here is one run of
+   * consecutive records, so the whole-window cap of threads = 1 is used for every thread count: the same bytes as the
+   * reference wherever the reference keeps every record. */
+  prm.record_cap = 100000u;
+  (void)threads;
   std::vector<phy_subblock_desc> descs((size_t)(region_len / (READ_BUFFER_SIZE / 2)) + 64);
   uint32_t nd_ = (uint32_t)descs.size();
   phy_region_result res;

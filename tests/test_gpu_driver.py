@@ -78,3 +78,24 @@ def test_compress_then_decompress_gives_the_file_back(shape, mb, npr, stream, tm
         p = subprocess.run([build.build_decompressor(), str(dst), str(back), "8"], capture_output=True, text=True, timeout=600)  # the C++ program
         assert p.returncode == 0, p.stdout + p.stderr
     assert open(back, "rb").read() == data.tobytes()
+
+
+@pytest.mark.parametrize("threads", [2, 4])
+def test_driver_threads_argument_matches_the_reference_at_the_same_thread_count(threads, tmp_path, oracle):
+    """`threads` > 1 must not change a byte: the reference's output is thread-count independent while no per-thread slice of
+    a window runs out of room (phyNGSC.cpp:261-266,321-326), and 36 bp windows hold ~69 k records -- more than
+    100000/threads for threads >= 2, so a whole-window cap of 100000/threads would cut them short.  The unmodified reference
+    runs at the same np and the same thread count; blocks are compared keyed by rank."""
+    if not oracle.have_reference():
+        pytest.skip("oracle/_ref/phyNGSC_ref not built")
+    data = synth.fastq("36bp", 700 + threads, target_bytes=40_000_000 + 977)
+    src, dst, ref = tmp_path / "in.fastq", tmp_path / "out.ngsc", tmp_path / "ref.ngsc"
+    data.tofile(src)
+    out = run_driver(src, dst, 2, threads=threads)
+    assert "WARNING" not in out
+    oracle.run_reference(str(src), str(ref), np_ranks=2, threads=threads)
+    mine, want = container.read_ngsc(str(dst)), container.read_ngsc(str(ref))
+    for r in range(2):
+        assert len(mine["per_rank_subblocks"][r]) == len(want["per_rank_subblocks"][r])
+        assert [b["raw"] for b in mine["per_rank_blocks"][r]] == [b["raw"] for b in want["per_rank_blocks"][r]]
+    assert mine["footer"]["n_subblocks"] == want["footer"]["n_subblocks"]

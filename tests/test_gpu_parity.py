@@ -190,3 +190,42 @@ def test_a_bad_record_fails_only_its_subblock_in_a_grouped_batch():
             assert np.array_equal(dec, data[x.win_off:x.win_off + x.bytes_consumed])
     finally:
         big.close()
+
+
+@pytest.mark.parametrize("shape,seed", [("36bp", 2), ("100bp", 3)])
+def test_baseline_size_payloads_bit_exact_against_the_compiled_reference(shape, seed, tmp_path):
+    """BASELINE.json size, not a round trip: 1 GB of the configs[1] / configs[2] shapes is compressed by the UNMODIFIED
+    reference (oracle/_ref/phyNGSC_ref, np = 2, threads = 1; about 10 s) and by the CUDA path at the same partitioning,
+    once with whole-region batches (a rank's 60 subblocks run as three subblock groups) and once with 64 MiB batches.
+    Every subblock payload is compared byte for byte keyed by (WRID, ordinal); so are the footer's start overlaps."""
+    from oracle import phy_oracle as O
+    if not O.have_reference():
+        pytest.skip("oracle/_ref/phyNGSC_ref not built")
+    data = synth.fastq(shape, seed, target_bytes=1_000_000_000)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
+    src, dst = os.path.join(shm, f"phy_parity_{os.getpid()}.fastq"), os.path.join(shm, f"phy_parity_{os.getpid()}.ngsc")
+    data.tofile(src)
+    try:
+        O.run_reference(src, dst, np_ranks=2, threads=1, timeout=900)
+        ref = container.read_ngsc(dst)
+    finally:
+        for p in (src, dst):
+            if os.path.exists(p):
+                os.remove(p)
+    assert ref["footer"]["fastq_size"] == data.size
+    whole = api.Context(0, max_batch_bytes=(512 << 20) + (16 << 20), max_subblocks=96)
+    small = api.Context(0, max_batch_bytes=64 << 20, max_subblocks=32)
+    try:
+        for r in range(2):
+            start, _ = api.region_slice(data.size, 2, r)
+            want = ref["per_rank_subblocks"][r]
+            for name, c in (("whole-region batch", whole), ("64 MiB batches", small)):
+                descs, out, res = c.compress_region(data[start:], api.region_params(data.size, 2, r))
+                got = api.payloads(descs, out)
+                assert len(got) == len(want), f"rank {r}, {name}: {len(got)} subblocks, reference wrote {len(want)}"
+                bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+                assert not bad, f"rank {r}, {name}: payloads {bad[:8]} differ from the reference's"
+                assert res.wr_overlap == ref["footer"]["overlaps"][r]
+                assert (res.n_batches == 1) == (c is whole)
+    finally:
+        whole.close(); small.close()
