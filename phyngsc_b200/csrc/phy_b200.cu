@@ -11,10 +11,11 @@
 
 #include "../../include/phyngsc_b200.h"
 #include "phy_kernels.cuh"
+#include "phy_encode.cuh"
 
 using namespace phy;
 
-#define NKERN 16
+#define NKERN 20
 #define GROUPS_MAX 4
 
 static_assert(sizeof(phy_subblock_desc) == 72, "phy_subblock_desc layout is part of the ABI");
@@ -33,6 +34,7 @@ struct phy_ctx {
   u32 *tile_cnt = nullptr, *tile_off = nullptr; uint2 *nl_mask = nullptr;
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
+  u32 *tmp = nullptr; u64 tmp_cap = 0; u64 *tmp_used = nullptr; /* temporary buffer of the single-walk encoder (words) */
   /* second input / output buffers and copy streams of the pipelined region call (allocated on first use) */
   u8 *in2 = nullptr, *out2 = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -67,10 +69,11 @@ struct phy_ctx {
 static const u32 SPAN_MAX = 96 * 1024;
 static const u32 QH_DYN_MAX = 200 * 1024; /* private rows + span buffers of k_qhist */
 static const u32 ENC_STAGE_MAX = 24 * 1024; /* a warp's stage in the encoder kernels: 32 records of up to 768 bytes on average */
+static const u32 ENC_DYN_MAX = 200 * 1024;  /* dynamic shared memory of the single-walk encoder kernels */
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
 static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "qhist", "classify", "zero_hist",
-                                          "stat2", "huff", "lengths", "layout", "outscan", "zero_out", "emit"};
+                                          "stat2", "huff", "slots", "enc_title", "enc_qd", "lengths", "layout", "outscan", "zero_out", "place", "emit"};
 
 extern "C" int phy_abi_version(void) { return PHY_ABI_VERSION; }
 
@@ -107,7 +110,7 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->plan_state,
-                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2};
+                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl};
   for (void *p : host) if (p) cudaFreeHost(p);
@@ -174,6 +177,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaMalloc(&ctx->sbout, sizeof(SbOut) * ctx->max_sb));
   CK(cudaMalloc(&ctx->arena, (size_t)ctx->arena_words * 4 * ctx->max_sb));
   CK(cudaMalloc(&ctx->out, ctx->out_cap + 64));
+  ctx->tmp_cap = (ctx->max_batch + ctx->max_batch / 2) / 4 + (1u << 20); /* 1.5 bytes per input byte: slots are sized by bounds, not by what is written */
+  CK(cudaMalloc(&ctx->tmp, ctx->tmp_cap * 4));
+  CK(cudaMalloc(&ctx->tmp_used, sizeof(u64)));
   CK(cudaHostAlloc(&ctx->h_hdr, sizeof(BatchHdr), cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_plans, sizeof(SbPlan) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_sbout, sizeof(SbOut) * ctx->max_sb, cudaHostAllocDefault));
@@ -193,6 +199,11 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
+  CK(cudaFuncSetAttribute(k_enc_title, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_enc_qd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_enc_qd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_enc_qd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_enc_qd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   return PHY_OK;
 }
 
@@ -232,6 +243,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.out = out; d.out_cap = ctx->out_cap;
   d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
   d.span_bytes = 0;
+  d.tmp = ctx->tmp; d.tmp_cap = ctx->tmp_cap; d.tmp_used = ctx->tmp_used;
   cudaStream_t st = ctx->stream;
   if (ctx->prev_groups) { /* the previous batch is complete (the callers synchronise): its alphabet is the hint for this one */
     u32 mx = 0;
@@ -258,6 +270,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   } while (0)
   PMARK();
   CK(cudaMemsetAsync(ctx->tile_off, 0, (size_t)((d.ntiles + SUPER - 1) / SUPER) * 4, st));
+  CK(cudaMemsetAsync(ctx->tmp_used, 0, sizeof(u64), st));
   k_nl_count<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
   k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
   k_nl_emit<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
@@ -306,6 +319,22 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     u32 es = (H.max_span32 + 16 + 255) & ~255u;
     d.enc_stage = es > ENC_STAGE_MAX ? ENC_STAGE_MAX : es; /* wider blocks fail their subblock with PHY_ERR_UNSUPPORTED */
   }
+  /* Single-walk encoder (phy_encode.cuh): G lanes share a record's quality / DNA codes so that a lane's run of read
+   * positions stays short (its staging words and the records a warp keeps staged shrink with G); PHY_ENC=0 switches
+   * the single-walk kernels off (every subblock then takes k_lengths + k_emit). */
+  static const int enc_env = getenv("PHY_ENC") ? atoi(getenv("PHY_ENC")) : 1;
+  static const int encg_env = getenv("PHY_ENC_G") ? atoi(getenv("PHY_ENC_G")) : 0;
+  static const int qdbuf_env = getenv("PHY_QD_NBUF") ? atoi(getenv("PHY_QD_NBUF")) : 0;
+  u32 encG = H.max_len <= 64 ? 1u : H.max_len <= 192 ? 4u : 8u;
+  if (encg_env == 1 || encg_env == 2 || encg_env == 4 || encg_env == 8) encG = (u32)encg_env;
+  d.fg.g = enc_env ? encG : 0u;
+  d.fg.lpw_q = (seg_len(H.max_len, encG) * 12u + 31u) / 32u + 2u; /* packed codes are at most 12 bits long */
+  d.fg.pk_bytes = 0;
+  d.qd_stage = ((32u / encG) * H.max_rec + 32u + 255u) & ~255u;
+  if (encG == 1) d.qd_stage = (H.max_span32 + 16 + 255) & ~255u;
+  d.qd_nbuf = qdbuf_env == 1 || qdbuf_env == 2 ? (u32)qdbuf_env : (encG == 1 ? 1u : 2u);
+  d.ts = (((H.max_tlen + 16u + 15u) & ~15u) | 16u);
+  const u32 max_tasks = (H.max_chunks * CH + TASK_RECORDS - 1) / TASK_RECORDS;
   /* Subblock groups: the subblocks of the batch are split into G consecutive groups that run the rest of the pipeline on
    * their own streams.  Several of its stages are latency-bound (one warp per subblock in k_classify, one warp per table
    * in k_huff, one CTA per subblock in k_layout): while one group sits in such a stage the other keeps the SMs busy.
@@ -371,7 +400,25 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     else { CK(cudaEventSynchronize(ctx->ev_rb[g])); pk = (ctx->h_hdr_g[g].max_pk_bytes + 15u) & ~15u; }
     e.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
     k_huff<<<dim3(16, Sg), 128, 4 * sizeof(HuffScratch), gs>>>(e); GMARK();
-    /* one warp per 32-record block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
+    /* single-walk encoder: slots, then title + info and quality + DNA of every task into the temporary buffer */
+    e.fg.pk_bytes = e.pk_bytes;
+    const u32 title_dyn = ENC_WARPS * (2u * 32u * e.ts + (32u * LPW_T + CCW + 32u) * 4u);
+    const u32 qd_dyn = e.fg.pk_bytes + ENC_WARPS * (e.qd_nbuf * e.qd_stage + (32u * e.fg.lpw_q + 2u * CCW) * 4u);
+    if (e.fg.g && (title_dyn > ENC_DYN_MAX || qd_dyn > ENC_DYN_MAX || e.fg.pk_bytes == 0)) e.fg.g = 0; /* does not fit: two-walk kernels */
+    k_slots<<<Sg, 32, 0, gs>>>(e); GMARK();
+    const dim3 g_enc((max_tasks + ENC_WARPS - 1) / ENC_WARPS, Sg);
+    if (e.fg.g) k_enc_title<<<g_enc, ENC_WARPS * 32, title_dyn, gs>>>(e);
+    GMARK();
+    switch (e.fg.g) {
+      case 1: k_enc_qd<1><<<g_enc, ENC_WARPS * 32, qd_dyn, gs>>>(e); break;
+      case 2: k_enc_qd<2><<<g_enc, ENC_WARPS * 32, qd_dyn, gs>>>(e); break;
+      case 4: k_enc_qd<4><<<g_enc, ENC_WARPS * 32, qd_dyn, gs>>>(e); break;
+      case 8: k_enc_qd<8><<<g_enc, ENC_WARPS * 32, qd_dyn, gs>>>(e); break;
+      default: break;
+    }
+    GMARK();
+    /* two-walk kernels for the subblocks the single-walk kernels could not take (bounds beyond their staging): one warp
+     * per 32-record block while at least ~32 warps of such CTAs fit an SM, else warp pairs on a shared stage */
     const u32 solo_dyn = e.pk_bytes + EW * e.enc_stage, pair_dyn = e.pk_bytes + EP * e.enc_stage;
     const bool pair = pair_env >= 0 ? pair_env != 0 : (solo_dyn + 7 * 1024) * 4 > 227u * 1024;
     const dim3 ge_solo((4 * H.max_chunks + EW * EGW - 1) / (EW * EGW), Sg), ge_pair((4 * H.max_chunks + EP * EGW - 1) / (EP * EGW), Sg);
@@ -383,10 +430,12 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     k_outscan<<<1, 256, 0, gs>>>(e); GMARK();
     if (G > 1) CK(cudaEventRecord(ctx->ev_scan[g], gs));
     k_zero_out<<<148 * 4, 256, 0, gs>>>(e); GMARK();
+    if (e.fg.g) k_place<<<dim3(32, Sg), 256, 0, gs>>>(e);
+    GMARK();
     if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
     else k_emit<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
     GMARK();
-    ctx->launches += 12;
+    ctx->launches += e.fg.g ? 16 : 13;
     CK(cudaMemcpyAsync(ctx->h_sbout + s0[g], e.sbout, sizeof(SbOut) * Sg, cudaMemcpyDeviceToHost, gs));
     CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* max_pk_bytes: the next batch's hint */
     if (g == G - 1) CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* total_out = the end of the last group */

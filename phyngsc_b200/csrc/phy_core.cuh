@@ -216,7 +216,7 @@ struct FieldClass {
   u8 sep, kind, is_delta, has_table, is_len_const, pad[3];
   u32 mism[MASKW];
 };
-struct TableDesc { u32 n, freq_off, cl_off, tree_off, tree_len, dst; };
+struct TableDesc { u32 n, freq_off, cl_off, tree_off, tree_len, dst, maxlen; }; /* maxlen: longest code of the built table */
 
 struct SbClass {
   i32 status; u32 R, nf, P, nnc;
@@ -239,6 +239,12 @@ struct SbClass {
   u32 info_len, thdr_len, title_len, qhdr_len, qual_len, dhdr_len, dna_len, payload_len;
   u64 qbits_total, dbits_total;
   u64 out_off;
+  /* single-walk encoder (phy_fast.cuh): tasks of 256 records with slots in the temporary buffer */
+  u64 tmp_base;                /* first word of this subblock's region of the temporary buffer                */
+  u32 fast;                    /* 1: encoded by the single-walk kernels, 0: by the two-walk kernels           */
+  u32 ntask, task_off;         /* arena: [3][ntask] quality bits / DNA bits / title bytes per task, then [3][ntask] their exclusive scans */
+  u32 strd_q, strd_d, strd_t;  /* slot sizes in words                                                         */
+  u32 info_words, pad_fast;
   u8 symbols[256], quals[256], sym_code[256], qua_code[256];
   u8 ncf[MAXF];                /* the nnc non-constant fields in title order ...                              */
   u16 ncskip[MAXF];            /* ... and the bytes of constant tokens (with their separators) in front of each */
@@ -474,6 +480,9 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   C.flagbits_off = al.take(C.nblk);
   C.nchunk = (R + CHUNK_RECORDS - 1) / CHUNK_RECORDS;
   C.blk3_off = al.take(3 * C.nblk);
+  C.ntask = (R + 255) / 256;
+  C.task_off = al.take(6 * C.ntask);
+  C.fast = 0; C.tmp_base = 0; C.strd_q = C.strd_d = C.strd_t = C.info_words = 0; C.pad_fast = 0;
   if (al.used & 1) al.take(1); /* 8-byte alignment for the code tables */
   u32 cl_off = al.used;
   u64 cl_words = 2ull * ((u64)(C.max_qlen + 1) * nq + (C.plain ? 0 : nsym) + (u64)ntab_chr * 256);
@@ -516,7 +525,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
   C.tq0 = 0;
   for (u32 p = 0; p <= C.max_qlen; ++p, ++tid) {
     td[tid].n = nq; td[tid].freq_off = C.qstat_off + p * nq; td[tid].cl_off = cl_off; td[tid].tree_off = tree_off;
-    td[tid].tree_len = 0; td[tid].dst = 0;
+    td[tid].tree_len = 0; td[tid].dst = 0; td[tid].maxlen = 0;
     cl_off += 2 * nq; tree_off += tcap_q;
   }
   C.tdna = NOTAB;
@@ -524,7 +533,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
     /* sym_stats (tasks.cpp:233-236) are counted into arena[dnastat_off + sym_code] after the zeroing pass */
     C.tdna = tid;
     td[tid].n = nsym; td[tid].freq_off = dnastat_off; td[tid].cl_off = cl_off; td[tid].tree_off = tree_off;
-    td[tid].tree_len = 0; td[tid].dst = 0;
+    td[tid].tree_len = 0; td[tid].dst = 0; td[tid].maxlen = 0;
     cl_off += 2 * nsym; tree_off += align_up(tree_blob_cap(nsym), 4) / 4; ++tid;
   }
   for (u32 f = 0; f < nf; ++f) {
@@ -532,7 +541,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
     if (F.kind == K_NUM && F.has_table) {
       F.tab = tid; F.cl_off = cl_off; F.freq_off = numhist_off[f];
       td[tid].n = F.diff; td[tid].freq_off = numhist_off[f]; td[tid].cl_off = cl_off; td[tid].tree_off = tree_off;
-      td[tid].tree_len = 0; td[tid].dst = 0;
+      td[tid].tree_len = 0; td[tid].dst = 0; td[tid].maxlen = 0;
       cl_off += 2 * F.diff; tree_off += align_up(tree_blob_cap(F.diff), 4) / 4; ++tid;
     }
   }
@@ -549,7 +558,7 @@ PHY_HDN void classify_subblock(const u8 *b, const u8 *lut, const SbAcc &A, u32 R
       if (!need) { sm[j] = (u16)NOTAB; continue; }
       sm[j] = (u16)tid;
       td[tid].n = 256; td[tid].freq_off = chrhist_off + slot * 256; td[tid].cl_off = cl_off; td[tid].tree_off = tree_off;
-      td[tid].tree_len = 0; td[tid].dst = 0;
+      td[tid].tree_len = 0; td[tid].dst = 0; td[tid].maxlen = 0;
       cl_off += 512; tree_off += tcap_c; ++tid; ++slot;
     }
   }

@@ -30,6 +30,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "phy_core.cuh"
+#include "phy_fast.cuh"
 
 namespace phy {
 
@@ -64,6 +65,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
   u32 max_len;         /* longest sequence line of the batch's subblocks */
   u32 max_span64, max_span32; /* widest 64- / 32-record span (k_qhist may stage smaller groups than the 128-record chunk) */
+  u32 max_rec, max_tlen;      /* longest record and longest title line (both with their newline) */
 };
 
 struct SbOut {         /* device -> host, one per subblock */
@@ -93,6 +95,12 @@ struct Dev {
   u32 qh_rows;                /* rows of a k_qhist CTA's private table */
   u32 enc_stage;              /* bytes of one warp's stage buffer in the encoder kernels (a 32-record block) */
   u32 qh_recs, qh_stage;      /* records per pipeline stage of k_qhist (128, 64 or 32) and the bytes of a stage buffer */
+  /* single-walk encoder (phy_encode.cuh) */
+  u32 *tmp; u64 tmp_cap;      /* temporary buffer of the tasks' runs (words) */
+  u64 *tmp_used;              /* words handed out so far in this batch */
+  FastGeom fg;
+  u32 ts;                     /* bytes of one lane's title slot in k_enc_title (a multiple of 16) */
+  u32 qd_nbuf, qd_stage;      /* stage buffers per warp of k_enc_qd and their size */
 };
 
 /* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0; d.hdr->max_rec = 0; d.hdr->max_tlen = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -363,9 +371,14 @@ __global__ void __launch_bounds__(256) k_spanmax(Dev d) {
     if ((g & 1u) == 0) m64 = max(m64, d.rstart[P.first_rec + min(i + 64, n)] - lo);
     if ((g & 3u) == 0) mx = max(mx, d.rstart[P.first_rec + min(i + CH, n)] - lo);
   }
-  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) ml = max(ml, d.se[P.first_rec + i] - d.te[P.first_rec + i] - 1);
+  u32 mr = 0, mt = 0;
+  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < P.n_records; i += gridDim.x * 256) {
+    const u32 r = P.first_rec + i, rs = d.rstart[r], te = d.te[r];
+    ml = max(ml, d.se[r] - te - 1); mr = max(mr, d.rstart[r + 1] - rs); mt = max(mt, te + 1 - rs);
+  }
   mx = __reduce_max_sync(0xFFFFFFFFu, mx); m64 = __reduce_max_sync(0xFFFFFFFFu, m64); m32 = __reduce_max_sync(0xFFFFFFFFu, m32);
-  ml = __reduce_max_sync(0xFFFFFFFFu, ml);
+  ml = __reduce_max_sync(0xFFFFFFFFu, ml); mr = __reduce_max_sync(0xFFFFFFFFu, mr); mt = __reduce_max_sync(0xFFFFFFFFu, mt);
+  if ((threadIdx.x & 31) == 0 && mr) { atomicMax(&d.hdr->max_rec, mr); atomicMax(&d.hdr->max_tlen, mt); }
   if ((threadIdx.x & 31) == 0 && mx) atomicMax(&d.hdr->max_span, mx);
   if ((threadIdx.x & 31) == 0 && m64) atomicMax(&d.hdr->max_span64, m64);
   if ((threadIdx.x & 31) == 0 && m32) atomicMax(&d.hdr->max_span32, m32);
@@ -1140,6 +1153,13 @@ __global__ void __launch_bounds__(128) k_huff(Dev d) {
     u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS[w], lane, 32u, WarpSync());
     if (lane == 0) td[t].tree_len = blob;
     __syncwarp();
+    { /* longest code: bounds the staging of the single-walk encoder (phy_fast.cuh) */
+      const u64 *cl = (const u64 *)(arena + D.cl_off);
+      u32 ml = 0;
+      for (u32 i = lane; i < D.n && blob; i += 32) ml = max(ml, (u32)(cl[i] >> 32));
+      ml = __reduce_max_sync(0xFFFFFFFFu, ml);
+      if (lane == 0) td[t].maxlen = ml;
+    }
     if (t - C.tq0 <= C.max_qlen) { /* quality table: 16-bit copy (len << 12 | code, PK_ESC for the rare codes beyond 12 bits) for the shared-memory walkers */
       u16 *pk = (u16 *)(arena + C.qpk_off) + (size_t)(t - C.tq0) * D.n;
       const u64 *cl = (const u64 *)(arena + D.cl_off);
@@ -1182,13 +1202,14 @@ template <class Sink> __device__ __forceinline__ void put_pk_esc(Sink &s, u32 e,
 }
 /* ESC: the subblock has packed entries with the escape (a code longer than 12 bits somewhere); compiled separately so
  * that the common case carries neither the test nor its registers */
+/* qp / sp point at read position pos0 (0 unless several lanes share a record); L symbols are coded from there */
 template <bool ESC, class Sink>
-__device__ __forceinline__ void quality_walk_pk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
+__device__ __forceinline__ void quality_walk_pk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s, u32 pos0 = 0) {
   const bool wx = __any_sync(__activemask(), xfer);
   const u32 xm = xfer ? 0xFFu : 0u;
   const u32 nq = T.nq;
-  const u16 *row = T.pk + nq;
-  const u64 *frow = T.qcl + nq; /* the same position in the 64-bit tables */
+  const u16 *row = T.pk + (size_t)(pos0 + 1) * nq;
+  const u64 *frow = T.qcl + (size_t)(pos0 + 1) * nq; /* the same position in the 64-bit tables */
   u32 j = 0;
 #define PHY_Q4_BODY                                                                                                          \
   const u32 c0 = T.qmap[q0], c1 = T.qmap[q1], c2 = T.qmap[q2], c3 = T.qmap[q3];                                            \
@@ -1218,15 +1239,15 @@ __device__ __forceinline__ void quality_walk_pk(const u8 *qp, const u8 *sp, u32 
   }
 }
 template <class Sink>
-__device__ __forceinline__ void quality_walk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
+__device__ __forceinline__ void quality_walk(const u8 *qp, const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s, u32 pos0 = 0) {
   if (T.pk) {
-    if (T.has_esc) quality_walk_pk<true>(qp, sp, L, xfer, T, s);
-    else quality_walk_pk<false>(qp, sp, L, xfer, T, s);
+    if (T.has_esc) quality_walk_pk<true>(qp, sp, L, xfer, T, s, pos0);
+    else quality_walk_pk<false>(qp, sp, L, xfer, T, s, pos0);
     return;
   }
   const u32 xm = xfer ? 0xFFu : 0u;
   const u32 nq = T.nq;
-  const u64 *row = T.qcl + nq;
+  const u64 *row = T.qcl + (size_t)(pos0 + 1) * nq;
   for (u32 j = 0; j < L; ++j, row += nq) {
     const u64 e = row[T.qmap[qp[j] + (T.xq[sp[j]] & xm)]];
     s.put((u32)e, (u32)(e >> 32));
@@ -1336,7 +1357,7 @@ __global__ void __launch_bounds__(EW * 32) k_lengths(Dev d) {
   const u32 role = PAIR ? (threadIdx.x >> 5) & 1u : 0u;
   const bool do_q = !PAIR || role == 0, do_d = !PAIR || role == 1;
   SbClass &C = d.cls[s];
-  if (C.status) return;
+  if (C.status || C.fast) return; /* fast: the single-walk kernels (phy_encode.cuh) encode this subblock */
   const u32 nblk = C.nblk;
   if (blockIdx.x * (NST * EGW) >= nblk) return;
   const u32 g0 = min((blockIdx.x * NST + w) * EGW, nblk), g1 = min(g0 + EGW, nblk);
@@ -1473,9 +1494,20 @@ __global__ void __launch_bounds__(256) k_layout(Dev d) {
       for (u32 i = tid & 31; i < tlen[t]; i += 32) dst[i] = src[i];
     }
   }
-  u64 qb = cta_scan_inplace(arena + C.blk3_off, C.nblk, ws, &ovf);
-  u64 db = cta_scan_inplace(arena + C.blk3_off + C.nblk, C.nblk, ws, &ovf);
-  u64 tb = C.nnc ? cta_scan_inplace(arena + C.blk3_off + 2 * C.nblk, C.nblk, ws, &ovf) : 0;
+  u64 qb, db, tb;
+  if (C.fast) { /* single-walk encoder: one total per task of 256 records; the scans go behind the totals */
+    const u32 nt = C.ntask;
+    u32 *len3 = arena + C.task_off, *base3 = len3 + 3 * nt;
+    for (u32 i = tid; i < 3 * nt; i += 256) base3[i] = len3[i];
+    __syncthreads();
+    qb = cta_scan_inplace(base3, nt, ws, &ovf);
+    db = cta_scan_inplace(base3 + nt, nt, ws, &ovf);
+    tb = cta_scan_inplace(base3 + 2 * nt, nt, ws, &ovf);
+  } else {
+    qb = cta_scan_inplace(arena + C.blk3_off, C.nblk, ws, &ovf);
+    db = cta_scan_inplace(arena + C.blk3_off + C.nblk, C.nblk, ws, &ovf);
+    tb = C.nnc ? cta_scan_inplace(arena + C.blk3_off + 2 * C.nblk, C.nblk, ws, &ovf) : 0;
+  }
   __syncthreads();
   if (tid == 0) {
     if (ovf || tb > 0x7FFFFFFFull) { C.status = E_CAPACITY; return; }
@@ -1544,7 +1576,7 @@ __global__ void __launch_bounds__(EW * 32, PAIR ? 5 : 4) k_emit(Dev d) {
   const u32 role = PAIR ? (threadIdx.x >> 5) & 1u : 0u;
   const bool do_q = !PAIR || role == 0, do_d = !PAIR || role == 1;
   const SbClass &C = d.cls[s];
-  if (C.status) return;
+  if (C.status || C.fast) return;
   const u32 nblk = C.nblk;
   if (blockIdx.x * (NST * EGW) >= nblk) return;
   const u32 g0 = min((blockIdx.x * NST + w) * EGW, nblk), g1 = min(g0 + EGW, nblk);

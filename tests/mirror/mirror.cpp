@@ -8,13 +8,164 @@
 #include <vector>
 
 #include "../../phyngsc_b200/csrc/phy_core.cuh"
+#include "../../phyngsc_b200/csrc/phy_fast.cuh"
 
 using namespace phy;
 
 static void amax(u32 &a, u32 v) { if (v > a) a = v; }
 
-extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 rec_start, i32 overlap, u32 cap,
-                                      u8 *out, u32 out_cap, u32 *sec_len, u32 *n_records, u64 *bytes_consumed) {
+
+// ---- single-walk encoder, emulated serially (one "warp" = 32 lanes run one after the other) ------------------------
+struct HostStream {
+  StreamState st; std::vector<u32> cc; u32 *slot; u32 slot_words; bool over;
+  void init(u32 *slot_, u32 words) { st.init(); cc.assign(4096, 0); slot = slot_; slot_words = words; over = false; }
+  void flush(u32 bits) {
+    u32 nf = st.full_words(bits);
+    if (st.tpos + nf + 1 > slot_words) over = true; else for (u32 j = 0; j < nf; ++j) slot[st.tpos + j] = cc[j];
+    u32 rem = cc[nf];
+    for (u32 j = 0; j <= nf; ++j) cc[j] = 0;
+    cc[0] = rem;
+    st.advance(bits);
+  }
+  // pieces of the 32 lanes: lp[lane * lpw ...], nbits[lane]
+  void append(const u32 *lp, u32 lpw, const u32 *nbits) {
+    u32 excl = 0;
+    for (u32 l = 0; l < 32; ++l) { if (nbits[l]) lane_concat(cc.data(), st.carry + excl, lp + l * lpw, 1u, nbits[l]); excl += nbits[l]; }
+    flush(excl);
+  }
+  void pad_to_byte() { u32 p = st.pad_to_byte(); if (p) flush(p); }
+  u32 finish() { if (st.carry && st.tpos < slot_words) slot[st.tpos] = cc[0]; return st.total; }
+};
+
+static int fast_encode(const u8 *b, const u8 *lut, const std::vector<u32> &te, const std::vector<u32> &se, const std::vector<u32> &rstart,
+                       const std::vector<u16> &kx, const std::vector<u32> &vals, u32 nf, u32 *arena, u32 AW, SbClass *C, u32 G, u8 *out, u32 out_cap) {
+  (void)AW;
+  const u32 R = C->R;
+  TableDesc *td = (TableDesc *)(arena + C->tabdesc_off);
+  // k_slots
+  u32 qsum = 0, qmax = 0;
+  for (u32 p = 1; p <= C->max_qlen; ++p) { qsum += td[C->tq0 + p].maxlen; if (td[C->tq0 + p].maxlen > qmax) qmax = td[C->tq0 + p].maxlen; }
+  const u32 tb = title_bound_part(*C, arena, td, 0u, 1u);
+  const u32 seg_max = seg_len(C->max_qlen, G), dper = C->plain ? 2u : td[C->tdna].maxlen;
+  const u32 lpw_q = (seg_max * (qmax > dper ? qmax : dper) + 31) / 32 + 2;
+  if (C->nnc + tb > 32u * (LPW_T - 1)) return 1000; // the GPU would take the two-walk kernels
+  C->strd_q = (u32)((u64)TASK_RECORDS * qsum / 32) + 3; C->strd_d = (u32)((u64)TASK_RECORDS * C->max_qlen * dper / 32) + 3;
+  C->strd_t = (u32)((u64)TASK_BLOCKS * ((C->nnc + 32ull * tb + 7) / 8 * 8) / 32) + 3;
+  C->info_words = (u32)(((u64)R * C->nb_len + 31) / 32) + 1;
+  const u32 strd = C->strd_q + C->strd_d + C->strd_t;
+  std::vector<u32> tmp((size_t)C->info_words + (size_t)C->ntask * strd, 0xDEADBEEFu); // stale contents must not matter
+  u32 *len3 = arena + C->task_off, *base3 = len3 + 3 * C->ntask;
+  auto prev_of = [&](u32 r) { return [&, r](u32 f, i32) { return r ? (i32)vals[(size_t)(r - 1) * nf + f] : 0; }; };
+  bool over = false;
+  std::vector<u32> lp(32 * (lpw_q > LPW_T ? lpw_q : LPW_T));
+  for (u32 task = 0; task < C->ntask; ++task) {
+    u32 *slot = tmp.data() + C->info_words + (size_t)task * strd;
+    // k_enc_title
+    HostStream T; T.init(slot + C->strd_q + C->strd_d, C->strd_t);
+    for (u32 g = task * TASK_BLOCKS; g < (task + 1) * TASK_BLOCKS && g < C->nblk; ++g) {
+      u32 lo = g * 32, nrec = R - lo < 32 ? R - lo : 32, flags = arena[C->flagbits_off + g];
+      u32 ci[32] = {0};
+      for (u32 l = 0; l < nrec && C->nb_len; ++l) {
+        u32 L = se[lo + l] - te[lo + l] - 1, pos = l * C->nb_len, sh = pos & 31, v = L << (32 - C->nb_len);
+        cc_or(ci, pos >> 5, v >> sh);
+        if (sh + C->nb_len > 32) cc_or(ci, (pos >> 5) + 1, v << (32 - sh));
+      }
+      for (u32 l = 0; l < (nrec * C->nb_len + 31) / 32; ++l) tmp[g * C->nb_len + l] = ci[l];
+      if (!C->nnc) continue;
+      u32 nb[32];
+      for (u32 l = 0; l < 32; ++l) {
+        nb[l] = 0;
+        if (l >= nrec) continue;
+        LaneSinkT<PtrStore> sk; sk.init(PtrStore{lp.data() + l * LPW_T, 1u}, LPW_T);
+        if (l == 0) { u32 v = 0; for (u32 k = 0; k < C->nnc; ++k) v = (v << 1) | ((flags >> C->ncf[k]) & 1u); sk.put(v, C->nnc); }
+        title_record(b, lut, rstart[lo + l], te[lo + l], *C, C->f, C->ncf, C->ncskip, arena, flags, l == 0, prev_of(lo + l), sk);
+        nb[l] = sk.finish(); over = over || sk.over;
+      }
+      T.append(lp.data(), LPW_T, nb);
+      T.pad_to_byte();
+    }
+    len3[2 * C->ntask + task] = T.finish() >> 3; over = over || T.over;
+    // k_enc_qd<G>
+    HostStream Q, D; Q.init(slot, C->strd_q); D.init(slot + C->strd_q, C->strd_d);
+    const u32 RW = 32 / G, rec0 = task * TASK_RECORDS, rec1 = rec0 + TASK_RECORDS < R ? rec0 + TASK_RECORDS : R;
+    const u64 *qcl = (const u64 *)(arena + td[C->tq0].cl_off);
+    const u64 *dcl = C->plain ? (const u64 *)0 : (const u64 *)(arena + td[C->tdna].cl_off);
+    for (u32 i0 = rec0; i0 < rec1; i0 += RW) {
+      u32 qn[32], dn[32];
+      std::vector<u32> lpd(32 * lpw_q);
+      for (u32 l = 0; l < 32; ++l) {
+        qn[l] = dn[l] = 0;
+        u32 i = i0 + l / G, part = l % G;
+        if (i >= rec1) continue;
+        u32 L = se[i] - te[i] - 1, seg = seg_len(L, G), a = part * seg < L ? part * seg : L, e = a + seg < L ? a + seg : L;
+        bool xf = kx[i] >> 15;
+        const u8 *sp = b + te[i] + 1, *qp = b + se[i] + 3;
+        LaneSinkT<PtrStore> sq; sq.init(PtrStore{lp.data() + l * lpw_q, 1u}, lpw_q);
+        for (u32 j = a; j < e; ++j) {
+          u8 q = qp[j];
+          if (xf) { u32 am = amb_code(sp[j]); if (am > 1) q = xfer_qual(am, q); }
+          u64 en = qcl[(size_t)(j + 1) * C->nq + C->qua_code[q]];
+          sq.put((u32)en, (u32)(en >> 32));
+        }
+        qn[l] = sq.finish(); over = over || sq.over;
+        LaneSinkT<PtrStore> sd; sd.init(PtrStore{lpd.data() + l * lpw_q, 1u}, lpw_q);
+        for (u32 j = a; j < e; ++j) {
+          u8 c = sp[j];
+          if (xf && !is_acgt(c)) continue;
+          if (C->plain) sd.put(C->sym_code[c], 2); else { u64 en = dcl[C->sym_code[c]]; sd.put((u32)en, (u32)(en >> 32)); }
+        }
+        dn[l] = sd.finish(); over = over || sd.over;
+      }
+      Q.append(lp.data(), lpw_q, qn);
+      D.append(lpd.data(), lpw_q, dn);
+    }
+    len3[task] = Q.finish(); len3[C->ntask + task] = D.finish(); over = over || Q.over || D.over;
+  }
+  if (over) return E_CAPACITY;
+  // k_layout
+  std::vector<u32> tlen(C->ntab), tdst(C->ntab);
+  for (u32 i = 0; i < C->ntab; ++i) tlen[i] = td[i].tree_len;
+  if (!layout_headers(b, *C, arena, tlen.data(), tdst.data())) return E_UNSUPPORTED;
+  u8 *stage = (u8 *)(arena + C->stage_off);
+  for (u32 i = 0; i < C->ntab; ++i) memcpy(stage + tdst[i], (u8 *)(arena + td[i].tree_off), td[i].tree_len);
+  u64 tot[3] = {0, 0, 0};
+  for (u32 k = 0; k < 3; ++k) for (u32 t = 0; t < C->ntask; ++t) { base3[k * C->ntask + t] = (u32)tot[k]; tot[k] += len3[k * C->ntask + t]; }
+  finish_layout(*C, (u32)tot[2], tot[0], tot[1]);
+  if (C->payload_len > out_cap) return E_CAPACITY;
+  // k_place
+  memset(out, 0, (C->payload_len + 7) & ~3u);
+  u32 *outw = (u32 *)out;
+  ByteWriter w; w.p = out; w.n = 0;
+  w.word(C->R); w.word(C->max_qlen); w.word(C->max_slen); w.byte((u8)C->nsym); w.byte(0); w.byte((u8)C->nq); w.word(C->flags);
+  const u32 o_title = C->info_len, o_qual = o_title + C->title_len, o_dna = o_qual + C->qual_len;
+  memcpy(out + o_title, stage, C->thdr_len);
+  memcpy(out + o_qual, stage + C->thdr_cap, C->qhdr_len);
+  memcpy(out + o_dna, stage + C->thdr_cap + C->qhdr_cap, C->dhdr_len);
+  auto place = [&](u64 dbit, const u32 *src, u32 nbits) {
+    if (!nbits) return;
+    u32 sh = (u32)(dbit & 31), nsrc = (nbits + 31) / 32, nd = (sh + nbits + 31) / 32;
+    for (u32 j = 0; j < nd; ++j) outw[(dbit >> 5) + j] |= bswap32(shifted_word(src, nsrc, sh, j));
+  };
+  const u64 info_bits = (u64)R * C->nb_len;
+  for (u64 b0 = 0; b0 < info_bits; b0 += 32ull * PIECE_WORDS)
+    place((u64)INFO_FIXED * 8 + b0, tmp.data() + b0 / 32, (u32)(info_bits - b0 < 32ull * PIECE_WORDS ? info_bits - b0 : 32ull * PIECE_WORDS));
+  const u64 bit0[3] = {(u64)(o_qual + C->qhdr_len) * 8, (u64)(o_dna + C->dhdr_len) * 8, (u64)(o_title + C->thdr_len) * 8};
+  for (u32 task = 0; task < C->ntask; ++task)
+    for (u32 k = 0; k < 3; ++k) {
+      u32 bits = len3[k * C->ntask + task] * (k == 2 ? 8u : 1u);
+      const u32 *src = tmp.data() + C->info_words + (size_t)task * strd + (k == 0 ? 0u : k == 1 ? C->strd_q : C->strd_q + C->strd_d);
+      u64 tbase = (u64)base3[k * C->ntask + task] * (k == 2 ? 8u : 1u);
+      for (u32 b0 = 0; b0 < bits; b0 += 32 * PIECE_WORDS)
+        place(bit0[k] + tbase + b0, src + b0 / 32, bits - b0 < 32 * PIECE_WORDS ? bits - b0 : 32 * PIECE_WORDS);
+    }
+  return 0;
+}
+
+// fastG = 0: the two-walk encoder (count, scan, write).  fastG = 1, 2, 4, 8: the single-walk encoder of phy_fast.cuh /
+// phy_encode.cuh emulated lane by lane -- lane-private sinks, warp concatenation with carry, task slots in a temporary
+// buffer, scans of the task totals, placement with shifted_word -- with fastG lanes per record for quality and DNA.
+static int mirror_window(const u8 *b, u64 readable, i64 rsize, u32 rec_start, i32 overlap, u32 cap,
+                         u8 *out, u32 out_cap, u32 *sec_len, u32 *n_records, u64 *bytes_consumed, u32 fastG) {
   // record split, serial (same rule as the plan kernel: phyNGSC.cpp:254-331)
   std::vector<u32> te, se, rstart;
   {
@@ -135,6 +286,20 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
     for (u32 i = 0; i < C->ntab; ++i)
       td[i].tree_len = huff_table(arena + td[i].freq_off, td[i].n, (u64 *)(arena + td[i].cl_off), (u8 *)(arena + td[i].tree_off), *HS, 0u, 1u, NoSync());
     delete HS;
+    for (u32 i = 0; i < C->ntab; ++i) {
+      u32 ml = 0;
+      for (u32 k = 0; k < td[i].n && td[i].tree_len; ++k) { u32 l = (u32)(((const u64 *)(arena + td[i].cl_off))[k] >> 32); if (l > ml) ml = l; }
+      td[i].maxlen = ml;
+    }
+    if (fastG) {
+      rc = fast_encode(b, lut, te, se, rstart, kx, vals, nf, arena, AW, C, fastG, out, out_cap);
+      if (!rc) {
+        sec_len[0] = C->info_len; sec_len[1] = C->title_len; sec_len[2] = C->qual_len; sec_len[3] = C->dna_len;
+        *n_records = R; *bytes_consumed = rstart[R];
+      }
+      free(A); free(arena); free(C);
+      return rc;
+    }
     // lengths
     auto prev_of = [&](u32 r) { return [&, r](u32 f, i32) { return r ? (i32)vals[(size_t)(r - 1) * nf + f] : 0; }; };
     for (u32 r = 0; r < R; ++r) {
@@ -209,6 +374,15 @@ extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 
   }
   free(A); free(arena); free(C);
   return rc;
+}
+
+extern "C" int mirror_compress_window(const u8 *b, u64 readable, i64 rsize, u32 rec_start, i32 overlap, u32 cap,
+                                      u8 *out, u32 out_cap, u32 *sec_len, u32 *n_records, u64 *bytes_consumed) {
+  return mirror_window(b, readable, rsize, rec_start, overlap, cap, out, out_cap, sec_len, n_records, bytes_consumed, 0);
+}
+extern "C" int mirror_compress_window_fast(const u8 *b, u64 readable, i64 rsize, u32 rec_start, i32 overlap, u32 cap,
+                                           u8 *out, u32 out_cap, u32 *sec_len, u32 *n_records, u64 *bytes_consumed, u32 lanes_per_record) {
+  return mirror_window(b, readable, rsize, rec_start, overlap, cap, out, out_cap, sec_len, n_records, bytes_consumed, lanes_per_record);
 }
 
 extern "C" u32 mirror_huffman(const u32 *freq, u32 n, u64 *cl, u8 *tree) {
