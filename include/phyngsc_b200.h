@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PHY_ABI_VERSION 1
+#define PHY_ABI_VERSION 2
 
 enum {
   PHY_OK = 0,
@@ -45,7 +45,12 @@ typedef struct {
   int32_t rank;           /* p_rank                                                         */
   uint64_t window_bytes;  /* READ_BUFFER_SIZE, 8 MiB in the reference (defs.h:20)           */
   uint32_t overlap;       /* 500 (phyNGSC.cpp:48)                                           */
-  uint32_t record_cap;    /* records_per_th at threads = 1: 100000 (phyNGSC.cpp:51,321)     */
+  uint32_t record_cap;    /* records a window can hold: 100000 (records_per_th x threads, phyNGSC.cpp:51,82,321) */
+  uint32_t threads;       /* the reference's third CLI argument (0 is read as 1).  It only moves where the stop rule
+                             of phyNGSC.cpp:315 starts to apply: threads before the last take every record whose title
+                             ends in their slice of the window (:261-266, :303), so windows shorter than
+                             threads x overlap keep more records than with one thread                         */
+  uint32_t reserved;      /* 0 */
 } phy_region_params;
 
 /* One subblock as the reference's loop body produces it. */

@@ -182,8 +182,17 @@ static int64_t find_nl(const uint8_t *b, int64_t from, int64_t limit) {
   return q ? (int64_t)(q - b) : -1;
 }
 
+/* no_threads of the reference (its third CLI argument).  Thread t owns the window bytes [t*size/T, (t+1)*size/T)
+ * (phyNGSC.cpp:261-266) and takes every record whose title newline lies there (:268, :303); only the LAST thread
+ * evaluates the stop rule (:315), and like every thread not before its own second record.  So with T > 1 every record
+ * whose title ends before (T-1)*size/T is taken unconditionally -- the same records as with one thread unless the window
+ * is shorter than about T x overlap (the small final window of a rank).  Per-thread record caps are not restated. */
+static int g_threads = 1;
+void phy_oracle_set_threads(int threads) { g_threads = threads < 1 ? 1 : threads; }
+
 static int split_records(const uint8_t *b, int64_t readable, int64_t size, int64_t rec_start, int64_t overlap,
                          uint32_t cap, rec_t **out, uint32_t *n_out, uint32_t *warn) {
+  const int64_t bT = (int64_t)(g_threads - 1) * size / g_threads; /* first byte of the last thread's slice */
   uint32_t n = 0, room = 1024;
   rec_t *r = (rec_t *)malloc(room * sizeof(rec_t));
   if (!r) return PHY_ORACLE_ENOMEM;
@@ -204,9 +213,11 @@ static int split_records(const uint8_t *b, int64_t readable, int64_t size, int64
       if (!nr) { free(r); return PHY_ORACLE_ENOMEM; }
       r = nr;
     }
+    const int64_t prev_t = (int64_t)r[n - 1].title_end;
     r[n].title_end = (uint32_t)t; r[n].seq_end = (uint32_t)s; ++n;
     i = s + (s - t) + 3;
-    if (i >= size - overlap) break;
+    const int in_last_slice = t >= bT, first_of_last_slice = g_threads > 1 && prev_t < bT;
+    if (in_last_slice && !first_of_last_slice && i >= size - overlap) break;
     if (n > cap) { *warn |= 1u; break; }
     ++i;
   }

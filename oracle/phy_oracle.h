@@ -45,6 +45,9 @@ typedef struct {
 uint32_t phy_oracle_huffman(const uint32_t *freq, uint32_t n, int compact, uint32_t *code, uint32_t *len,
                             uint8_t *tree_out, uint32_t tree_cap);
 
+/* no_threads of the reference for the calls that follow (default 1); see split_records in phy_oracle.c */
+void phy_oracle_set_threads(int threads);
+
 /* One subblock.  win[0..readable) must be addressable; r_buffer_size is the reference's window
  * size (drives the stop rule), readable >= r_buffer_size allows the read-slack semantics (Q4). */
 int phy_oracle_compress_window(const uint8_t *win, uint64_t readable, int64_t r_buffer_size, uint32_t rec_start,

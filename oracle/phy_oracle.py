@@ -107,13 +107,17 @@ class OracleError(Exception):
         self.rc = rc
 
 
-def compress_rank(file_bytes, np_ranks, rank, window_bytes=WINDOW_BYTES, block_bytes=BLOCK_BYTES, record_cap=RECORD_CAP):
+def compress_rank(file_bytes, np_ranks, rank, window_bytes=WINDOW_BYTES, block_bytes=BLOCK_BYTES, record_cap=RECORD_CAP, threads=1):
     """Everything one rank does.  -> dict(subblocks=[bytes], blocks=[bytes], records=[...], windows=[(off,len,rec_start,overlap)],
     last_block_size, wr_overlap, section_lens)."""
     a = np.frombuffer(file_bytes, dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else file_bytes
     a = np.ascontiguousarray(a)
     r = _Rank()
-    rc = lib().phy_oracle_compress_rank(a.ctypes.data, a.size, np_ranks, rank, window_bytes, block_bytes, record_cap, C.byref(r))
+    lib().phy_oracle_set_threads(int(threads))
+    try:
+        rc = lib().phy_oracle_compress_rank(a.ctypes.data, a.size, np_ranks, rank, window_bytes, block_bytes, record_cap, C.byref(r))
+    finally:
+        lib().phy_oracle_set_threads(1)
     if rc:
         raise OracleError(rc)
     ns, nb = r.n_subblocks, r.n_blocks

@@ -16,7 +16,7 @@ RECORD_CAP = 100000      # phyNGSC.cpp:51 at threads = 1
 
 class RegionParams(C.Structure):
     _fields_ = [("file_size", C.c_uint64), ("np", C.c_int32), ("rank", C.c_int32), ("window_bytes", C.c_uint64),
-                ("overlap", C.c_uint32), ("record_cap", C.c_uint32)]
+                ("overlap", C.c_uint32), ("record_cap", C.c_uint32), ("threads", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class SubblockDesc(C.Structure):
@@ -118,8 +118,8 @@ class _Pinned:
             self.ptr = None
 
 
-def region_params(file_size, np_ranks, rank, window_bytes=WINDOW_BYTES, overlap=OVERLAP, record_cap=RECORD_CAP):
-    return RegionParams(file_size, np_ranks, rank, window_bytes, overlap, record_cap)
+def region_params(file_size, np_ranks, rank, window_bytes=WINDOW_BYTES, overlap=OVERLAP, record_cap=RECORD_CAP, threads=1):
+    return RegionParams(file_size, np_ranks, rank, window_bytes, overlap, record_cap, threads, 0)
 
 
 def region_slice(file_size, np_ranks, rank, slack=0, overlap=OVERLAP):

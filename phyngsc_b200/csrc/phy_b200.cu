@@ -12,6 +12,7 @@
 #include "../../include/phyngsc_b200.h"
 #include "phy_kernels.cuh"
 #include "phy_encode.cuh"
+#include "phy_seqstat.cuh"
 
 using namespace phy;
 
@@ -19,6 +20,7 @@ using namespace phy;
 #define GROUPS_MAX 4
 
 static_assert(sizeof(phy_subblock_desc) == 72, "phy_subblock_desc layout is part of the ABI");
+static_assert(sizeof(phy_region_params) == 40, "phy_region_params layout is part of the ABI");
 
 struct phy_ctx {
   int device = 0;
@@ -72,7 +74,7 @@ static const u32 ENC_STAGE_MAX = 24 * 1024; /* a warp's stage in the encoder ker
 static const u32 ENC_DYN_MAX = 200 * 1024;  /* dynamic shared memory of the single-walk encoder kernels */
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */
 
-static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "qhist", "classify", "zero_hist",
+static const char *KERNEL_NAMES[NKERN] = {"nl_count", "nl_scan", "nl_emit", "plan", "plan_readback", "stat1", "seqstat", "classify", "zero_hist",
                                           "stat2", "huff", "slots", "enc_title", "enc_qd", "lengths", "layout", "outscan", "zero_out", "place", "emit"};
 
 extern "C" int phy_abi_version(void) { return PHY_ABI_VERSION; }
@@ -191,9 +193,13 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
     for (u32 c = 0; c < 256; ++c) { u32 a = amb_code((u8)c); lut[c] = a > 1 ? (u8)(79u + 8u * a) : (u8)0; }
     CK(cudaMemcpyToSymbol(g_xq_lut, lut, sizeof lut));
   }
-  CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPAN_MAX + MAXF * CH * 4)));
-  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SPAN_MAX + MAXF * CH * 4)));
-  CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QH_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_dnacount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_lengths<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_lengths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
@@ -290,31 +296,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
-  const u32 span_v = span + d.max_nf * CH * 4; /* + numeric values per field and record */
   /* launch geometry shared by all subblock groups of the batch */
-  u32 qh_dyn = 0;
-  static const int qh_nt_env = getenv("PHY_QH_NT") ? atoi(getenv("PHY_QH_NT")) : 0;
-  const u32 qh_threads = qh_nt_env ? (u32)qh_nt_env : (H.max_len > 192 ? 512u : 256u); /* very long reads (one record slot per 256 threads): a second slot on the same private table */
-  { /* k_qhist: private table of min(longest read, 256) rows beside two stage buffers.  Long records are staged in
-     * groups of 64 or 32 instead of 128 so that two CTAs still fit an SM (fewer, larger groups beat more CTAs: the
-     * per-group barriers and list building are what a CTA spends its time on besides counting). */
-    static const u32 budget = getenv("PHY_QH_KB") ? (u32)atoi(getenv("PHY_QH_KB")) * 1024u : 112u * 1024; /* two CTAs per SM */
-    d.qh_rows = H.max_len < 1 ? 1u : H.max_len > 256 ? 256u : H.max_len;
-    const u32 hb = (d.qh_rows * QR_ROWW * 4 + 15u) & ~15u;
-    const u32 spans[3] = {span, (H.max_span64 + 16 + 1023) & ~1023u, (H.max_span32 + 16 + 1023) & ~1023u};
-    int pick = 0;
-    while (pick < 2 && hb + 2 * spans[pick] > budget) ++pick;
-    d.qh_recs = 128u >> pick; d.qh_stage = spans[pick] > SPAN_MAX ? SPAN_MAX : spans[pick];
-    u32 nb = 2;
-    if (hb + nb * d.qh_stage > QH_DYN_MAX) nb = 1;
-    d.qh_nbuf = nb;
-    qh_dyn = hb + d.qh_nbuf * d.qh_stage;
-  }
-  {
-    static const int nbuf_env = getenv("PHY_S2_NBUF") ? atoi(getenv("PHY_S2_NBUF")) : 1;
-    d.s2_nbuf = (nbuf_env == 2 && 2 * span + d.max_nf * CH * 4 <= 200u * 1024) ? 2u : 1u;
-  }
-  const u32 s2_dyn = d.s2_nbuf * span + d.max_nf * CH * 4;
   {
     u32 es = (H.max_span32 + 16 + 255) & ~255u;
     d.enc_stage = es > ENC_STAGE_MAX ? ENC_STAGE_MAX : es; /* wider blocks fail their subblock with PHY_ERR_UNSUPPORTED */
@@ -335,6 +317,12 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.qd_nbuf = qdbuf_env == 1 || qdbuf_env == 2 ? (u32)qdbuf_env : (encG == 1 ? 1u : 2u);
   d.ts = (((H.max_tlen + 16u + 15u) & ~15u) | 16u);
   const u32 max_tasks = (H.max_chunks * CH + TASK_RECORDS - 1) / TASK_RECORDS;
+  /* statistics: k_seqstat uses the lane split and the record stages of k_enc_qd, k_stat1 / k_stat2 stage title lines only */
+  d.sq_rows = H.max_len < 1 ? 1u : H.max_len > RAW_ROWS - 1 ? RAW_ROWS - 1 : H.max_len;
+  d.sq_stage = d.qd_stage; d.sq_nbuf = 2;
+  const u32 sq_dyn = ((d.sq_rows * SQ_ROWW * 4u + 15u) & ~15u) + SQ_WARPS * d.sq_nbuf * d.sq_stage;
+  const u32 title_stat_dyn = 2u * CH * d.ts + d.max_nf * CH * 4u; /* two stages of title slots + numeric values per field and record */
+  if (sq_dyn > ENC_DYN_MAX || title_stat_dyn > ENC_DYN_MAX) { ctx->err = "records too long for the statistics kernels' shared memory"; return PHY_ERR_UNSUPPORTED; }
   /* Subblock groups: the subblocks of the batch are split into G consecutive groups that run the rest of the pipeline on
    * their own streams.  Several of its stages are latency-bound (one warp per subblock in k_classify, one warp per table
    * in k_huff, one CTA per subblock in k_layout): while one group sits in such a stage the other keeps the SMs busy.
@@ -372,9 +360,19 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     CK(cudaMemcpyAsync(ctx->hdr_g + g, ctx->h_hdr_g + g, sizeof(BatchHdr), cudaMemcpyHostToDevice, gs));
     CK(cudaMemsetAsync(e.acc, 0, sizeof(SbAcc) * Sg, gs));
     GMARK();
-    k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, Sg), CH, span_v, gs>>>(e);
+    k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, Sg), CH, title_stat_dyn, gs>>>(e);
     k_xdelta<<<Sg, 128, 0, gs>>>(e); GMARK();
-    k_qhist<<<dim3(H.max_qchunks, Sg), qh_threads, qh_dyn, gs>>>(e); GMARK();
+    k_zero_raw<<<dim3(4, Sg), 256, 0, gs>>>(e);
+    {
+      const dim3 g_sq((max_tasks + SQ_WARPS - 1) / SQ_WARPS, Sg);
+      switch (encG) {
+        case 1: k_seqstat<1><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
+        case 2: k_seqstat<2><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
+        case 4: k_seqstat<4><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
+        default: k_seqstat<8><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
+      }
+    }
+    GMARK();
     k_classify<<<Sg, 32, 0, gs>>>(e); GMARK();
     /* the group header now holds the exact size of the packed quality tables: the copy is ordered before the
      * statistics kernels that follow, so the host gets it while they keep the GPU busy (only waited for when the
@@ -382,7 +380,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs));
     CK(cudaEventRecord(ctx->ev_rb[g], gs));
     k_zero_hist<<<dim3(8, Sg), 256, 0, gs>>>(e); GMARK();
-    k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, s2_dyn, gs>>>(e); GMARK();
+    k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, title_stat_dyn, gs>>>(e);
+    k_dnacount<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, span, gs>>>(e); /* returns at once unless the DNA is Huffman coded */
+    GMARK();
   }
   static const int pair_env = getenv("PHY_EMIT_PAIR") ? atoi(getenv("PHY_EMIT_PAIR")) : -1;
   static const bool pk_exact = getenv("PHY_PK_EXACT") != nullptr;
@@ -435,7 +435,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
     if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
     else k_emit<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
     GMARK();
-    ctx->launches += e.fg.g ? 16 : 13;
+    ctx->launches += e.fg.g ? 19 : 16;
     CK(cudaMemcpyAsync(ctx->h_sbout + s0[g], e.sbout, sizeof(SbOut) * Sg, cudaMemcpyDeviceToHost, gs));
     CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* max_pk_bytes: the next batch's hint */
     if (g == G - 1) CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs)); /* total_out = the end of the last group */
@@ -475,7 +475,7 @@ static int init_plan(phy_ctx *ctx, const uint8_t *region_host, u64 region_len, c
       first = (u32)f;
     }
   }
-  plan_init(st, p->file_size, p->np, p->rank, p->window_bytes, p->overlap, p->record_cap, first);
+  plan_init(st, p->file_size, p->np, p->rank, p->window_bytes, p->overlap, p->record_cap, first, p->threads);
   if ((u64)st.wr_len > region_len) { ctx->err = "region_len is shorter than the rank's working region"; return PHY_ERR_ARG; }
   return PHY_OK;
 }

@@ -821,6 +821,7 @@ struct PlanState {
   i32 is_last;      /* last rank                                                           */
   u32 rec_start;    /* rec_start_pos of the next window (non-zero only for the very first) */
   u32 record_cap;
+  u32 threads;      /* no_threads of the reference: where in a window its stop rule starts to apply */
   i32 done, status;
   u32 n_subblocks_total;
 };
@@ -836,7 +837,7 @@ struct SbPlan {
   u32 pad;
 };
 
-PHY_HD void plan_init(PlanState &st, u64 file_size, i32 np, i32 rank, u64 window_bytes, u32 overlap, u32 record_cap, u32 first_rec_start) {
+PHY_HD void plan_init(PlanState &st, u64 file_size, i32 np, i32 rank, u64 window_bytes, u32 overlap, u32 record_cap, u32 first_rec_start, u32 threads = 1) {
   i64 region = (i64)(file_size / (u64)np);
   i64 wr_start = (i64)rank * region;
   i64 wr_end = (rank != np - 1) ? wr_start + region + (i64)overlap - 1 : (i64)file_size - 1;
@@ -844,7 +845,7 @@ PHY_HD void plan_init(PlanState &st, u64 file_size, i32 np, i32 rank, u64 window
   st.overlap = (i32)overlap; st.is_last = rank == np - 1;
   st.rsize = (i64)window_bytes;
   if (region < st.rsize) { st.rsize = wr_end - wr_start + 1; if (st.is_last) st.overlap = 0; } /* phyNGSC.cpp:119-124 */
-  st.bytes_read = 0; st.rec_start = first_rec_start; st.record_cap = record_cap;
+  st.bytes_read = 0; st.rec_start = first_rec_start; st.record_cap = record_cap; st.threads = threads ? threads : 1u;
   st.done = region <= 0; st.status = 0; st.n_subblocks_total = 0;
 }
 

@@ -123,10 +123,6 @@ __global__ void __launch_bounds__(32) k_slots(Dev d) {
 }
 
 /* ---- title + info -------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ void cp_async16(u32 dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 /* dynamic shared memory per warp: [2 title stages of 32 * ts bytes][32 * LPW_T staging words][CCW words][32 words for the info bits] */
 __device__ __forceinline__ u32 enc_title_warp_bytes(u32 ts) { return 2u * 32u * ts + (32u * LPW_T + CCW + 32u) * 4u; }
 
@@ -169,7 +165,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_title(Dev d) {
     const u32 r = P.first_rec + min(g0 * 32 + lane, R - 1);
     n_rs = d.rstart[r]; n_te = d.te[r]; n_se = d.se[r]; n_fl = nnc ? flag_p[g0] : 0u;
   }
-  bool fits = nnc ? stage_title(0, n_rs, n_te) : true;
+  bool fits = nnc ? stage_title(0, n_rs, n_te) : true; /* slots are sized for the longest title line of the batch: always true */
   cp_async_commit();
   for (u32 g = g0; g < g1; ++g) {
     const u32 nrec = min(32u, R - g * 32), buf = (g - g0) & 1u;
@@ -192,6 +188,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_title(Dev d) {
       __syncwarp();
       if (lane < (nrec * nb_len + 31) / 32) tmp[g * nb_len + lane] = ci[lane];
     }
+    if (!__all_sync(0xFFFFFFFFu, fits)) break; /* never walk a line that is not staged */
     if (nnc) {
       cp_async_wait<1>();
       __syncwarp();

@@ -101,6 +101,7 @@ struct Dev {
   FastGeom fg;
   u32 ts;                     /* bytes of one lane's title slot in k_enc_title (a multiple of 16) */
   u32 qd_nbuf, qd_stage;      /* stage buffers per warp of k_enc_qd and their size */
+  u32 sq_rows, sq_nbuf, sq_stage; /* k_seqstat: rows of the CTA's private quality table, stage buffers per warp and their size */
 };
 
 /* character classes of the title tokeniser (fill_char_lut), uploaded once per context */
@@ -277,11 +278,24 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     i64 target = ws + st.rsize - st.overlap, size_lim = ws + lim;
     u32 last = F, rs_next = 0xFFFFFFFFu; /* rs_next: rstart[last + 1] when the probe already holds it */
     bool capped = false;
+    const i64 guess = (i64)F + (i64)((float)(target - (ws + st.rec_start)) * dens); /* records per byte of the previous window; the probe absorbs the rounding */
+    /* With no_threads > 1 the reference's stop rule only runs in the last thread's slice of the window, from that
+     * slice's second record on (phyNGSC.cpp:261-266, 303, 315): every record whose title ends before the slice is taken,
+     * and Fs -- the first record whose title ends inside it -- plays the part record F plays with one thread. */
+    u32 Fs = F;
+    if (st.threads > 1) {
+      const i64 bT = ws + (i64)(st.threads - 1) * st.rsize / (i64)st.threads;
+      const u32 te_hi = (u32)min((u64)NR, ((u64)NL + 3) / 4); /* te[] is valid below this index */
+      if (F < te_hi && (i64)d.te[F] < bT) {
+        const i64 g2 = (i64)F + (i64)((float)(bT - (ws + st.rec_start)) * dens);
+        Fs = warp_lower_bound(d.te, F + 1, te_hi, bT, g2);
+        if (Fs >= te_hi || (i64)d.te[Fs] >= size_lim) Fs = Fs - 1; /* no title ends in the last slice: the earlier threads' records are all there is */
+      }
+    }
     /* One round trip in the common case: the title newline of the second record, and a 128-wide probe (four table
      * entries per lane) of the record table around the interpolated position of the last record, are loaded together. */
-    const i64 guess = (i64)F + (i64)((float)(target - (ws + st.rec_start)) * dens); /* records per byte of the previous window; the probe absorbs the rounding */
     u32 pbase;
-    { i64 gb = guess - 64; pbase = gb < (i64)F + 2 ? F + 2 : (u32)gb; pbase = (pbase + 3u) & ~3u; }
+    { i64 gb = guess - 64; pbase = gb < (i64)Fs + 2 ? Fs + 2 : (u32)gb; pbase = (pbase + 3u) & ~3u; }
     const u32 pidx = pbase + 4 * lane;
     /* the probe regions of the next two windows are predictable: bring them into L2 while this window is resolved */
 #pragma unroll
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(d.te + nidx));
       }
     }
-    const u32 te_f1 = 4ull * (F + 1) < NL ? d.te[F + 1] : 0xFFFFFFFFu;
+    const u32 te_f1 = 4ull * (Fs + 1) < NL ? d.te[Fs + 1] : 0xFFFFFFFFu;
     uint4 prs = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), pte = prs;
     if (pidx <= NR) { /* the tables have four entries of slack behind the last record */
       prs = *(const uint4 *)(d.rstart + pidx); pte = *(const uint4 *)(d.te + pidx);
@@ -300,6 +314,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
       if (pidx + 2 > NR) prs.z = 0xFFFFFFFFu;
       if (pidx + 3 > NR) prs.w = 0xFFFFFFFFu;
     }
+    last = Fs;
     if ((i64)te_f1 < size_lim) {
       u32 m;
       const u32 kl = (i64)prs.x >= target ? 0u : (i64)prs.y >= target ? 1u : (i64)prs.z >= target ? 2u : (i64)prs.w >= target ? 3u : 4u;
@@ -307,7 +322,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
       const u32 hl = bal ? __ffs(bal) - 1 : 0u;
       const u32 hk = __shfl_sync(0xFFFFFFFFu, kl, hl);
       const u32 cand = pbase + 4 * hl + hk;
-      const bool hit = bal != 0 && (cand > pbase || pbase == F + 2) && cand <= NR;
+      const bool hit = bal != 0 && (cand > pbase || pbase == Fs + 2) && cand <= NR;
       u32 te_last = 0xFFFFFFFFu;
       if (hit) {
         m = cand;
@@ -317,13 +332,13 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
           const u32 q = m - 1 - pbase, ql = q >> 2, qk = q & 3u;
           const u32 tsel = qk == 0 ? pte.x : qk == 1 ? pte.y : qk == 2 ? pte.z : pte.w;
           te_last = 4ull * (m - 1) < NL ? __shfl_sync(0xFFFFFFFFu, tsel, ql) : 0xFFFFFFFFu;
-        } else te_last = te_f1; /* m == F + 2 */
+        } else te_last = te_f1; /* m == Fs + 2 */
       }
-      else m = warp_lower_bound(d.rstart, F + 2, NR + 1, target, guess);
+      else m = warp_lower_bound(d.rstart, Fs + 2, NR + 1, target, guess);
       last = m - 1;
       if (last > F + st.record_cap) { last = F + st.record_cap; capped = true; te_last = 0xFFFFFFFFu; rs_next = 0xFFFFFFFFu; }
       if (te_last == 0xFFFFFFFFu && 4ull * last < NL) te_last = d.te[last];
-      while (last > F && !(4ull * last < NL && (i64)te_last < size_lim)) {
+      while (last > Fs && !(4ull * last < NL && (i64)te_last < size_lim)) {
         --last; capped = false; rs_next = 0xFFFFFFFFu;
         te_last = 4ull * last < NL ? d.te[last] : 0xFFFFFFFFu;
       }
@@ -457,9 +472,6 @@ __device__ __forceinline__ bool eq_bytes(const u8 *x, const u8 *y, u32 n) {
 struct Stat1S {
   u32 facc[MAXF][8];
   u32 mism[MAXF][MASKW];
-  u32 dna[256];
-  u32 qp[8];
-  u32 maxq, maxs, inv_minq;
   i32 err;
   u32 nf, ts0, te0;
   u32 off0[MAXF], len0[MAXF];
@@ -476,37 +488,43 @@ struct Stat1S {
 #endif
 constexpr int S1G = PHY_S1G; /* 128-record chunks per k_stat1 CTA */
 
-/* A CTA walks S1G consecutive chunks of one subblock (bulk-copy staging, ChunkStage); record 0 is tokenised and the
- * shared-memory accumulators are flushed to the subblock's once per CTA.
- * dynamic shared memory: [span_bytes stage buffer][nf x CH numeric values] */
+/* per-thread staging of title lines: 16-byte cp.async pieces from the aligned address below the line's first byte into the
+ * thread's slot (a stage holds one slot of `ts` bytes per thread) */
+__device__ __forceinline__ void cp_async16(u32 dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ bool stage_title_line(const u8 *in, u32 slot_a, u32 ts, u32 rs, u32 te) {
+  const u32 a0 = rs & ~15u, n = (te + 1 - a0 + 15u) >> 4;
+  if (n * 16u > ts) return false;
+  for (u32 k = 0; k < n; ++k) cp_async16(slot_a + 16 * k, in + a0 + 16 * k);
+  return true;
+}
+
+/* Title field reductions (tasks.cpp:22-223 as closed forms).  A CTA walks S1G consecutive 128-record chunks of one
+ * subblock, thread = record; only the title lines are staged (two stages of one slot per thread, the next chunk's lines
+ * arrive while the current chunk is walked).  Record 0 is tokenised and the shared-memory accumulators are flushed to the
+ * subblock's once per CTA.  The sequence / quality side of the statistics is k_seqstat (phy_seqstat.cuh).
+ * dynamic shared memory: [2 stages of CH slots of d.ts bytes][nf x CH numeric values] */
 __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ Stat1S S;
-  __shared__ __align__(8) u64 bar;
-  __shared__ u32 c_lo[S1G + 1];
-  __shared__ __align__(16) u8 lut[256], dlut[256];
+  __shared__ __align__(16) u8 lut[256];
   const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const SbPlan P = d.plans[s];
   const u32 R = P.n_records, nchunk = (R + CH - 1) / CH, c0 = blockIdx.x * S1G, c1 = min(c0 + S1G, nchunk);
   if (P.status || c0 >= nchunk) return;
   for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
   load_lut(lut);
-  for (u32 i = tid; i < 256; i += CH) dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'T' ? 4 : i == 'G' ? 8 : 0);
-  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * CH, R)];
   const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
-  ChunkStage stage; stage.init(dyn_smem, &bar);
-  u32 *vals = vals_area(dyn_smem, d.span_bytes); /* vals[f * CH + tid] */
+  const u32 tsz = d.ts;
+  const u8 *slots = (const u8 *)dyn_smem;
+  const u32 slots_a = (u32)__cvta_generic_to_shared(dyn_smem);
+  u32 *vals = (u32 *)((u8 *)dyn_smem + 2u * CH * tsz); /* vals[f * CH + tid] */
   /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
   const bool r0_ok = te0 - ts0 + 1 <= R0_MAX;
   if (r0_ok) for (u32 i = tid; i <= te0 - ts0; i += CH) S.r0[i] = d.in[ts0 + i];
   __syncthreads();
-  {
-    bool fits = true;
-    for (u32 k = 0; k < c1 - c0; ++k) fits = fits && c_lo[k + 1] - (c_lo[k] & ~15u) + 16 <= d.span_bytes;
-    if (!fits) { if (tid == 0) atomicMin(&d.acc[s].status, (i32)E_UNSUPPORTED); return; } /* records far beyond the reference's 500-byte domain */
-  }
   if (tid == 0) {
-    stage.request(d.in, c_lo[0], c_lo[1]);
     S.ts0 = ts0; S.te0 = te0;
     if (!r0_ok) S.err = E_UNSUPPORTED;
     else {
@@ -518,8 +536,10 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     }
   }
   /* this thread's record of the first chunk */
-  u32 n_ts = 0, n_te = 0, n_se = 0, n_nx = 0;
-  { const u32 i = c0 * CH + tid; if (i < R) { const u32 r = P.first_rec + i; n_ts = d.rstart[r]; n_te = d.te[r]; n_se = d.se[r]; n_nx = d.rstart[r + 1]; } }
+  u32 n_ts = 0, n_te = 0;
+  bool fits = true, n_fits = true; /* the slots are sized for the longest title line of the batch (BatchHdr::max_tlen): always true */
+  { const u32 i = c0 * CH + tid; if (i < R) { const u32 r = P.first_rec + i; n_ts = d.rstart[r]; n_te = d.te[r]; n_fits = stage_title_line(d.in, slots_a + tid * tsz, tsz, n_ts, n_te); } }
+  cp_async_commit();
   __syncthreads();
   const u32 nf = S.nf;
   const bool seed_ok = S.err == 0;
@@ -530,78 +550,19 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     atomicMax(&S.facc[tid][3], k0); atomicMax(&S.facc[tid][4], ~k0);
   }
   for (u32 c = c0; c < c1; ++c) {
-  const u32 nrec = min((u32)CH, R - c * CH);
+  const u32 nrec = min((u32)CH, R - c * CH), buf = (c - c0) & 1u;
   const bool active = tid < nrec;
-  const u32 r = P.first_rec + c * CH + (active ? tid : 0);
-  const u32 ts = n_ts, te = n_te, se = n_se, nx = n_nx;
-  { const u32 i = (c + 1) * CH + tid; if (c + 1 < c1 && i < R) { const u32 rn = P.first_rec + i; n_ts = d.rstart[rn]; n_te = d.te[rn]; n_se = d.se[rn]; n_nx = d.rstart[rn + 1]; } }
-  const u8 *b = stage.wait(c_lo[c - c0]);
-  const u32 L = se - te - 1, qs = se + 3;
+  const u32 ts = n_ts, te = n_te;
+  const bool cur_fits = n_fits;
+  fits = fits && cur_fits;
+  { /* next chunk's record: its title line starts to arrive now */
+    const u32 i = (c + 1) * CH + tid;
+    if (c + 1 < c1 && i < R) { const u32 rn = P.first_rec + i; n_ts = d.rstart[rn]; n_te = d.te[rn]; n_fits = stage_title_line(d.in, slots_a + ((buf ^ 1u) * CH + tid) * tsz, tsz, n_ts, n_te); }
+    cp_async_commit();
+  }
+  cp_async_wait<1>();
+  const u8 *b = slots + (size_t)(buf * CH + tid) * tsz - (ts & ~15u); /* b[pos] is valid for the positions of this thread's title line */
   i32 err = 0;
-  if (active) {
-    if (L == 0 || b[se + 1] != '+' || b[se + 2] != '\n' || nx != 2 * se - te + 3) err = E_MALFORMED;
-    else if (L > (u32)MAX_READ) err = E_UNSUPPORTED;
-    else if (r == P.first_rec) { /* colour space, phyNGSC.cpp:473-487: not implemented */
-      u8 c0b = b[te + 1], c1b = b[te + 2];
-      if ((c0b >= '0' && c0b <= '3') || (c1b >= '0' && c1b <= '3')) err = E_COLORSPACE;
-    }
-  }
-  /* sequence (phyNGSC.cpp:549-619).  Four bases per step: the 2-bit index (c >> 1) & 3 selects the byte the base
-   * must equal ("ACTG"[idx]) and a one-hot presence byte with two byte permutes, so a read of plain A/C/G/T costs
-   * about three instructions per base and its quality line is not touched at all -- the quality alphabet comes from
-   * k_qhist's raw histogram.  Only records that hold another byte walk their bases and qualities one by one.
-   * Only the PRESENCE of A/C/G/T is recorded here (that decides plain 2-bit coding); exact symbol counts are taken
-   * by k_stat2 in the rare Huffman-DNA case. */
-  u32 kept = 0, pres = 0, myL = 0;
-  if (active && !err) {
-    const u8 *sp = b + te + 1, *qp = b + qs;
-    u32 bad = 0, ph = 0, j = 0;
-    {
-      const u32 a = (u32)(size_t)sp & 3u;
-      const u32 *wp = (const u32 *)(sp - a);
-      u32 w0 = wp[0];
-      for (; j + 4 <= L; j += 4) {
-        const u32 w1 = *++wp;
-        const u32 v = __funnelshift_r(w0, w1, a * 8);
-        w0 = w1;
-        const u32 z = (v >> 1) & 0x03030303u;
-        const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
-        bad |= __byte_perm(0x47544341u, 0, sel) ^ v;
-        ph |= __byte_perm(0x08040201u, 0, sel);
-      }
-      for (; j < L; ++j) { const u32 f = dlut[sp[j]]; ph |= f; bad |= f ? 0u : 1u; }
-    }
-    u32 xfer = 0, namb = 0;
-    if (bad) { /* some base is not A/C/G/T: decide the ambiguity transfer (phyNGSC.cpp:549-588) */
-      bool ok = true, nul = false;
-      ph = 0;
-      for (j = 0; j < L; ++j) {
-        const u8 c = sp[j], q = qp[j];
-        const u32 f = dlut[c];
-        if (f) ph |= f;
-        else { ++namb; nul = nul || c == 0; if (amb_code(c) == 0 || q < 33 || q > 40) ok = false; }
-      }
-      xfer = (namb && ok) ? 1u : 0u;
-      if (!xfer) for (j = 0; j < L; ++j) { const u8 c = sp[j]; if (!dlut[c]) S.dna[c] = 1; } /* the byte stays in the DNA; presence is all that is needed here */
-      if (nul) err = E_UNSUPPORTED;
-    }
-    ph |= ph >> 16; ph |= ph >> 8;
-    pres = ph & 0xFu;
-    kept = xfer ? L - namb : L; myL = L;
-    d.kx[r] = (u16)(kept | (xfer << 15));
-  }
-  {
-    u32 pr = __reduce_or_sync(0xFFFFFFFFu, pres);
-    u32 mq = __reduce_max_sync(0xFFFFFFFFu, myL), ms = __reduce_max_sync(0xFFFFFFFFu, kept);
-    u32 iq = __reduce_max_sync(0xFFFFFFFFu, myL ? ~myL : 0u);
-    if (lane == 0) {
-      if (pr & 1u) S.dna['A'] = 1;
-      if (pr & 2u) S.dna['C'] = 1;
-      if (pr & 4u) S.dna['T'] = 1;
-      if (pr & 8u) S.dna['G'] = 1;
-      atomicMax(&S.maxq, mq); atomicMax(&S.maxs, ms); atomicMax(&S.inv_minq, iq);
-    }
-  }
   /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way.
    * Most tokens repeat record 0's: a token whose bytes AND separator equal record 0's is that token, so a warp
    * whose 32 records all pass this comparison neither tokenises the field nor reduces anything -- record 0's own
@@ -619,7 +580,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     }
   }
   __syncthreads();
-  const bool walk = active && !err && seed_ok;
+  const bool walk = active && seed_ok && cur_fits;
   bool fields_ok = true;
   u32 my_done = 0; /* fields this warp tokenised in this chunk (their values are in the table) */
   TitleCursor cur; cur.init(b, ts, te, lut);
@@ -701,16 +662,14 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
     if (lane == 0) { atomicMax(&S.facc[f][5], kmax); atomicMax(&S.facc[f][6], kinv); }
   }
   if (err) atomicMin(&S.err, err);
-  __syncthreads(); /* every thread has left the stage buffer and the value table */
-  if (tid == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
+  __syncthreads(); /* every thread has left the value table */
   } /* chunk loop */
+  cp_async_wait<0>();
+  if (!__syncthreads_and(fits) && tid == 0) atomicMin(&S.err, (i32)E_UNSUPPORTED); /* a title line longer than the slots */
+  __syncthreads();
   /* flush to the subblock accumulators */
   SbAcc *A = d.acc + s;
-  if (tid == 0) {
-    if (S.err) atomicMin(&A->status, S.err);
-    atomicMax(&A->max_qlen, S.maxq); atomicMax(&A->max_slen, S.maxs); atomicMax(&A->inv_min_qlen, S.inv_minq);
-  }
-  for (u32 i = tid; i < 256; i += CH) if (S.dna[i]) atomicAdd(&A->dna_occ[i], S.dna[i]);
+  if (tid == 0 && S.err) atomicMin(&A->status, S.err);
   if (seed_ok)
     for (u32 i = tid; i < nf * 8; i += CH) {
       u32 f = i >> 3, k = i & 7, v = S.facc[f][k];
@@ -733,12 +692,7 @@ __global__ void __launch_bounds__(128) k_xdelta(Dev d) {
   const SbPlan P = d.plans[s];
   SbAcc *A = d.acc + s;
   if (P.status || A->status) return;
-  { /* the raw per-position quality table of k_qhist: rows 0..max_qlen of 256 counters */
-    if (A->max_qlen + 1 > RAW_ROWS) { if (tid == 0) atomicMin(&A->status, (i32)E_UNSUPPORTED); return; }
-    uint4 *raw = (uint4 *)raw_table(d, s);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (u32 i = tid; i < (A->max_qlen + 1) * 64; i += 128) raw[i] = z;
-  }
+  if (A->max_qlen + 1 > RAW_ROWS) { if (tid == 0) atomicMin(&A->status, (i32)E_UNSUPPORTED); return; } /* the raw per-position quality table has RAW_ROWS rows */
   const u32 nchunk = (P.n_records + CH - 1) / CH;
   if (tid < MAXF) { mx[tid] = 0; mn[tid] = 0; }
   if (tid == 0) nf_s = min((u32)MAXF, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
@@ -976,97 +930,130 @@ __device__ __forceinline__ void load_title_tabs(const SbClass &C, TitleTabs &T) 
   for (u32 i = threadIdx.x; i < MAXF / 4; i += blockDim.x) ((u32 *)T.ncf)[i] = ((const u32 *)C.ncf)[i];
 }
 
-/* A CTA walks S2G consecutive chunks of one subblock; their bytes arrive through the bulk-copy pipeline (span_request)
- * while the previous chunk is processed, tables are loaded and the private char histograms flushed once per CTA.
- * Only the non-constant fields are visited (SbClass::ncf / ncskip).
- * One stage buffer and more resident CTAs beat two buffers and fewer CTAs here (measured on 36 bp: 0.34 vs 0.44 ms).
- * dynamic shared memory: [s2_nbuf stage buffers of span_bytes][nnc x CH numeric values] */
-__global__ void __launch_bounds__(CH) k_stat2(Dev d) {
+/* Exact DNA symbol counts (sym_stats, tasks.cpp:233-236): only needed -- and only run -- when more than four symbols
+ * force Huffman-coded DNA.  A CTA walks S2G consecutive chunks of one subblock, thread = record, spans staged by the
+ * bulk-copy engine; four bases per step like k_seqstat, A/C/G/T by popcount of their one-hot bytes.
+ * dynamic shared memory: [span_bytes stage buffer] */
+__global__ void __launch_bounds__(CH) k_dnacount(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ TitleTabs T;
-  __shared__ u32 pvals[2][MAXF];
-  __shared__ __align__(8) u64 bars[2];
+  __shared__ __align__(8) u64 bar;
   __shared__ u32 c_lo[S2G + 1];
-  __shared__ __align__(16) u8 lut[256];
-  __shared__ u32 chist[CSLOTS * 256];
-  __shared__ u32 dnah[256]; /* exact DNA symbol counts by symbol code (Huffman-coded DNA only) */
+  __shared__ u32 dnah[256]; /* by symbol code */
   const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const SbClass &C = d.cls[s];
-  const bool count_dna = !C.plain; /* sym_stats (tasks.cpp:233-236) are needed only when more than four symbols force Huffman-coded DNA */
-  if (C.status || (C.nnc == 0 && !count_dna)) return; /* every field constant: no histogram, no block flag is ever read */
+  if (C.status || C.plain) return;
   const u32 c0 = blockIdx.x * S2G, c1 = min(c0 + S2G, C.nchunk);
   if (c0 >= C.nchunk) return;
   const SbPlan P = d.plans[s];
   u32 *arena = d.arena + (size_t)s * d.arena_words;
-  const u32 nnc = C.nnc, R = C.R;
+  const u32 R = C.R;
   if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * CH, R)];
+  for (u32 i = tid; i < 256; i += CH) dnah[i] = 0;
+  ChunkStage stage; stage.init(dyn_smem, &bar);
+  __syncthreads();
+  {
+    bool fits = true;
+    for (u32 k = 0; k < c1 - c0; ++k) fits = fits && c_lo[k + 1] - (c_lo[k] & ~15u) + 16 <= d.span_bytes;
+    if (!fits) { if (tid == 0) atomicMin(&d.cls[s].status, (i32)E_UNSUPPORTED); return; }
+  }
+  if (tid == 0) stage.request(d.in, c_lo[0], c_lo[1]);
+  for (u32 c = c0; c < c1; ++c) {
+    const u32 nrec = min((u32)CH, R - c * CH);
+    const bool active = tid < nrec;
+    u32 my_te = 0, my_se = 0, my_kx = 0;
+    if (active) { const u32 r = P.first_rec + c * CH + tid; my_te = d.te[r]; my_se = d.se[r]; my_kx = d.kx[r]; }
+    const u8 *b = stage.wait(c_lo[c - c0]);
+    u32 nA = 0, nC = 0, nT = 0, nG = 0;
+    if (active) {
+      const u8 *sp = b + my_te + 1;
+      const u32 L = my_se - my_te - 1;
+      const bool xfer = my_kx >> 15;
+      const u32 a = (u32)(size_t)sp & 3u;
+      const u32 *wp = (const u32 *)(sp - a);
+      u32 w0 = wp[0], j = 0;
+      for (; j + 4 <= L; j += 4) {
+        const u32 w1 = *++wp;
+        const u32 v = __funnelshift_r(w0, w1, a * 8);
+        w0 = w1;
+        const u32 z = (v >> 1) & 0x03030303u;
+        const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
+        u32 oh = __byte_perm(0x08040201u, 0, sel);
+        const u32 bad = __byte_perm(0x47544341u, 0, sel) ^ v;
+        if (bad) { /* some of the four is not A/C/G/T: it counts under its own symbol unless the record's codes were transferred */
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if ((bad >> (8 * q)) & 0xFFu) { oh &= ~(0xFFu << (8 * q)); if (!xfer) atomicAdd(&dnah[C.sym_code[(v >> (8 * q)) & 0xFFu]], 1u); }
+        }
+        nA += __popc(oh & 0x01010101u); nC += __popc(oh & 0x02020202u); nT += __popc(oh & 0x04040404u); nG += __popc(oh & 0x08080808u);
+      }
+      for (; j < L; ++j) {
+        const u8 ch = sp[j];
+        if (ch == 'A') ++nA; else if (ch == 'C') ++nC; else if (ch == 'T') ++nT; else if (ch == 'G') ++nG;
+        else if (!xfer) atomicAdd(&dnah[C.sym_code[ch]], 1u);
+      }
+    }
+    nA = __reduce_add_sync(0xFFFFFFFFu, nA); nC = __reduce_add_sync(0xFFFFFFFFu, nC);
+    nT = __reduce_add_sync(0xFFFFFFFFu, nT); nG = __reduce_add_sync(0xFFFFFFFFu, nG);
+    if (lane == 0) {
+      if (nA) atomicAdd(&dnah[C.sym_code['A']], nA);
+      if (nC) atomicAdd(&dnah[C.sym_code['C']], nC);
+      if (nT) atomicAdd(&dnah[C.sym_code['T']], nT);
+      if (nG) atomicAdd(&dnah[C.sym_code['G']], nG);
+    }
+    __syncthreads(); /* the stage buffer is free again */
+    if (tid == 0 && c + 1 < c1) stage.request(d.in, c_lo[c + 1 - c0], c_lo[c + 2 - c0]);
+  }
+  for (u32 i = tid; i < C.nsym; i += CH) if (dnah[i]) atomicAdd(arena + C.dnastat_off + i, dnah[i]);
+}
+
+/* Numeric / char histograms and 32-record block descriptors.  A CTA walks S2G consecutive chunks of one subblock,
+ * thread = record, warp = 32-record block; only the title lines are staged (per-thread cp.async slots, the next chunk's
+ * lines arrive while the current chunk is walked); tables are loaded and the private char histograms flushed once per CTA.
+ * Only the non-constant fields are visited (SbClass::ncf / ncskip).
+ * dynamic shared memory: [2 stages of CH slots of d.ts bytes][nnc x CH numeric values] */
+__global__ void __launch_bounds__(CH) k_stat2(Dev d) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ TitleTabs T;
+  __shared__ u32 pvals[2][MAXF];
+  __shared__ __align__(16) u8 lut[256];
+  __shared__ u32 chist[CSLOTS * 256];
+  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const SbClass &C = d.cls[s];
+  if (C.status || C.nnc == 0) return; /* every field constant: no histogram, no block flag is ever read */
+  const u32 c0 = blockIdx.x * S2G, c1 = min(c0 + S2G, C.nchunk);
+  if (c0 >= C.nchunk) return;
+  const SbPlan P = d.plans[s];
+  u32 *arena = d.arena + (size_t)s * d.arena_words;
+  const u32 nnc = C.nnc, R = C.R, tsz = d.ts;
   load_lut(lut);
-  const u32 nbuf = d.s2_nbuf;
-  u32 *vals = (u32 *)((u8 *)dyn_smem + nbuf * d.span_bytes); /* vals[k * CH + tid], k = index in the non-constant list */
+  const u8 *slots = (const u8 *)dyn_smem;
+  const u32 slots_a = (u32)__cvta_generic_to_shared(dyn_smem);
+  u32 *vals = (u32 *)((u8 *)dyn_smem + 2u * CH * tsz); /* vals[k * CH + tid], k = index in the non-constant list */
   /* char histograms of the first CSLOTS per-position tables are privatised in shared memory */
   const u32 ncs = min(C.ntab - C.tchr0, (u32)CSLOTS);
   for (u32 i = tid; i < ncs * 256; i += CH) chist[i] = 0;
-  if (count_dna) for (u32 i = tid; i < 256; i += CH) dnah[i] = 0;
   load_title_tabs(C, T);
-  const u32 buf_a0 = (u32)__cvta_generic_to_shared(dyn_smem), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);
-  if (tid == 0) { mbar_init(bar_a0, 1); mbar_init(bar_a0 + 8, 1); mbar_fence_init(); }
   if (tid < nnc && c0 > 0) pvals[0][tid] = d.chunk_last[((size_t)P.chunk_base + c0 - 1) * MAXF + C.ncf[tid]]; /* record before the first chunk */
+  u32 ts = 0, te = 0;
+  bool n_fits = true; /* the slots are sized for the longest title line of the batch: always true */
+  { const u32 i = c0 * CH + tid; if (i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; n_fits = stage_title_line(d.in, slots_a + tid * tsz, tsz, ts, te); } }
+  cp_async_commit();
   __syncthreads();
-  auto request = [&](u32 c) { const u32 st = (c - c0) % nbuf; span_request(d.in, c_lo[c - c0], c_lo[c - c0 + 1], buf_a0 + st * d.span_bytes, bar_a0 + 8 * st); };
-  if (tid == 0) request(c0);
-  u32 phases = 0;
-  u32 ts = 0, te = 0, se = 0, kx = 0;
-  { const u32 i = c0 * CH + tid; if (i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; if (count_dna) { se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; } } }
   for (u32 c = c0; c < c1; ++c) {
-    const u32 st = (c - c0) % nbuf, pb = (c - c0) & 1u;
+    const u32 buf = (c - c0) & 1u, pb = buf;
     const u32 nrec = min((u32)CH, R - c * CH);
-    const bool active = tid < nrec;
-    const u32 r = P.first_rec + c * CH + (active ? tid : 0);
+    const u32 my_ts = ts, my_te = te;
+    const bool active = tid < nrec && n_fits;
+    const u32 r = P.first_rec + c * CH + (tid < nrec ? tid : 0);
     const u32 wbase = tid & ~31u;
-    if (nbuf == 2 && tid == 0 && c + 1 < c1) request(c + 1);
-    const u32 my_ts = ts, my_te = te, my_se = se, my_kx = kx;
-    { const u32 i = (c + 1) * CH + tid; if (c + 1 < c1 && i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; if (count_dna) { se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; } } } /* next chunk's record */
-    mbar_wait(bar_a0 + 8 * st, (phases >> st) & 1u); phases ^= 1u << st;
-    const u8 *b = (const u8 *)dyn_smem + st * d.span_bytes - (c_lo[c - c0] & ~15u);
-    if (count_dna) { /* exact counts of the kept bases: four per step like k_stat1, A/C/G/T by popcount of their one-hot bytes */
-      u32 nA = 0, nC = 0, nT = 0, nG = 0;
-      if (active) {
-        const u8 *sp = b + my_te + 1;
-        const u32 L = my_se - my_te - 1;
-        const bool xfer = my_kx >> 15;
-        const u32 a = (u32)(size_t)sp & 3u;
-        const u32 *wp = (const u32 *)(sp - a);
-        u32 w0 = wp[0], j = 0;
-        for (; j + 4 <= L; j += 4) {
-          const u32 w1 = *++wp;
-          const u32 v = __funnelshift_r(w0, w1, a * 8);
-          w0 = w1;
-          const u32 z = (v >> 1) & 0x03030303u;
-          const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
-          u32 oh = __byte_perm(0x08040201u, 0, sel);
-          const u32 bad = __byte_perm(0x47544341u, 0, sel) ^ v;
-          if (bad) { /* some of the four is not A/C/G/T: it counts under its own symbol unless the record's codes were transferred */
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if ((bad >> (8 * q)) & 0xFFu) { oh &= ~(0xFFu << (8 * q)); if (!xfer) atomicAdd(&dnah[C.sym_code[(v >> (8 * q)) & 0xFFu]], 1u); }
-          }
-          nA += __popc(oh & 0x01010101u); nC += __popc(oh & 0x02020202u); nT += __popc(oh & 0x04040404u); nG += __popc(oh & 0x08080808u);
-        }
-        for (; j < L; ++j) {
-          const u8 ch = sp[j];
-          if (ch == 'A') ++nA; else if (ch == 'C') ++nC; else if (ch == 'T') ++nT; else if (ch == 'G') ++nG;
-          else if (!xfer) atomicAdd(&dnah[C.sym_code[ch]], 1u);
-        }
-      }
-      nA = __reduce_add_sync(0xFFFFFFFFu, nA); nC = __reduce_add_sync(0xFFFFFFFFu, nC);
-      nT = __reduce_add_sync(0xFFFFFFFFu, nT); nG = __reduce_add_sync(0xFFFFFFFFu, nG);
-      if (lane == 0) {
-        if (nA) atomicAdd(&dnah[C.sym_code['A']], nA);
-        if (nC) atomicAdd(&dnah[C.sym_code['C']], nC);
-        if (nT) atomicAdd(&dnah[C.sym_code['T']], nT);
-        if (nG) atomicAdd(&dnah[C.sym_code['G']], nG);
-      }
+    { /* next chunk's record: its title line starts to arrive now */
+      const u32 i = (c + 1) * CH + tid;
+      if (c + 1 < c1 && i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; n_fits = stage_title_line(d.in, slots_a + ((buf ^ 1u) * CH + tid) * tsz, tsz, ts, te); }
+      cp_async_commit();
     }
+    cp_async_wait<1>();
+    const u8 *b = slots + (size_t)(buf * CH + tid) * tsz - (my_ts & ~15u);
+    __syncwarp(); /* string fields are compared with lane 0's token: its slot must have arrived as well */
     u32 flags = 0;
     /* one walk: string fields are finished here, numeric values are parked in shared memory */
     TitleCursor cur; cur.init(b, my_ts, my_te, lut);
@@ -1078,11 +1065,13 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
       if (active) cur.next(t);
       if (F.kind == K_NUM) { vals[k * CH + tid] = t.v; continue; }
       u32 len = t.end - t.start;
-      u32 st_lo = __shfl_sync(0xFFFFFFFFu, t.start, 0), len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
+      /* lane 0's token of this field, addressed inside lane 0's slot */
+      const u32 len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
+      const u32 a0_off = (u32)__shfl_sync(0xFFFFFFFFu, (u32)((b + t.start) - slots), 0);
       bool pred = true;
       if (active) {
         pred = len == len_lo;
-        const u8 *a = b + t.start, *a0 = b + st_lo;
+        const u8 *a = b + t.start, *a0 = slots + a0_off;
         for (u32 j = 0; pred && j < len; ++j) pred = a[j] == a0[j];
         const u16 *sm = (const u16 *)(arena + F.slotmap_off);
         for (u32 j = 0; j < len; ++j)
@@ -1107,30 +1096,30 @@ __global__ void __launch_bounds__(CH) k_stat2(Dev d) {
       i32 pv = (i32)(tid > 0 ? vals[k * CH + tid - 1] : pvals[pb][k]);
       if (tid == CH - 1) pvals[pb ^ 1u][k] = (u32)v; /* record before the next chunk */
       i32 dl = wsub(v, pv);
-      bool hasd = active && r > P.first_rec;
+      const bool on = tid < nrec;
+      bool hasd = on && r > P.first_rec;
       bool pred;
       if (F.is_delta) {
         /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
         i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
         if (nrec - wbase < 2) bd = 0;
-        pred = !active || lane < 2 || dl == bd;
+        pred = !on || lane < 2 || dl == bd;
         pred = __all_sync(0xFFFFFFFFu, pred) && bd == F.min_d;
         if (F.has_table) warp_hist_add(arena + F.freq_off, (u32)wsub(dl, F.base), hasd);
       } else {
         i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
-        pred = __all_sync(0xFFFFFFFFu, !active || v == v_lo);
+        pred = __all_sync(0xFFFFFFFFu, !on || v == v_lo);
         if (F.has_table) {
-          warp_hist_add(arena + F.freq_off, (u32)wsub(v, F.base), active);
-          if (active && r == P.first_rec) atomicAdd(arena + F.freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
+          warp_hist_add(arena + F.freq_off, (u32)wsub(v, F.base), on);
+          if (on && r == P.first_rec) atomicAdd(arena + F.freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
         }
       }
       if (pred) flags |= 1u << f;
     }
     if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (c * CH + wbase) / 32] = flags;
-    __syncthreads(); /* the stage buffer and the value table are free again */
-    if (nbuf == 1 && tid == 0 && c + 1 < c1) request(c + 1);
+    __syncthreads(); /* the value table is free again */
   }
-  if (count_dna) for (u32 i = tid; i < C.nsym; i += CH) if (dnah[i]) atomicAdd(arena + C.dnastat_off + i, dnah[i]);
+  cp_async_wait<0>();
   for (u32 i = tid; i < ncs * 256; i += CH) {
     u32 v = chist[i];
     if (v) atomicAdd(arena + C.chr_freq_off + i, v);

@@ -15,8 +15,8 @@
  * to the reference's.
  *
  * Differences kept on purpose: np = 1 is accepted (the reference refuses np < 2, :91-97; WRID then takes 0 bits);
- * `threads` is accepted and checked like the reference does but changes nothing: the reference's output is thread-count
- * independent and the GPU path has no thread count.
+ * `threads` does not parallelise anything here (the GPU path has no thread count); it is passed to the library because the
+ * reference's choice of records in very short windows depends on it (see the record cap comment in main).
  * Built against a real <mpi.h> when mpicxx exists, otherwise against host/mpi_shim/mpi.h (PHY_SHIM_NP=<n> ./phyNGSC_b200 ...).
  */
 #include <mpi.h>
@@ -202,13 +202,13 @@ int main(int argc, char **argv) {
 
   phy_region_params prm;
   prm.file_size = size; prm.np = np; prm.rank = rank; prm.window_bytes = READ_BUFFER_SIZE; prm.overlap = OVERLAP;
-  /* Record cap.  The reference gives each of its `threads` byte slices of a window room for 100000/threads + 1 records
-   * (phyNGSC.cpp:51,82,261-266,321-326) and its output does not depend on `threads` as long as no slice runs out of room
-   * (when one does, the reference silently drops the rest of that slice).  A subblock here is one run of
-   * consecutive records, so the whole-window cap of threads = 1 is used for every thread count: the same bytes as the
-   * reference wherever the reference keeps every record. */
+  /* `threads` (phyNGSC.cpp:51,82): the reference cuts a window into that many byte slices.  Its output is the same for
+   * every thread count except in windows shorter than about threads x overlap, where the slices before the last keep
+   * records the stop rule of :315 would have left for the next rank -- the library reproduces that rule.
+   * Its per-slice record caps (100000/threads + 1 records, :321-326) silently drop the rest of a slice when hit; a
+   * subblock here is one run of consecutive records, so the whole-window cap is used for every thread count. */
   prm.record_cap = 100000u;
-  (void)threads;
+  prm.threads = (uint32_t)threads; prm.reserved = 0;
   std::vector<phy_subblock_desc> descs((size_t)(region_len / (READ_BUFFER_SIZE / 2)) + 64);
   uint32_t nd_ = (uint32_t)descs.size();
   phy_region_result res;

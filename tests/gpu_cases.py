@@ -15,12 +15,12 @@ def first_diff(a, b):
     return k
 
 
-def compare_rank(ctx, data, npr, rank, window_bytes=api.WINDOW_BYTES, record_cap=api.RECORD_CAP, whole_tail=True, verbose=True):
+def compare_rank(ctx, data, npr, rank, window_bytes=api.WINDOW_BYTES, record_cap=api.RECORD_CAP, whole_tail=True, verbose=True, threads=1):
     """-> list of problem strings (empty = parity)."""
-    ref = O.compress_rank(data, npr, rank, window_bytes=window_bytes, record_cap=record_cap)
+    ref = O.compress_rank(data, npr, rank, window_bytes=window_bytes, record_cap=record_cap, threads=threads)
     start, end = api.region_slice(data.size, npr, rank)
     region = data[start:] if whole_tail else data[start:end]
-    prm = api.region_params(data.size, npr, rank, window_bytes=window_bytes, record_cap=record_cap)
+    prm = api.region_params(data.size, npr, rank, window_bytes=window_bytes, record_cap=record_cap, threads=threads)
     probs = []
     try:
         descs, out, res = ctx.compress_region(region, prm, check=True)
@@ -76,6 +76,8 @@ CASES = [  # (name, shape, seed, bytes, np, window_bytes)
     ("long300_two_position_passes", "py:long300", 34, 3_000_000, 2, 1 << 20),
     ("odd_quality_bytes", "py:odd_qual", 35, 1_500_000, 2, 512 * 1024),
     ("tiny_reads", "py:tiny", 36, 600_000, 2, 128 * 1024),
+    ("36bp_threads4_short_last_window", "36bp", 702, 40_000_000 + 846, 2, 1 << 23, 4),
+    ("100bp_threads3_small_windows", "100bp", 37, 1_500_000, 2, 64 * 1024, 3),
 ]
 
 
@@ -116,9 +118,10 @@ def py_fastq(kind, seed, nbytes):
 
 
 def run_case(ctx, case):
-    name, shape, seed, nbytes, npr, win = case
+    name, shape, seed, nbytes, npr, win = case[:6]
+    threads = case[6] if len(case) > 6 else 1
     data = py_fastq(shape[3:], seed, nbytes) if shape.startswith("py:") else synth.fastq(shape, seed, target_bytes=nbytes + 131)
     probs = []
     for r in range(npr):
-        probs += compare_rank(ctx, data, npr, r, window_bytes=win)
+        probs += compare_rank(ctx, data, npr, r, window_bytes=win, threads=threads)
     return probs

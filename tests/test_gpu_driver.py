@@ -82,20 +82,33 @@ def test_compress_then_decompress_gives_the_file_back(shape, mb, npr, stream, tm
 
 @pytest.mark.parametrize("threads", [2, 4])
 def test_driver_threads_argument_matches_the_reference_at_the_same_thread_count(threads, tmp_path, oracle):
-    """`threads` > 1 must not change a byte: the reference's output is thread-count independent while no per-thread slice of
-    a window runs out of room (phyNGSC.cpp:261-266,321-326), and 36 bp windows hold ~69 k records -- more than
-    100000/threads for threads >= 2, so a whole-window cap of 100000/threads would cut them short.  The unmodified reference
-    runs at the same np and the same thread count; blocks are compared keyed by rank."""
-    if not oracle.have_reference():
-        pytest.skip("oracle/_ref/phyNGSC_ref not built")
+    """`threads` > 1: 36 bp windows hold ~69 k records (more than 100000/threads, so a whole-window cap of 100000/threads
+    would cut them short), and the small final window of rank 0 keeps more records than with one thread because only the
+    reference's last thread applies the stop rule (phyNGSC.cpp:261-266, 303, 315).  The driver's blocks must equal the
+    oracle's at that thread count and -- keyed by rank -- the unmodified reference's (which is flaky with more than one
+    thread, SURVEY.md Q16: it gets a few attempts)."""
     data = synth.fastq("36bp", 700 + threads, target_bytes=40_000_000 + 977)
     src, dst, ref = tmp_path / "in.fastq", tmp_path / "out.ngsc", tmp_path / "ref.ngsc"
     data.tofile(src)
     out = run_driver(src, dst, 2, threads=threads)
     assert "WARNING" not in out
-    oracle.run_reference(str(src), str(ref), np_ranks=2, threads=threads)
-    mine, want = container.read_ngsc(str(dst)), container.read_ngsc(str(ref))
+    mine = container.read_ngsc(str(dst))
+    one = [oracle.compress_rank(data, 2, r, threads=1)["subblocks"] for r in range(2)]
     for r in range(2):
-        assert len(mine["per_rank_subblocks"][r]) == len(want["per_rank_subblocks"][r])
+        assert mine["per_rank_subblocks"][r] == oracle.compress_rank(data, 2, r, threads=threads)["subblocks"]
+    assert mine["per_rank_subblocks"] != one, "this input was chosen because its last window depends on the thread count"
+    if not oracle.have_reference():
+        pytest.skip("oracle/_ref/phyNGSC_ref not built")
+    want = None
+    for _ in range(4):
+        try:
+            oracle.run_reference(str(src), str(ref), np_ranks=2, threads=threads, timeout=90)
+            want = container.read_ngsc(str(ref))
+            break
+        except Exception:  # noqa: BLE001  (hang or crash of the multi-threaded reference)
+            continue
+    if want is None:
+        pytest.skip("the reference did not finish with this thread count")
+    for r in range(2):
         assert [b["raw"] for b in mine["per_rank_blocks"][r]] == [b["raw"] for b in want["per_rank_blocks"][r]]
     assert mine["footer"]["n_subblocks"] == want["footer"]["n_subblocks"]

@@ -58,6 +58,31 @@ def test_rank_payloads_and_blocks_match_reference(shape, mb, npr, tmp_path, orac
         assert [b["raw"] for b in ng["per_rank_blocks"][r]] == mine["blocks"]
 
 
+@pytest.mark.parametrize("threads", [2, 4])
+def test_thread_count_rule_matches_reference(threads, tmp_path, oracle):
+    """no_threads > 1: only the reference's last thread applies the stop rule (phyNGSC.cpp:261-266, 303, 315), so the
+    short final window of rank 0 keeps more records than with one thread on this input.  The multi-threaded reference
+    is flaky: it gets a few attempts with a short timeout."""
+    data = synth.fastq("36bp", 702, target_bytes=40_000_000 + 977)
+    src = tmp_path / "in.fastq"
+    data.tofile(src)
+    ng = None
+    for _ in range(4):
+        try:
+            oracle.run_reference(str(src), str(tmp_path / "out.ngsc"), np_ranks=2, threads=threads, timeout=60)
+            ng = container.read_ngsc(str(tmp_path / "out.ngsc"))
+            break
+        except Exception:  # noqa: BLE001
+            continue
+    if ng is None:
+        pytest.skip("the reference did not finish with this thread count")
+    mine = [oracle.compress_rank(data, 2, r, threads=threads) for r in range(2)]
+    for r in range(2):
+        assert ng["per_rank_subblocks"][r] == mine[r]["subblocks"]
+        assert [b["raw"] for b in ng["per_rank_blocks"][r]] == mine[r]["blocks"]
+    assert mine[0]["subblocks"] != oracle.compress_rank(data, 2, 0, threads=1)["subblocks"]
+
+
 @pytest.mark.parametrize("shape", ["36bp", "100bp", "100bp_huffdna", "mixed_amb", "title_stress"])
 def test_oracle_payloads_decode_with_the_reference_decoder(shape):
     """Second, independent pin: the oracle's payloads, fed to the reference's own Fetch* functions
