@@ -47,6 +47,7 @@ struct phy_ctx {
   BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; SbOut *h_sbout = nullptr; PlanState *h_state = nullptr;
   u32 launches = 0;
   u64 resident_len = 0, resident_out = 0;
+  u8 *big_in = nullptr, *big_out = nullptr; u64 big_in_cap = 0, big_out_cap = 0; /* resident regions larger than one batch (phy_upload) */
   u32 last_S = 0;
   u32 nq_hint = 0, prev_groups = 0, prev_max_len = 0; /* quality alphabet size seen by the previous batch (sizes the packed tables' shared memory without a readback) */
   /* per-kernel timing (phy_profile): one event after every launch of run_batch */
@@ -112,7 +113,7 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->plan_state,
-                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used};
+                 ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl};
   for (void *p : host) if (p) cudaFreeHost(p);
@@ -237,7 +238,7 @@ extern "C" int64_t phy_find_first_record(const uint8_t *b, uint64_t lim) {
 
 /* Runs every kernel over the batch that is resident in ctx->in[0..len).  `start_pos` = first record of the
  * next window inside the batch.  On return h_hdr / h_plans / h_sbout describe the batch. */
-static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
+static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
   Dev d;
   memset(&d, 0, sizeof d);
   d.in = in; d.len = len; d.start_pos = start_pos;
@@ -246,7 +247,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u32 len, u32 start_pos
   d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
-  d.out = out; d.out_cap = ctx->out_cap;
+  d.out = out; d.out_cap = out_cap;
   d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
   d.span_bytes = 0;
   d.tmp = ctx->tmp; d.tmp_cap = ctx->tmp_cap; d.tmp_used = ctx->tmp_used;
@@ -481,75 +482,114 @@ static int init_plan(phy_ctx *ctx, const uint8_t *region_host, u64 region_len, c
 }
 
 extern "C" int phy_upload(phy_ctx *ctx, const uint8_t *region, uint64_t region_len) {
-  if (!ctx || !region) return PHY_ERR_ARG;
-  if (region_len == 0 || region_len > ctx->max_batch) { ctx->err = "region does not fit one batch"; return PHY_ERR_CAPACITY; }
+  if (!ctx || !region || region_len == 0) return PHY_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(ctx->in, region, region_len, cudaMemcpyHostToDevice, ctx->stream));
+  u8 *dst = ctx->in;
+  if (region_len > ctx->max_batch) { /* larger than one batch: its own device buffers, walked batch by batch */
+    if (ctx->big_in_cap < region_len) {
+      if (ctx->big_in) { CK(cudaFree(ctx->big_in)); ctx->big_in = nullptr; }
+      if (ctx->big_out) { CK(cudaFree(ctx->big_out)); ctx->big_out = nullptr; }
+      CK(cudaMalloc(&ctx->big_in, region_len + 4096));
+      ctx->big_in_cap = region_len;
+      ctx->big_out_cap = region_len / 2 + (1u << 20);
+      CK(cudaMalloc(&ctx->big_out, ctx->big_out_cap + 64));
+    }
+    dst = ctx->big_in;
+  }
+  for (u64 o = 0; o < region_len; o += 1ull << 30) { /* 1 GiB pieces: pageable sources are staged by the driver */
+    const u64 n = region_len - o < (1ull << 30) ? region_len - o : (1ull << 30);
+    CK(cudaMemcpyAsync(dst + o, region + o, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   /* 64 bytes of zero padding behind the data: vector loads may run past the end */
-  CK(cudaMemsetAsync(ctx->in + region_len, 0, 64, ctx->stream));
+  CK(cudaMemsetAsync(dst + region_len, 0, 64, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->resident_len = region_len;
   return PHY_OK;
 }
 
-/* last rank whose file does not end in '\n': the reference's arithmetic still places the next record
- * start one byte past the end; a virtual newline gives the splitter the same view */
-static int patch_trailing_newline(phy_ctx *ctx, u64 &len, bool is_last_rank, bool batch_final, u8 last_byte) {
-  if (is_last_rank && batch_final && last_byte != '\n') {
-    const u8 nl = '\n';
-    CK(cudaMemcpyAsync(ctx->in + len, &nl, 1, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    len += 1;
-  }
-  return PHY_OK;
-}
+/* How far before a batch's end the next one starts: a window that does not fit the rest of a batch (with the slack for
+ * records longer than the overlap) is left to the next batch, which therefore starts one window + slack earlier. */
+static u64 batch_back(const phy_ctx *ctx, const phy_region_params *p) { return (u64)p->window_bytes + ctx->slack; }
 
 extern "C" int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params,
                                      phy_subblock_desc *descs, uint32_t *inout_n_descs, phy_region_result *result) {
   if (!ctx || !descs || !inout_n_descs) return PHY_ERR_ARG;
   if (region_len == 0 || region_len != ctx->resident_len) { ctx->err = "resident bytes do not match region_len"; return PHY_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
+  const bool big = region_len > ctx->max_batch;
+  u8 *rin = big ? ctx->big_in : ctx->in, *rout = big ? ctx->big_out : ctx->out;
+  const u64 rout_cap = big ? ctx->big_out_cap : ctx->out_cap;
   PlanState st;
   u32 first = 0;
   if (params && params->rank != 0) {
     /* the head of the region is needed on the host for the '@' heuristic */
     u64 n = region_len < 65536 ? region_len : 65536;
     std::string head(n, '\0');
-    CK(cudaMemcpy(&head[0], ctx->in, n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&head[0], rin, n, cudaMemcpyDeviceToHost));
     int64_t f = phy_find_first_record((const uint8_t *)head.data(), n);
     if (f < 0) { ctx->err = "no record start found at the beginning of the region"; return (int)f; }
     first = (u32)f;
   }
   int rc = init_plan(ctx, nullptr, region_len, params, first, true, st);
   if (rc) return rc;
-  u8 last_byte = '\n';
-  if (st.is_last) CK(cudaMemcpy(&last_byte, ctx->in + region_len - 1, 1, cudaMemcpyDeviceToHost));
-  u64 len = region_len;
-  rc = patch_trailing_newline(ctx, len, st.is_last, true, last_byte);
-  if (rc) return rc;
+  u64 len_total = region_len;
+  if (st.is_last) { /* last rank whose file does not end in a newline: a virtual one (see patch_trailing_newline) */
+    u8 last_byte = '\n';
+    CK(cudaMemcpy(&last_byte, rin + region_len - 1, 1, cudaMemcpyDeviceToHost));
+    if (last_byte != '\n') { const u8 nl = '\n'; CK(cudaMemcpy(rin + region_len, &nl, 1, cudaMemcpyHostToDevice)); len_total += 1; }
+  }
+  const u64 back = batch_back(ctx, params);
+  if (big && ctx->max_batch < 2 * back + 4096) { ctx->err = "max_batch_bytes is too small for the window size"; return PHY_ERR_CAPACITY; }
   *ctx->h_state = st;
   ctx->launches = 0;
-  CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  rc = run_batch(ctx, ctx->in, ctx->out, (u32)len, first, 0, (i64)len, true);
-  if (rc) return rc;
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  const u32 S = ctx->last_S;
-  if (!ctx->h_state->done) { ctx->err = "batch did not cover the region (raise max_subblocks)"; return ctx->h_state->status ? ctx->h_state->status : PHY_ERR_CAPACITY; }
-  if (S > *inout_n_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
-  fill_descs(ctx, S, 0, descs);
-  *inout_n_descs = S;
-  ctx->resident_out = ctx->h_hdr->total_out;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(ctx->ev[0], s));
+  const u32 cap_descs = *inout_n_descs;
+  u32 nd = 0, nb = 0;
+  u64 base = 0, next_pos = 0, out_used = 0;
+  bool done = false;
+  while (!done) {
+    u64 blen = len_total - base;
+    if (blen > ctx->max_batch) blen = ctx->max_batch;
+    const bool final = base + blen == len_total;
+    const u32 start_pos = (u32)(next_pos - base) + (nb == 0 ? first : 0u);
+    rc = run_batch(ctx, rin + base, rout + out_used, rout_cap - out_used, (u32)blen, start_pos, (i64)base, (i64)len_total, final);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    const u32 S = ctx->last_S;
+    const PlanState hs = *ctx->h_state;
+    if (hs.status) { ctx->err = std::string("window chaining failed: ") + phy_strerror(hs.status); return hs.status; }
+    if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
+    fill_descs(ctx, S, out_used, descs + nd);
+    nd += S; ++nb;
+    if (S) out_used += ctx->h_hdr->total_out;
+    done = hs.done != 0;
+    if (!done) {
+      if (S == 0 && (u64)hs.bytes_read == next_pos && (final || (u64)hs.bytes_read < base + blen - back)) {
+        ctx->err = final ? "region exhausted before the working region was covered" : "a window does not fit one batch (raise max_batch_bytes)";
+        return final ? PHY_ERR_MALFORMED : PHY_ERR_CAPACITY;
+      }
+      next_pos = (u64)hs.bytes_read;
+      /* the chain stops early when the batch's subblock capacity is used up: the next round starts where it stopped,
+       * in the same bytes; otherwise the next batch starts one window + slack before this one's end */
+      const u64 nbase = final ? base : (base + blen - back) & ~(u64)255;
+      if (next_pos >= nbase) base = nbase;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[1], s));
+  CK(cudaStreamSynchronize(s));
+  *inout_n_descs = nd;
+  ctx->resident_out = out_used;
   int worst = 0;
   if (result) {
     memset(result, 0, sizeof *result);
-    result->n_subblocks = S; result->n_batches = 1; result->wr_overlap = (int32_t)first; result->kernel_launches = ctx->launches;
-    result->out_used = ctx->h_hdr->total_out;
+    result->n_subblocks = nd; result->n_batches = nb; result->wr_overlap = (int32_t)first; result->kernel_launches = ctx->launches;
+    result->out_used = out_used;
     CK(cudaEventElapsedTime(&result->kernel_ms, ctx->ev[0], ctx->ev[1]));
-    for (u32 i = 0; i < S; ++i) { result->bytes_in += descs[i].bytes_consumed; result->bytes_out += descs[i].out_len; }
+    for (u32 i = 0; i < nd; ++i) { result->bytes_in += descs[i].bytes_consumed; result->bytes_out += descs[i].out_len; }
   }
-  for (u32 i = 0; i < S; ++i) if (descs[i].status < worst) worst = descs[i].status;
+  for (u32 i = 0; i < nd; ++i) if (descs[i].status < worst) worst = descs[i].status;
   if (worst) ctx->err = std::string("a subblock failed: ") + phy_strerror(worst);
   return worst;
 }
@@ -558,7 +598,8 @@ extern "C" int phy_download(phy_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64
   if (!ctx || !out) return PHY_ERR_ARG;
   if (ctx->resident_out > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(out, ctx->out, ctx->resident_out, cudaMemcpyDeviceToHost, ctx->stream));
+  const u8 *src = ctx->resident_len > ctx->max_batch ? ctx->big_out : ctx->out;
+  CK(cudaMemcpyAsync(out, src, ctx->resident_out, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (out_len) *out_len = ctx->resident_out;
   return PHY_OK;
@@ -604,35 +645,31 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
   CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));
   const bool multi = region_len > ctx->max_batch;
-  if (multi) {
-    rc = pipeline_init(ctx);
-    if (rc) return rc;
-    if (!ctx->in2) { CK(cudaMalloc(&ctx->in2, ctx->max_batch + 4096)); CK(cudaMemset(ctx->in2, 0, ctx->max_batch + 4096)); }
-    if (!ctx->out2) CK(cudaMalloc(&ctx->out2, ctx->out_cap + 64));
-  } else {
-    rc = pipeline_init(ctx);
-    if (rc) return rc;
-  }
-  u8 *inb[2] = {ctx->in, multi ? ctx->in2 : ctx->in}, *outb[2] = {ctx->out, multi ? ctx->out2 : ctx->out};
-  const u64 back = (u64)params->window_bytes + ctx->slack; /* how far before a batch's end the next one starts */
+  rc = pipeline_init(ctx);
+  if (rc) return rc;
+  if (multi && !ctx->in2) { CK(cudaMalloc(&ctx->in2, ctx->max_batch + 4096)); CK(cudaMemset(ctx->in2, 0, ctx->max_batch + 4096)); }
+  if (!ctx->out2) CK(cudaMalloc(&ctx->out2, ctx->out_cap + 64));
+  u8 *inb[2] = {ctx->in, multi ? ctx->in2 : ctx->in}, *outb[2] = {ctx->out, ctx->out2};
+  const u64 back = batch_back(ctx, params);
   if (multi && ctx->max_batch < 2 * back + 4096) { ctx->err = "max_batch_bytes is too small for the window size"; return PHY_ERR_CAPACITY; }
   const u32 cap_descs = *inout_n_descs;
-  u32 nd = 0, nb = 0;
+  u32 nd = 0, nb = 0, nup = 0;
   u64 out_used = 0, next_pos = 0;
   float k_ms = 0, h2d_ms = 0, d2h_ms = 0;
-  u64 h2d_bytes = 0;
   int worst = 0;
   bool patch_nl = false; /* decided when the final batch is uploaded (the region's last byte must be there) */
 
-  /* enqueue the upload of the batch that starts at `base` into buffer `slot` (stream s_in).  Bytes that the
+  /* enqueue the upload of the batch that starts at `base` into input buffer `slot` (stream s_in).  Bytes that the
    * previous upload already brought to the device (the tail of the other buffer: consecutive batches overlap by one
    * window + slack) are copied device-to-device instead of crossing PCIe a second time. */
   u64 up_base = 0, up_blen = 0; int up_slot = -1; /* last upload issued on s_in */
+  bool up_timed[2] = {false, false};
   auto upload = [&](u64 base, int slot, u64 &blen, bool &final, u64 &len) -> int {
     blen = region_len - base;
     if (blen > ctx->max_batch) blen = ctx->max_batch;
     final = base + blen == region_len;
     len = blen;
+    if (up_timed[slot]) { float t; CK(cudaEventSynchronize(ctx->ev_in[slot])); CK(cudaEventElapsedTime(&t, ctx->ev_h0[slot], ctx->ev_in[slot])); h2d_ms += t; up_timed[slot] = false; }
     CK(cudaEventRecord(ctx->ev_h0[slot], ctx->s_in));
     u64 carry = 0;
     if (up_slot >= 0 && up_slot != slot && base >= up_base && base < up_base + up_blen) {
@@ -640,89 +677,93 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
       if (carry > blen) carry = blen;
       CK(cudaMemcpyAsync(inb[slot], inb[up_slot] + (base - up_base), carry, cudaMemcpyDeviceToDevice, ctx->s_in));
     }
-    need(base + blen);
+    /* host bytes in pieces: with a reader still filling the region (streamed variant) a piece crosses PCIe as soon as it is there */
+    const u64 piece = 16ull << 20;
+    for (u64 o = carry; o < blen; o += piece) {
+      const u64 n = blen - o < piece ? blen - o : piece;
+      need(base + o + n);
+      CK(cudaMemcpyAsync(inb[slot] + o, region + base + o, n, cudaMemcpyHostToDevice, ctx->s_in));
+    }
     if (final) patch_nl = st.is_last && region[region_len - 1] != '\n';
-    if (blen > carry) CK(cudaMemcpyAsync(inb[slot] + carry, region + base + carry, blen - carry, cudaMemcpyHostToDevice, ctx->s_in));
-    h2d_bytes += blen - carry;
-    if (final && patch_nl) { /* virtual trailing newline, see patch_trailing_newline */
+    if (final && patch_nl) { /* last rank whose file does not end in a newline: the reference's arithmetic still places the
+                              * next record start one byte past the end; a virtual newline gives the splitter the same view */
       CK(cudaMemcpyAsync(inb[slot] + blen, ctx->h_nl, 64, cudaMemcpyHostToDevice, ctx->s_in));
       len += 1;
     } else {
       CK(cudaMemsetAsync(inb[slot] + blen, 0, 64, ctx->s_in));
     }
     CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    up_timed[slot] = true; ++nup;
     up_base = base; up_blen = blen; up_slot = slot;
     return PHY_OK;
   };
 
+  /* Batches: input buffer `cur` holds the batch being compressed, the other one receives the next batch meanwhile (its
+   * start does not depend on this batch's result: one window + slack before this batch's end is never past the point
+   * where the window chain stops here).  Output buffers alternate every round: the payloads of round r leave for the
+   * host on s_out while round r + 1 runs. */
+  int cur = 0, oslot = 0;
   u64 base = 0, blen = 0, len = 0;
   bool final = false;
-  rc = upload(0, 0, blen, final, len);
+  rc = upload(0, cur, blen, final, len);
   if (rc) return rc;
-  bool done = false;
+  u64 nbase = 0, nblen = 0, nlen = 0;
+  bool nfinal = false, have_next = false, done = false;
   bool have_d2h[2] = {false, false};
+  auto speculate = [&]() -> int { /* the kernels of the batch before the previous one have left the other input buffer (the host synchronised on them) */
+    if (final || have_next || !multi) return PHY_OK;
+    nbase = (base + blen - back) & ~(u64)255;
+    int r = upload(nbase, cur ^ 1, nblen, nfinal, nlen);
+    have_next = r == PHY_OK;
+    return r;
+  };
   while (!done) {
-    const int cur = (int)(nb & 1), nxt = cur ^ 1;
-    /* speculative upload of the next batch */
-    u64 nbase = 0, nblen = 0, nlen = 0;
-    bool nfinal = false, have_next = false;
-    if (!final) {
-      nbase = (base + blen - back) & ~(u64)255;
-      CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_c[nxt], 0)); /* batch b-1 has finished reading that buffer */
-      rc = upload(nbase, nxt, nblen, nfinal, nlen);
-      if (rc) return rc;
-      have_next = true;
-    }
+    if (!wait) { rc = speculate(); if (rc) return rc; } /* region bytes are all there: the next upload is queued before this batch's kernels */
     CK(cudaStreamWaitEvent(s, ctx->ev_in[cur], 0));
-    if (have_d2h[cur]) CK(cudaStreamWaitEvent(s, ctx->ev_out[cur], 0)); /* payloads of batch b-2 have left that buffer */
+    if (have_d2h[oslot]) CK(cudaStreamWaitEvent(s, ctx->ev_out[oslot], 0)); /* the payloads of the round before the previous one have left that buffer */
     CK(cudaEventRecord(ctx->ev[1], s));
     const u32 start_pos = (u32)(next_pos - base) + (nb == 0 ? first : 0u);
-    rc = run_batch(ctx, inb[cur], outb[cur], (u32)len, start_pos, (i64)base, (i64)region_len, final);
+    rc = run_batch(ctx, inb[cur], outb[oslot], ctx->out_cap, (u32)len, start_pos, (i64)base, (i64)region_len, final);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], s));
-    CK(cudaEventRecord(ctx->ev_c[cur], s));
+    CK(cudaEventRecord(ctx->ev_c[oslot], s));
+    if (wait) { rc = speculate(); if (rc) return rc; } /* streamed: waiting for the reader must not hold this batch's kernels back */
     CK(cudaStreamSynchronize(s));
     const u32 S = ctx->last_S;
     const PlanState hs = *ctx->h_state;
     if (hs.status) { ctx->err = std::string("window chaining failed: ") + phy_strerror(hs.status); return hs.status; }
-    if (S == 0 && !hs.done) { ctx->err = "a window does not fit one batch (raise max_batch_bytes)"; return PHY_ERR_CAPACITY; }
     if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
     const u64 tot = S ? ctx->h_hdr->total_out : 0;
     if (out_used + tot > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
-    if (have_d2h[cur]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[cur], ctx->ev_out[cur])); d2h_ms += t; have_d2h[cur] = false; }
-    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_c[cur], 0));
-    CK(cudaEventRecord(ctx->ev_d0[cur], ctx->s_out));
-    if (tot) CK(cudaMemcpyAsync(out + out_used, outb[cur], tot, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaEventRecord(ctx->ev_out[cur], ctx->s_out));
-    have_d2h[cur] = true;
+    if (have_d2h[oslot]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[oslot], ctx->ev_out[oslot])); d2h_ms += t; have_d2h[oslot] = false; }
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_c[oslot], 0));
+    CK(cudaEventRecord(ctx->ev_d0[oslot], ctx->s_out));
+    if (tot) CK(cudaMemcpyAsync(out + out_used, outb[oslot], tot, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaEventRecord(ctx->ev_out[oslot], ctx->s_out));
+    have_d2h[oslot] = true;
     fill_descs(ctx, S, out_used, descs + nd);
     float t;
     CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); k_ms += t;
-    nd += S; out_used += tot; ++nb;
+    nd += S; out_used += tot; ++nb; oslot ^= 1;
     done = hs.done != 0;
-    next_pos = (u64)hs.bytes_read;
     if (!done) {
-      if (final) { ctx->err = "region exhausted before the working region was covered"; return PHY_ERR_MALFORMED; }
-      if (!have_next || next_pos < nbase) {
-        /* the chain stopped early (subblock capacity): the speculative upload starts too late, redo it */
-        CK(cudaStreamSynchronize(ctx->s_in));
-        nbase = next_pos & ~(u64)255;
-        rc = upload(nbase, nxt, nblen, nfinal, nlen);
-        if (rc) return rc;
+      const u64 stopped = (u64)hs.bytes_read;
+      if (S == 0 && stopped == next_pos && (final || stopped < ((base + blen - back) & ~(u64)255))) {
+        ctx->err = final ? "region exhausted before the working region was covered" : "a window does not fit one batch (raise max_batch_bytes)";
+        return final ? PHY_ERR_MALFORMED : PHY_ERR_CAPACITY;
       }
-      base = nbase; blen = nblen; len = nlen; final = nfinal;
+      next_pos = stopped;
+      if (have_next && next_pos >= nbase) { /* on to the next batch */
+        cur ^= 1; base = nbase; blen = nblen; len = nlen; final = nfinal; have_next = false;
+      } /* else: the chain stopped early because the batch's subblock capacity was used up; the next round continues in the same bytes */
     }
   }
   CK(cudaStreamSynchronize(ctx->s_in));
   CK(cudaStreamSynchronize(ctx->s_out));
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (have_d2h[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[i], ctx->ev_out[i])); d2h_ms += t; }
-  { /* upload time: not separable per batch once copies overlap; report bytes / measured copy windows of the last two */
-    float t = 0;
-    for (int i = 0; i < 2 && i < (int)nb; ++i) if (cudaEventElapsedTime(&t, ctx->ev_h0[i], ctx->ev_in[i]) == cudaSuccess) h2d_ms += t;
-    if (nb > 2) h2d_ms = h2d_ms / 2 * nb; /* extrapolated from the last two batches */
+    if (up_timed[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_h0[i], ctx->ev_in[i])); h2d_ms += t; }
   }
-  (void)h2d_bytes;
   *inout_n_descs = nd;
   if (result) {
     memset(result, 0, sizeof *result);

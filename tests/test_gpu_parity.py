@@ -229,3 +229,29 @@ def test_baseline_size_payloads_bit_exact_against_the_compiled_reference(shape, 
                 assert (res.n_batches == 1) == (c is whole)
     finally:
         whole.close(); small.close()
+
+
+def test_more_windows_than_subblock_capacity_continue_in_the_same_bytes(oracle):
+    """A batch holds more windows than the context's subblock capacity (small windows, max_subblocks = 5): the window chain
+    stops when the capacity is used up and the next round continues in the same resident bytes -- in the final batch, in a
+    single-batch region, in the middle of a multi-batch region and on the resident legs.  Same payloads as the oracle."""
+    data = synth.fastq("100bp", 49, target_bytes=3_000_000)
+    win = 64 * 1024
+    prm = api.region_params(data.size, 1, 0, window_bytes=win)
+    want = oracle.compress_rank(data, 1, 0, window_bytes=win)["subblocks"]
+    one = api.Context(0, max_batch_bytes=8 << 20, max_subblocks=5)
+    many = api.Context(0, max_batch_bytes=1 << 20, max_subblocks=5)
+    try:
+        d1, o1, r1 = one.compress_region(data, prm)
+        assert r1.n_batches >= len(want) // 5 and api.payloads(d1, o1) == want
+        d2, o2, r2 = many.compress_region(data, prm)
+        assert r2.n_batches > r1.n_batches // 2 and api.payloads(d2, o2) == want
+        for c in (one, many):  # resident legs: one batch / several batches of a region larger than max_batch_bytes
+            c.upload(data)
+            d3, r3 = c.compress_resident(data.size, prm)
+            o3 = np.empty(r3.out_used, np.uint8)
+            assert c.download(o3) == r3.out_used
+            assert api.payloads(d3, o3) == want
+            assert (r3.n_batches > 1)
+    finally:
+        one.close(); many.close()
