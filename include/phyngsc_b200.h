@@ -109,6 +109,19 @@ int phy_compress_region_streamed(phy_ctx *ctx, const uint8_t *region, uint64_t r
                                  phy_wait_fn wait, void *user, uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs,
                                  uint32_t *inout_n_descs, phy_region_result *result);
 
+/* The region is not in memory at all: the library pulls it through `read` (called from its own reader threads, in 16 MiB
+ * pieces, straight into pinned staging memory -- no copy of the region is ever pinned or held by the caller) and hands
+ * every batch of finished subblocks to `emit` on the calling thread while later batches are still being compressed.
+ * Replaces the per-subblock MPI_File_read_at / compress / copy-to-write-buffer loop of phyNGSC.cpp:168-906 for one rank.
+ *   read(user, off, dst, n)      fill dst with region bytes [off, off + n); return n, anything else is an error.
+ *                                Must be thread-safe (pread is) and must not call MPI (MPI_THREAD_FUNNELED, phyNGSC.cpp:57).
+ *   emit(user, descs, n, bytes)  n subblocks in order; payload i is bytes + descs[i].out_off (valid until emit returns);
+ *                                a non-zero return stops the call with PHY_ERR_ARG. */
+typedef int64_t (*phy_read_fn)(void *user, uint64_t off, void *dst, uint64_t n);
+typedef int (*phy_emit_fn)(void *user, const phy_subblock_desc *descs, uint32_t n, const uint8_t *payloads);
+int phy_compress_stream(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params, phy_read_fn read, void *read_user,
+                        phy_emit_fn emit, void *emit_user, phy_region_result *result);
+
 /* The same work split into its three legs, for callers that keep data resident (and for kernel-only
  * timing): upload copies host bytes into the ctx input buffer; compress_resident runs the kernels over
  * what is resident (single batch: region_len <= max_batch_bytes) leaving payloads in device memory

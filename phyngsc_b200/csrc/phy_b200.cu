@@ -7,7 +7,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/phyngsc_b200.h"
 #include "phy_kernels.cuh"
@@ -47,8 +52,10 @@ struct phy_ctx {
   BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; SbOut *h_sbout = nullptr; PlanState *h_state = nullptr;
   u32 launches = 0;
   u64 resident_len = 0, resident_out = 0;
+  u8 *ring = nullptr, *hout[2] = {nullptr, nullptr}; cudaEvent_t ev_ring[8] = {}; /* pinned staging of phy_compress_stream */
   u8 *big_in = nullptr, *big_out = nullptr; u64 big_in_cap = 0, big_out_cap = 0; /* resident regions larger than one batch (phy_upload) */
   u32 last_S = 0;
+  u32 qcode_hint = 0; /* longest quality code the previous batch saw */
   u32 nq_hint = 0, prev_groups = 0, prev_max_len = 0; /* quality alphabet size seen by the previous batch (sizes the packed tables' shared memory without a readback) */
   /* per-kernel timing (phy_profile): one event after every launch of run_batch */
   bool profile = false;
@@ -115,7 +122,8 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
-  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl};
+  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1]};
+  for (auto &e : ctx->ev_ring) if (e) cudaEventDestroy(e);
   for (void *p : host) if (p) cudaFreeHost(p);
   for (int i = 0; i < 2; ++i) {
     cudaEvent_t evs[] = {ctx->ev_in[i], ctx->ev_c[i], ctx->ev_out[i], ctx->ev_h0[i], ctx->ev_d0[i]};
@@ -197,10 +205,14 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_dnacount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
-  CK(cudaFuncSetAttribute(k_seqstat<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
-  CK(cudaFuncSetAttribute(k_seqstat<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
-  CK(cudaFuncSetAttribute(k_seqstat<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
-  CK(cudaFuncSetAttribute(k_seqstat<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
+  CK(cudaFuncSetAttribute(k_seqstat<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_lengths<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_lengths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
@@ -253,8 +265,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   d.tmp = ctx->tmp; d.tmp_cap = ctx->tmp_cap; d.tmp_used = ctx->tmp_used;
   cudaStream_t st = ctx->stream;
   if (ctx->prev_groups) { /* the previous batch is complete (the callers synchronise): its alphabet is the hint for this one */
-    u32 mx = 0;
-    for (u32 g = 0; g < ctx->prev_groups; ++g) mx = ctx->h_hdr_g[g].max_pk_bytes > mx ? ctx->h_hdr_g[g].max_pk_bytes : mx;
+    u32 mx = 0, mq = 0;
+    for (u32 g = 0; g < ctx->prev_groups; ++g) { mx = ctx->h_hdr_g[g].max_pk_bytes > mx ? ctx->h_hdr_g[g].max_pk_bytes : mx; mq = ctx->h_hdr_g[g].max_qcode > mq ? ctx->h_hdr_g[g].max_qcode : mq; }
+    ctx->qcode_hint = mq;
     if (ctx->prev_max_len) ctx->nq_hint = mx / 2 / (ctx->prev_max_len + 1);
     ctx->prev_groups = 0;
   }
@@ -310,18 +323,25 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   static const int qdbuf_env = getenv("PHY_QD_NBUF") ? atoi(getenv("PHY_QD_NBUF")) : 0;
   u32 encG = H.max_len <= 64 ? 1u : H.max_len <= 192 ? 4u : 8u;
   if (encg_env == 1 || encg_env == 2 || encg_env == 4 || encg_env == 8) encG = (u32)encg_env;
+  while (encG < 8 && seg_len(H.max_len, encG) > 64) encG *= 2; /* a lane keeps one bit per position of its run (k_seqstat) */
+  if (!(encg_env == 1 || encg_env == 2 || encg_env == 4 || encg_env == 8))
+    while (encG < 8 && seg_len(H.max_len, encG) * (ctx->qcode_hint > 12 ? ctx->qcode_hint : 12u) > 32u * 18u) encG *= 2; /* long codes: shorter runs keep the lane-private staging small (50-205 bp, skewed quality: 1.76 vs 2.24 ms per GB) */
   d.fg.g = enc_env ? encG : 0u;
-  d.fg.lpw_q = (seg_len(H.max_len, encG) * 12u + 31u) / 32u + 2u; /* packed codes are at most 12 bits long */
+  /* lane-private staging: a lane's run of positions times the longest quality code -- 12 bits unless the previous batch
+   * of this context saw longer ones (subblocks that need more than the kernels were launched with take the two-walk path) */
+  d.fg.lpw_q = (seg_len(H.max_len, encG) * (ctx->qcode_hint > 12 ? (ctx->qcode_hint > 24 ? 24u : ctx->qcode_hint) : 12u) + 31u) / 32u + 2u;
   d.fg.pk_bytes = 0;
   d.qd_stage = ((32u / encG) * H.max_rec + 32u + 255u) & ~255u;
   if (encG == 1) d.qd_stage = (H.max_span32 + 16 + 255) & ~255u;
-  d.qd_nbuf = qdbuf_env == 1 || qdbuf_env == 2 ? (u32)qdbuf_env : (encG == 1 ? 1u : 2u);
+  d.qd_nbuf = qdbuf_env == 1 || qdbuf_env == 2 ? (u32)qdbuf_env : (encG > 1 && d.qd_stage <= 2560 ? 2u : 1u); /* measured: a second stage only pays while it is small (100 bp: 0.86 vs 0.90 ms per GB, 150 bp: 0.89 vs 0.78) */
   d.ts = (((H.max_tlen + 16u + 15u) & ~15u) | 16u);
   const u32 max_tasks = (H.max_chunks * CH + TASK_RECORDS - 1) / TASK_RECORDS;
   /* statistics: k_seqstat uses the lane split and the record stages of k_enc_qd, k_stat1 / k_stat2 stage title lines only */
   d.sq_rows = H.max_len < 1 ? 1u : H.max_len > RAW_ROWS - 1 ? RAW_ROWS - 1 : H.max_len;
-  d.sq_stage = d.qd_stage; d.sq_nbuf = 2;
-  const u32 sq_dyn = ((d.sq_rows * SQ_ROWW * 4u + 15u) & ~15u) + SQ_WARPS * d.sq_nbuf * d.sq_stage;
+  static const int sqbuf_env = getenv("PHY_SQ_NBUF") ? atoi(getenv("PHY_SQ_NBUF")) : 0;
+  d.sq_stage = d.qd_stage; d.sq_nbuf = sqbuf_env == 2 ? 2u : 1u; /* one stage: more resident CTAs hide the copy better (100 bp: 0.66 vs 0.76 ms per GB) */
+  const bool sq_wide = d.sq_rows <= 126; /* 32-bit counters while the private table stays below 48 KB, else 16-bit pairs */
+  const u32 sq_dyn = ((d.sq_rows * (sq_wide ? 97u : SQ_ROWW) * 4u + 15u) & ~15u) + SQ_WARPS * d.sq_nbuf * d.sq_stage;
   const u32 title_stat_dyn = 2u * CH * d.ts + d.max_nf * CH * 4u; /* two stages of title slots + numeric values per field and record */
   if (sq_dyn > ENC_DYN_MAX || title_stat_dyn > ENC_DYN_MAX) { ctx->err = "records too long for the statistics kernels' shared memory"; return PHY_ERR_UNSUPPORTED; }
   /* Subblock groups: the subblocks of the batch are split into G consecutive groups that run the rest of the pipeline on
@@ -348,8 +368,8 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     e.plans += b; e.acc += b; e.cls += b; e.sbout += b; e.arena += (size_t)b * ctx->arena_words;
     e.hdr = ctx->hdr_g + g;
     e.prev_total = g ? &ctx->hdr_g[g - 1].total_out : nullptr;
-    BatchHdr hg = H; /* device-side consumers read S and status; max_pk_bytes / total_out are produced per group */
-    hg.S = s0[g + 1] - s0[g]; hg.max_pk_bytes = 0; hg.total_out = 0; hg.out_begin = 0;
+    BatchHdr hg = H; /* device-side consumers read S and status; max_pk_bytes / max_qcode / total_out are produced per group */
+    hg.S = s0[g + 1] - s0[g]; hg.max_pk_bytes = 0; hg.max_qcode = 0; hg.total_out = 0; hg.out_begin = 0;
     ctx->h_hdr_g[g] = hg;
   }
   /* phase 1 (statistics) of every group, then phase 2 (coding) once the group's packed-table size is known on the host */
@@ -366,12 +386,14 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     k_zero_raw<<<dim3(4, Sg), 256, 0, gs>>>(e);
     {
       const dim3 g_sq((max_tasks + SQ_WARPS - 1) / SQ_WARPS, Sg);
+#define PHY_SQ(G_) do { if (sq_wide) k_seqstat<G_, true><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); else k_seqstat<G_, false><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); } while (0)
       switch (encG) {
-        case 1: k_seqstat<1><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
-        case 2: k_seqstat<2><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
-        case 4: k_seqstat<4><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
-        default: k_seqstat<8><<<g_sq, SQ_WARPS * 32, sq_dyn, gs>>>(e); break;
+        case 1: PHY_SQ(1); break;
+        case 2: PHY_SQ(2); break;
+        case 4: PHY_SQ(4); break;
+        default: PHY_SQ(8); break;
       }
+#undef PHY_SQ
     }
     GMARK();
     k_classify<<<Sg, 32, 0, gs>>>(e); GMARK();
@@ -431,7 +453,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     k_outscan<<<1, 256, 0, gs>>>(e); GMARK();
     if (G > 1) CK(cudaEventRecord(ctx->ev_scan[g], gs));
     k_zero_out<<<148 * 4, 256, 0, gs>>>(e); GMARK();
-    if (e.fg.g) k_place<<<dim3(32, Sg), 256, 0, gs>>>(e);
+    if (e.fg.g) k_place<<<dim3(64, Sg), 256, 0, gs>>>(e);
     GMARK();
     if (pair) k_emit<true><<<ge_pair, EW * 32, pair_dyn, gs>>>(e);
     else k_emit<false><<<ge_solo, EW * 32, solo_dyn, gs>>>(e);
@@ -471,7 +493,7 @@ static int init_plan(phy_ctx *ctx, const uint8_t *region_host, u64 region_len, c
   if (p->rank != 0) {
     if (have_first) first = first_rec_start_known;
     else {
-      int64_t f = phy_find_first_record(region_host, region_len);
+      int64_t f = phy_find_first_record(region_host, region_len < (1u << 20) ? region_len : (1u << 20)); /* the caller has waited for this much */
       if (f < 0) { ctx->err = "no record start found at the beginning of the region"; return (int)f; }
       first = (u32)f;
     }
@@ -623,20 +645,81 @@ static int pipeline_init(phy_ctx *ctx) {
   return PHY_OK;
 }
 
+/* ---- streamed host I/O (phy_compress_stream) ------------------------------------------------------------------------- */
+/* The caller's region is not in memory: reader threads pull it chunk by chunk through the caller's read callback into a
+ * ring of pinned staging slots, the uploads consume the chunks in order, payloads come back into two pinned output slots and
+ * are handed to the caller's emit callback one batch behind the kernels. */
+static const u64 RING_CHUNK = 16ull << 20;
+static const int RING_SLOTS = 4;
+struct StreamIO {
+  phy_read_fn read = nullptr; void *ruser = nullptr; phy_emit_fn emit = nullptr; void *euser = nullptr;
+  phy_ctx *ctx = nullptr; u64 region_len = 0, nchunks = 0;
+  std::mutex m; std::condition_variable cv;
+  u64 ready[RING_SLOTS] = {0, 0, 0, 0};     /* slot holds chunk ready - 1 (0: nothing yet)                        */
+  u64 consumed[RING_SLOTS] = {0, 0, 0, 0};  /* uploads of chunk consumed - 1 from this slot have been enqueued       */
+  bool failed = false, stop = false;
+  std::vector<std::thread> readers;
+  /* pending emit (one batch behind) */
+  std::vector<phy_subblock_desc> pend; int pend_slot = -1;
+
+  void reader_main(int t, int nthreads) {
+    cudaSetDevice(ctx->device);
+    for (u64 k = (u64)t; k < nchunks; k += (u64)nthreads) {
+      const int slot = (int)(k % RING_SLOTS);
+      {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return stop || k < (u64)RING_SLOTS || consumed[slot] == k - RING_SLOTS + 1; });
+        if (stop) return;
+      }
+      if (k >= (u64)RING_SLOTS) cudaEventSynchronize(ctx->ev_ring[slot]); /* the copies out of the slot's previous chunk are done */
+      const u64 off = k * RING_CHUNK, n = region_len - off < RING_CHUNK ? region_len - off : RING_CHUNK;
+      const int64_t got = read(ruser, off, ctx->ring + (u64)slot * RING_CHUNK, n);
+      {
+        std::lock_guard<std::mutex> g(m);
+        if (got != (int64_t)n) failed = true;
+        ready[slot] = k + 1;
+      }
+      cv.notify_all();
+      if (got != (int64_t)n) return;
+    }
+  }
+  /* blocks until chunk k is in its slot; nullptr on a read failure */
+  const u8 *chunk(u64 k) {
+    const int slot = (int)(k % RING_SLOTS);
+    std::unique_lock<std::mutex> g(m);
+    cv.wait(g, [&] { return failed || ready[slot] == k + 1; });
+    return failed ? nullptr : ctx->ring + (u64)slot * RING_CHUNK;
+  }
+  void release(u64 k) { { std::lock_guard<std::mutex> g(m); consumed[k % RING_SLOTS] = k + 1; } cv.notify_all(); }
+  void shutdown() {
+    { std::lock_guard<std::mutex> g(m); stop = true; }
+    cv.notify_all();
+    for (auto &t : readers) if (t.joinable()) t.join();
+    readers.clear();
+  }
+  ~StreamIO() { shutdown(); }
+};
+
 /* Pipelined over batches: while batch b is compressed, batch b+1 streams host -> device on a second stream and
  * the payloads of batch b-1 stream device -> host on a third (double-buffered input and output).  The start of
  * batch b+1 does not depend on batch b's result: it is placed one window + slack before the end of batch b, which
  * is never past the point where the window chain stops in batch b. */
 static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,
                                 phy_wait_fn wait, void *wait_user, uint8_t *out, uint64_t out_cap, phy_subblock_desc *descs,
-                                uint32_t *inout_n_descs, phy_region_result *result) {
-  if (!ctx || !region || !out || !descs || !inout_n_descs || region_len == 0) return PHY_ERR_ARG;
+                                uint32_t *inout_n_descs, phy_region_result *result, StreamIO *io = nullptr) {
+  if (!ctx || region_len == 0) return PHY_ERR_ARG;
+  if (!io && (!region || !out || !descs || !inout_n_descs)) return PHY_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   /* `wait` (streamed variant): region[0, upto) is only valid after wait(user, upto) has returned */
   auto need = [&](u64 upto) { if (wait) wait(wait_user, upto < region_len ? upto : region_len); };
   PlanState st;
   if (params && params->rank != 0) need(1u << 20); /* the '@' heuristic looks at the head of the region */
-  int rc = init_plan(ctx, region, region_len, params, 0, false, st);
+  const uint8_t *head = region;
+  if (io) { /* streamed I/O: the head of the region is the head of chunk 0 */
+    head = io->chunk(0);
+    if (!head) { ctx->err = "reading the region failed"; return PHY_ERR_ARG; }
+  }
+  int rc = init_plan(ctx, head, region_len, params, 0, false, st);
   if (rc) return rc;
   const u32 first = st.rec_start;
   *ctx->h_state = st;
@@ -652,8 +735,11 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
   u8 *inb[2] = {ctx->in, multi ? ctx->in2 : ctx->in}, *outb[2] = {ctx->out, ctx->out2};
   const u64 back = batch_back(ctx, params);
   if (multi && ctx->max_batch < 2 * back + 4096) { ctx->err = "max_batch_bytes is too small for the window size"; return PHY_ERR_CAPACITY; }
-  const u32 cap_descs = *inout_n_descs;
-  u32 nd = 0, nb = 0, nup = 0;
+  std::vector<phy_subblock_desc> batch_descs; /* streamed I/O: descriptors of one batch at a time */
+  if (io) { batch_descs.resize(ctx->max_sb); descs = batch_descs.data(); }
+  const u32 cap_descs = io ? ctx->max_sb : *inout_n_descs;
+  u32 nd = 0, nb = 0, nup = 0, nd_total = 0;
+  u64 bytes_in_total = 0, bytes_out_total = 0;
   u64 out_used = 0, next_pos = 0;
   float k_ms = 0, h2d_ms = 0, d2h_ms = 0;
   int worst = 0;
@@ -679,12 +765,31 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
     }
     /* host bytes in pieces: with a reader still filling the region (streamed variant) a piece crosses PCIe as soon as it is there */
     const u64 piece = 16ull << 20;
-    for (u64 o = carry; o < blen; o += piece) {
-      const u64 n = blen - o < piece ? blen - o : piece;
-      need(base + o + n);
-      CK(cudaMemcpyAsync(inb[slot] + o, region + base + o, n, cudaMemcpyHostToDevice, ctx->s_in));
+    u8 last_byte = '\n';
+    for (u64 o = carry; o < blen;) {
+      u64 n = blen - o < piece ? blen - o : piece;
+      const u8 *src;
+      if (io) { /* the part of this piece that lies in one chunk of the ring */
+        const u64 off = base + o, k = off / RING_CHUNK, in_chunk = off - k * RING_CHUNK;
+        const u8 *c = io->chunk(k);
+        if (!c) { ctx->err = "reading the region failed"; return PHY_ERR_ARG; }
+        const u64 chunk_len = region_len - k * RING_CHUNK < RING_CHUNK ? region_len - k * RING_CHUNK : RING_CHUNK;
+        if (n > chunk_len - in_chunk) n = chunk_len - in_chunk;
+        src = c + in_chunk;
+        CK(cudaMemcpyAsync(inb[slot] + o, src, n, cudaMemcpyHostToDevice, ctx->s_in));
+        if (in_chunk + n == chunk_len) { /* the chunk has been consumed: its slot may be refilled once this copy is done */
+          CK(cudaEventRecord(ctx->ev_ring[k % RING_SLOTS], ctx->s_in));
+          io->release(k);
+        }
+      } else {
+        need(base + o + n);
+        src = region + base + o;
+        CK(cudaMemcpyAsync(inb[slot] + o, src, n, cudaMemcpyHostToDevice, ctx->s_in));
+      }
+      if (base + o + n == region_len) last_byte = src[n - 1];
+      o += n;
     }
-    if (final) patch_nl = st.is_last && region[region_len - 1] != '\n';
+    if (final) patch_nl = st.is_last && last_byte != '\n';
     if (final && patch_nl) { /* last rank whose file does not end in a newline: the reference's arithmetic still places the
                               * next record start one byte past the end; a virtual newline gives the splitter the same view */
       CK(cudaMemcpyAsync(inb[slot] + blen, ctx->h_nl, 64, cudaMemcpyHostToDevice, ctx->s_in));
@@ -718,7 +823,8 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
     return r;
   };
   while (!done) {
-    if (!wait) { rc = speculate(); if (rc) return rc; } /* region bytes are all there: the next upload is queued before this batch's kernels */
+    const bool late = wait != nullptr || io != nullptr; /* bytes may not be there yet: waiting for them must not hold this batch's kernels back */
+    if (!late) { rc = speculate(); if (rc) return rc; } /* region bytes are all there: the next upload is queued before this batch's kernels */
     CK(cudaStreamWaitEvent(s, ctx->ev_in[cur], 0));
     if (have_d2h[oslot]) CK(cudaStreamWaitEvent(s, ctx->ev_out[oslot], 0)); /* the payloads of the round before the previous one have left that buffer */
     CK(cudaEventRecord(ctx->ev[1], s));
@@ -727,21 +833,32 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], s));
     CK(cudaEventRecord(ctx->ev_c[oslot], s));
-    if (wait) { rc = speculate(); if (rc) return rc; } /* streamed: waiting for the reader must not hold this batch's kernels back */
+    if (late) { rc = speculate(); if (rc) return rc; }
     CK(cudaStreamSynchronize(s));
     const u32 S = ctx->last_S;
     const PlanState hs = *ctx->h_state;
     if (hs.status) { ctx->err = std::string("window chaining failed: ") + phy_strerror(hs.status); return hs.status; }
+    if (io) { nd = 0; out_used = 0; } /* every batch goes to its own pinned output slot and descriptor list */
     if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
     const u64 tot = S ? ctx->h_hdr->total_out : 0;
-    if (out_used + tot > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
+    if (!io && out_used + tot > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
+    uint8_t *hdst = io ? ctx->hout[oslot] : out + out_used;
     if (have_d2h[oslot]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[oslot], ctx->ev_out[oslot])); d2h_ms += t; have_d2h[oslot] = false; }
     CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_c[oslot], 0));
     CK(cudaEventRecord(ctx->ev_d0[oslot], ctx->s_out));
-    if (tot) CK(cudaMemcpyAsync(out + out_used, outb[oslot], tot, cudaMemcpyDeviceToHost, ctx->s_out));
+    if (tot) CK(cudaMemcpyAsync(hdst, outb[oslot], tot, cudaMemcpyDeviceToHost, ctx->s_out));
     CK(cudaEventRecord(ctx->ev_out[oslot], ctx->s_out));
     have_d2h[oslot] = true;
     fill_descs(ctx, S, out_used, descs + nd);
+    for (u32 i = 0; i < S; ++i) { bytes_in_total += descs[nd + i].bytes_consumed; bytes_out_total += descs[nd + i].out_len; if (descs[nd + i].status < worst) worst = descs[nd + i].status; }
+    nd_total += S;
+    if (io) { /* hand the previous batch to the caller (its payloads have arrived meanwhile), remember this one */
+      if (io->pend_slot >= 0) {
+        CK(cudaEventSynchronize(ctx->ev_out[io->pend_slot]));
+        if (io->emit(io->euser, io->pend.data(), (uint32_t)io->pend.size(), ctx->hout[io->pend_slot])) { ctx->err = "the emit callback stopped the call"; return PHY_ERR_ARG; }
+      }
+      io->pend.assign(descs, descs + S); io->pend_slot = oslot;
+    }
     float t;
     CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); k_ms += t;
     nd += S; out_used += tot; ++nb; oslot ^= 1;
@@ -764,16 +881,42 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
     if (have_d2h[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[i], ctx->ev_out[i])); d2h_ms += t; }
     if (up_timed[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_h0[i], ctx->ev_in[i])); h2d_ms += t; }
   }
-  *inout_n_descs = nd;
+  if (io && io->pend_slot >= 0) { /* the last batch */
+    if (io->emit(io->euser, io->pend.data(), (uint32_t)io->pend.size(), ctx->hout[io->pend_slot])) { ctx->err = "the emit callback stopped the call"; return PHY_ERR_ARG; }
+    io->pend_slot = -1;
+  }
+  if (inout_n_descs) *inout_n_descs = io ? nd_total : nd;
   if (result) {
     memset(result, 0, sizeof *result);
-    result->n_subblocks = nd; result->n_batches = nb; result->wr_overlap = (int32_t)first; result->kernel_launches = ctx->launches;
-    result->kernel_ms = k_ms; result->h2d_ms = h2d_ms; result->d2h_ms = d2h_ms; result->out_used = out_used;
-    for (u32 i = 0; i < nd; ++i) { result->bytes_in += descs[i].bytes_consumed; result->bytes_out += descs[i].out_len; }
+    result->n_subblocks = nd_total; result->n_batches = nb; result->wr_overlap = (int32_t)first; result->kernel_launches = ctx->launches;
+    result->kernel_ms = k_ms; result->h2d_ms = h2d_ms; result->d2h_ms = d2h_ms; result->out_used = io ? bytes_out_total : out_used;
+    result->bytes_in = bytes_in_total; result->bytes_out = bytes_out_total;
   }
-  for (u32 i = 0; i < nd; ++i) if (descs[i].status < worst) worst = descs[i].status;
   if (worst) ctx->err = std::string("a subblock failed: ") + phy_strerror(worst);
   return worst;
+}
+
+extern "C" int phy_compress_stream(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params, phy_read_fn read, void *read_user,
+                                   phy_emit_fn emit, void *emit_user, phy_region_result *result) {
+  if (!ctx || !params || !read || !emit || region_len == 0) return PHY_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = pipeline_init(ctx);
+  if (rc) return rc;
+  if (!ctx->ring) {
+    CK(cudaHostAlloc(&ctx->ring, RING_CHUNK * RING_SLOTS, cudaHostAllocDefault));
+    for (int i = 0; i < 2; ++i) CK(cudaHostAlloc(&ctx->hout[i], ctx->out_cap + 64, cudaHostAllocDefault));
+    for (int i = 0; i < RING_SLOTS; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
+  }
+  StreamIO io;
+  io.read = read; io.ruser = read_user; io.emit = emit; io.euser = emit_user; io.ctx = ctx; io.region_len = region_len;
+  io.nchunks = (region_len + RING_CHUNK - 1) / RING_CHUNK;
+  static const int nreaders_env = getenv("PHY_READERS") ? atoi(getenv("PHY_READERS")) : 2;
+  const int nreaders = nreaders_env < 1 ? 1 : nreaders_env > RING_SLOTS ? RING_SLOTS : nreaders_env;
+  for (int t = 0; t < nreaders; ++t) io.readers.emplace_back([&io, t, nreaders] { io.reader_main(t, nreaders); });
+  rc = compress_region_impl(ctx, nullptr, region_len, params, nullptr, nullptr, nullptr, 0, nullptr, nullptr, result, &io);
+  io.shutdown();
+  cudaStreamSynchronize(ctx->s_in); /* a failed call may leave copies out of the ring in flight */
+  return rc;
 }
 
 extern "C" int phy_compress_region(phy_ctx *ctx, const uint8_t *region, uint64_t region_len, const phy_region_params *params,

@@ -50,13 +50,12 @@ struct WarpStream {
   __device__ __forceinline__ void flush(u32 bits) {
     const u32 lane = threadIdx.x & 31;
     const u32 nf = st.full_words(bits);
-    if (st.tpos + nf + 1 > slot_words) over = true;
-    else for (u32 j = lane; j < nf; j += 32) slot[st.tpos + j] = cc[j];
-    const u32 rem = cc[nf];
+    const bool room = st.tpos + nf + 1 <= slot_words;
+    if (!room) over = true;
+    for (u32 j = lane; j < nf; j += 32) { const u32 v = cc[j]; if (room) slot[st.tpos + j] = v; cc[j] = 0; }
+    const u32 rem = cc[nf]; /* no lane clears this word in the loop above */
     __syncwarp();
-    for (u32 j = lane; j <= nf; j += 32) cc[j] = 0;
-    __syncwarp();
-    if (lane == 0) cc[0] = rem;
+    if (lane == 0) { cc[nf] = 0; cc[0] = rem; }
     __syncwarp();
     st.advance(bits);
   }
@@ -66,8 +65,14 @@ struct WarpStream {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += y; }
     const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - nbits;
+    if (total <= (CCW - 2) * 32 - st.carry) { /* the common case: everything fits at once */
+      if (nbits) lane_concat(cc, st.carry + excl, lp, 32u, nbits);
+      __syncwarp();
+      flush(total);
+      return;
+    }
     u32 base = 0;
-    while (base < total) { /* one turn in the common case */
+    while (base < total) {
       const u32 room = (CCW - 2) * 32 - st.carry;
       const bool go = excl >= base && incl - base <= room;
       const u32 end = __reduce_max_sync(0xFFFFFFFFu, go ? incl : base);
@@ -102,7 +107,8 @@ __global__ void __launch_bounds__(32) k_slots(Dev d) {
   const u32 tb = __reduce_add_sync(0xFFFFFFFFu, title_bound_part(C, arena, td, lane, 32u));
   if (lane) return;
   const u32 pk_bytes = (C.max_qlen + 1) * C.nq * 2u;
-  if (C.qpk_bad || C.qpk_esc || pk_bytes > d.fg.pk_bytes) fast = false; /* the walkers of the single-walk kernels read the packed tables from shared memory */
+  if (C.qpk_bad || pk_bytes > d.fg.pk_bytes) fast = false; /* the walkers of the single-walk kernels read the packed tables from shared memory */
+  atomicMax(&d.hdr->max_qcode, qmax);
   const u32 g = d.fg.g ? d.fg.g : 1u, seg = seg_len(C.max_qlen, g);
   const u32 dper = C.plain ? 2u : td[C.tdna].maxlen;
   if (seg * qmax > 32u * (d.fg.lpw_q - 1) || seg * dper > 32u * (d.fg.lpw_q - 1)) fast = false;
@@ -304,10 +310,24 @@ __device__ __forceinline__ void place_run(u32 *outw, u64 dbit, const u32 *src, u
   if (!nbits) return;
   const u32 lane = threadIdx.x & 31, sh = (u32)(dbit & 31), nsrc = (nbits + 31) / 32, nd = (sh + nbits + 31) / 32;
   u32 *dst = outw + (dbit >> 5);
-  for (u32 j = lane; j < nd; j += 32) {
-    const u32 v = bswap32(shifted_word(src, nsrc, sh, j));
-    const bool shared = (j == 0 && sh) || (j == nd - 1 && ((sh + nbits) & 31u));
-    if (shared) { if (v) atomicOr(dst + j, v); } else dst[j] = v;
+  /* words 1 .. nd-2 belong to this run alone: plain stores, four per lane in flight; the first and the last word may be
+   * shared with a neighbouring run */
+  u32 j = 1 + lane;
+  for (; j + 96 < nd - 1; j += 128) {
+    const u32 a0 = src[j - 1], a1 = src[j], b0 = src[j + 31], b1 = src[j + 32], c0 = src[j + 63], c1 = src[j + 64], d0 = src[j + 95], d1 = src[j + 96];
+    dst[j] = bswap32(sh ? (a0 << (32 - sh)) | (a1 >> sh) : a1);
+    dst[j + 32] = bswap32(sh ? (b0 << (32 - sh)) | (b1 >> sh) : b1);
+    dst[j + 64] = bswap32(sh ? (c0 << (32 - sh)) | (c1 >> sh) : c1);
+    dst[j + 96] = bswap32(sh ? (d0 << (32 - sh)) | (d1 >> sh) : d1);
+  }
+  for (; j + 1 < nd; j += 32) dst[j] = bswap32(shifted_word(src, nsrc, sh, j));
+  if (lane < 2) {
+    const u32 e = lane ? nd - 1 : 0u;
+    if (lane == 0 || nd > 1) {
+      const u32 v = bswap32(shifted_word(src, nsrc, sh, e));
+      const bool shared = (e == 0 && sh) || (e == nd - 1 && ((sh + nbits) & 31u));
+      if (shared) { if (v) atomicOr(dst + e, v); } else dst[e] = v;
+    }
   }
 }
 
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(256) k_place(Dev d) {
   const u32 ni = (u32)((info_bits + 32ull * PIECE_WORDS - 1) / (32ull * PIECE_WORDS));
   const u32 cq = (C.strd_q + PIECE_WORDS - 1) / PIECE_WORDS, cd = (C.strd_d + PIECE_WORDS - 1) / PIECE_WORDS, ct = (C.strd_t + PIECE_WORDS - 1) / PIECE_WORDS;
   const u32 per_task = cq + cd + ct, npieces = ni + ntask * per_task;
-  const u64 bit0[3] = {(obase + o_qual + C.qhdr_len) * 8, (obase + o_dna + C.dhdr_len) * 8, (obase + o_title + C.thdr_len) * 8};
+  const u64 bit_q = (obase + o_qual + C.qhdr_len) * 8, bit_d = (obase + o_dna + C.dhdr_len) * 8, bit_t = (obase + o_title + C.thdr_len) * 8;
   for (u32 p = blockIdx.x * 8 + w; p < npieces; p += gridDim.x * 8) {
     if (p < ni) { /* info length bits: one dense run per subblock */
       const u64 b0 = (u64)p * PIECE_WORDS * 32;
@@ -357,7 +377,7 @@ __global__ void __launch_bounds__(256) k_place(Dev d) {
     const u32 nb = min(PIECE_WORDS * 32, bits - b0);
     const u32 *src = tmp + C.info_words + (size_t)task * strd + (kind == 0 ? 0u : kind == 1 ? C.strd_q : C.strd_q + C.strd_d) + piece * PIECE_WORDS;
     const u64 tb = (u64)base3[kind * ntask + task] * (kind == 2 ? 8u : 1u);
-    place_run(outw, bit0[kind] + tb + b0, src, nb);
+    place_run(outw, (kind == 0 ? bit_q : kind == 1 ? bit_d : bit_t) + tb + b0, src, nb);
   }
 }
 

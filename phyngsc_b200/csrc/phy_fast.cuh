@@ -49,13 +49,10 @@ struct PtrStore {
 template <class Store>
 struct LaneSinkT {
   u32 lo, hi, fill, nwords, cap;
-  bool over; /* more words than the staging holds (the caller's bound was wrong): nothing is written past the end */
+  bool over; /* more words than the staging holds: cannot happen when the caller's bound holds (k_slots checks it before a subblock takes this path) */
   Store st;
   PHY_HD void init(const Store &store_, u32 cap_words) { lo = hi = 0; fill = 0; nwords = 0; cap = cap_words; over = false; st = store_; }
-  PHY_HD void store(u32 w) {
-    if (nwords < cap) st.put(w); else over = true;
-    st.next(); ++nwords;
-  }
+  PHY_HD void store(u32 w) { st.put(w); st.next(); ++nwords; }
   PHY_HD void put(u32 v, u32 n) { /* n <= 32, v < 2^n */
     hi = shl_c(lo, hi, n);
     lo = shl_c(0u, lo, n) | v;
@@ -66,6 +63,7 @@ struct LaneSinkT {
   PHY_HD u32 finish() {
     const u32 n = 32u * nwords + fill;
     if (fill) { store(lo << (32 - fill)); fill = 0; }
+    over = nwords > cap;
     return n;
   }
 };

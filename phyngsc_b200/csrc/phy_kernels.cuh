@@ -66,6 +66,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u32 max_len;         /* longest sequence line of the batch's subblocks */
   u32 max_span64, max_span32; /* widest 64- / 32-record span (k_qhist may stage smaller groups than the 128-record chunk) */
   u32 max_rec, max_tlen;      /* longest record and longest title line (both with their newline) */
+  u32 max_qcode, pad_hdr;     /* longest quality code of the batch's subblocks (sizes the next batch's lane-private staging) */
 };
 
 struct SbOut {         /* device -> host, one per subblock */
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0; d.hdr->max_rec = 0; d.hdr->max_tlen = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0; d.hdr->max_rec = 0; d.hdr->max_tlen = 0; d.hdr->max_qcode = 0; d.hdr->pad_hdr = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -1244,8 +1245,9 @@ __device__ __forceinline__ void quality_walk(const u8 *qp, const u8 *sp, u32 L, 
 }
 template <class Sink>
 __device__ __forceinline__ void dna_walk(const u8 *sp, u32 L, bool xfer, const WalkTabs &T, Sink &s) {
-  const bool wx = __any_sync(__activemask(), xfer);
-  if (T.dna_mode == 2 && !wx) {
+  if (T.dna_mode == 2) {
+    /* alphabet exactly A, C, G, T: four bases per step, sixteen per append.  A byte that is not one of the four can only
+     * be a transferred ambiguity code (anything else would be in the alphabet): it is left out (phyNGSC.cpp:549-588). */
     const u32 a = (u32)(size_t)sp & 3u;
     const u32 *wp = (const u32 *)(sp - a);
     u32 w0 = wp[0], acc = 0, cnt = 0, j = 0;
@@ -1253,12 +1255,26 @@ __device__ __forceinline__ void dna_walk(const u8 *sp, u32 L, bool xfer, const W
       const u32 w1 = *++wp;
       const u32 v = __funnelshift_r(w0, w1, a * 8);
       w0 = w1;
-      const u32 z = ((v >> 1) & 0x03030303u) ^ ((v >> 2) & 0x01010101u);
-      acc = (acc << 8) | ((z * 0x40100401u) >> 24);
-      cnt += 4;
-      if (cnt == 16) { s.put(acc, 32); acc = 0; cnt = 0; }
+      const u32 zz = (v >> 1) & 0x03030303u;
+      const u32 bad = __byte_perm(0x47544341u, 0, __byte_perm(zz | (zz >> 4), 0, 0x4420)) ^ v;
+      const u32 z = zz ^ ((v >> 2) & 0x01010101u);
+      if (bad == 0) {
+        acc = (acc << 8) | ((z * 0x40100401u) >> 24);
+        cnt += 4;
+        if (cnt == 16) { s.put(acc, 32); acc = 0; cnt = 0; }
+      } else { /* rare: what is pending goes out first, so that cnt stays a multiple of four in the steps above */
+        s.put(acc, 2 * cnt); acc = 0; cnt = 0;
+#pragma unroll
+        for (u32 t = 0; t < 4; ++t)
+          if (((bad >> (8 * t)) & 0xFFu) == 0) s.put((z >> (8 * t)) & 3u, 2);
+      }
     }
-    for (; j < L; ++j) { acc = (acc << 2) | T.smap[sp[j]]; ++cnt; }
+    for (; j < L; ++j) {
+      const u8 c = sp[j];
+      if (T.xq[c]) continue;
+      acc = (acc << 2) | T.smap[c];
+      if (++cnt == 16) { s.put(acc, 32); acc = 0; cnt = 0; }
+    }
     s.put(acc, 2 * cnt);
     return;
   }

@@ -44,10 +44,30 @@ template <int G> __device__ __forceinline__ u32 grp_add(u32 v) {
   return v;
 }
 
-/* dynamic shared memory: [sq_rows * SQ_ROWW words: private table][per warp: sq_nbuf stages of sq_stage bytes] */
-template <int G>
+__device__ __forceinline__ u32 lds_u32(u32 addr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+/* red.shared with an immediate byte offset (the four positions of a step lie in consecutive rows) */
+template <int OFF> __device__ __forceinline__ void sm_red_add_at(u32 addr, u32 v) { asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory"); }
+
+/* One step of four read positions: counters of the private table.  WIDE: 32-bit counters, 97 words per row, the byte
+ * itself indexes the row (row base shifted by -33).  Packed: 16-bit counters two per word, 49 words per row. */
+template <bool WIDE> struct SqRow {
+  static constexpr u32 ROWB = WIDE ? 97u * 4u : SQ_ROWW * 4u; /* bytes per row */
+  template <int I> static __device__ __forceinline__ void count(u32 rowbase, u32 vq) {
+    const u32 c = __byte_perm(vq, 0, 0x4440 + I); /* byte I, zero-extended */
+    if (WIDE) sm_red_add_at<I * (int)ROWB>(rowbase + c * 4u, 1u);
+    else { const u32 k = c - 33u; sm_red_add_at<I * (int)ROWB>(rowbase + (k >> 1) * 4u, 1u << ((k & 1u) * 16u)); }
+  }
+  static __device__ __forceinline__ void count_byte(u32 rowbase, u32 q) { /* q in 33..127 */
+    if (WIDE) sm_red_add(rowbase + q * 4u, 1u);
+    else { const u32 k = q - 33u; sm_red_add(rowbase + (k >> 1) * 4u, 1u << ((k & 1u) * 16u)); }
+  }
+};
+
+/* dynamic shared memory: [private table: sq_rows rows][per warp: sq_nbuf stages of sq_stage bytes] */
+template <int G, bool WIDE>
 __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
   constexpr u32 RW = 32 / G;
+  typedef SqRow<WIDE> Row;
   extern __shared__ uint4 dyn_smem[];
   __shared__ u32 s_dna[256];
   __shared__ u32 s_maxq, s_maxs, s_invminq;
@@ -61,7 +81,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
   if (P.status || blockIdx.x * SQ_WARPS >= ntask) return;
   const u32 task = blockIdx.x * SQ_WARPS + w;
   u32 *hist = (u32 *)dyn_smem;
-  const u32 hist_words = d.sq_rows * SQ_ROWW, hist_a = (u32)__cvta_generic_to_shared(hist);
+  const u32 hist_words = d.sq_rows * (Row::ROWB / 4), hist_a = (u32)__cvta_generic_to_shared(hist);
   for (u32 i = tid; i < hist_words; i += SQ_WARPS * 32) hist[i] = 0;
   for (u32 i = tid; i < 256; i += SQ_WARPS * 32) { s_dna[i] = 0; dlut[i] = (u8)(i == 'A' ? 1 : i == 'C' ? 2 : i == 'T' ? 4 : i == 'G' ? 8 : 0); }
   load_xq(xq);
@@ -84,6 +104,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
   if (fits && lane == 0) for (u32 k = 0; k < nbuf && k < nround; ++k) request(k);
   u32 phases = 0;
   const u32 sub = lane / G, part = lane % G;
+  const u32 rb0 = hist_a - (WIDE ? 33u * 4u : 0u); /* row base of position 0 (WIDE: the byte value indexes the row directly) */
   u32 n_te = 0, n_se = 0, n_nx = 0;
   if (fits && nround) { const u32 r = P.first_rec + min(rec0 + sub, rec1 - 1); n_te = d.te[r]; n_se = d.se[r]; n_nx = d.rstart[r + 1]; }
   u32 w_pres = 0, w_maxq = 0, w_maxs = 0, w_invminq = 0;
@@ -94,61 +115,92 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
     if (k + 1 < nround) { const u32 r = P.first_rec + min(rec0 + (k + 1) * RW + sub, rec1 - 1); n_te = d.te[r]; n_se = d.se[r]; n_nx = d.rstart[r + 1]; }
     const u32 sb = k % nbuf;
     mbar_wait(bar_a + 8 * sb, (phases >> sb) & 1u); phases ^= 1u << sb;
-    const u8 *b = wb + sb * stage_bytes - (r_lo[w][k] & ~15u);
+    const u32 b_a = stage_a + sb * stage_bytes - (r_lo[w][k] & ~15u); /* shared address of batch position 0 */
     const u32 L = se - te - 1;
     bool rec_ok = active;
     if (active && part == 0) { /* the four-line shape (phyNGSC.cpp:466-471 assumes it) */
-      if (L == 0 || b[se + 1] != '+' || b[se + 2] != '\n' || nx != 2 * se - te + 3) { err = E_MALFORMED; rec_ok = false; }
+      if (L == 0 || lds_u8(b_a + se + 1) != '+' || lds_u8(b_a + se + 2) != '\n' || nx != 2 * se - te + 3) { err = E_MALFORMED; rec_ok = false; }
       else if (L > (u32)MAX_READ || L + 1 > RAW_ROWS) { err = E_UNSUPPORTED; rec_ok = false; } /* the raw quality table has RAW_ROWS rows */
       else if (i == 0) { /* colour space, phyNGSC.cpp:473-487: not implemented */
-        const u8 c0b = b[te + 1], c1b = b[te + 2];
+        const u32 c0b = lds_u8(b_a + te + 1), c1b = lds_u8(b_a + te + 2);
         if ((c0b >= '0' && c0b <= '3') || (c1b >= '0' && c1b <= '3')) err = E_COLORSPACE;
       }
     }
     rec_ok = __shfl_sync(0xFFFFFFFFu, rec_ok, lane & ~(G - 1)) != 0;
     const u32 seg = seg_len(L, G);
     const u32 a = rec_ok ? min(L, part * seg) : 0u, n = rec_ok ? min(L, a + seg) - a : 0u;
-    const u8 *sp = b + te + 1 + a;
-    const u32 q_a = stage_a + sb * stage_bytes + (se + 3 + a - (r_lo[w][k] & ~15u)); /* shared address of this lane's first quality byte */
-    /* bases of this lane's run, four per step: the 2-bit index (c >> 1) & 3 selects the byte the base must equal
-     * ("ACTG"[idx]) and a one-hot presence byte with two byte permutes */
-    u32 bad = 0, ph = 0;
-    {
-      const u32 al = (u32)(size_t)sp & 3u;
-      const u32 *wp = (const u32 *)(sp - al);
-      u32 w0 = wp[0], j = 0;
-      for (; j + 4 <= n; j += 4) {
-        const u32 w1 = *++wp;
-        const u32 v = __funnelshift_r(w0, w1, al * 8);
-        w0 = w1;
-        const u32 z = (v >> 1) & 0x03030303u;
-        const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
-        bad |= __byte_perm(0x47544341u, 0, sel) ^ v;
-        ph |= __byte_perm(0x08040201u, 0, sel);
-      }
-      for (; j < n; ++j) { const u32 f = dlut[sp[j]]; ph |= f; bad |= f ? 0u : 1u; }
-    }
-    u32 xfer = 0, namb = 0;
-    if (__any_sync(0xFFFFFFFFu, bad != 0)) { /* some base of the round is not A/C/G/T: ambiguity transfer per record (phyNGSC.cpp:549-588) */
-      const bool rec_bad = grp_or<G>(bad) != 0;
-      u32 okf = 1, nul = 0;
-      if (rec_bad) {
-        const u32 qa0 = q_a;
-        ph = 0;
-        for (u32 j = 0; j < n; ++j) {
-          const u8 c = sp[j];
-          const u32 f = dlut[c];
-          if (f) ph |= f;
-          else { const u32 q = lds_u8(qa0 + j); ++namb; nul |= c == 0 ? 1u : 0u; if (xq[c] == 0 || q < 33 || q > 40) okf = 0; }
+    const u32 s_a = b_a + te + 1 + a, q_a = s_a + L + 3; /* shared addresses of this lane's first base / quality byte */
+    /* One walk over the lane's run, four positions per step, started at a staggered step (the lanes of a warp then add to
+     * different rows): the bases are checked against "ACTG"[(c >> 1) & 3] with two byte permutes (and leave a one-hot
+     * presence byte), the quality bytes are counted unless the base above them is not A/C/G/T -- those positions are
+     * kept in `badpos` and settled once the record's ambiguity transfer is decided. */
+    u32 ph = 0;
+    u64 badpos = 0;
+    const u32 ng = n >> 2;
+    if (ng) {
+      const u32 g0 = sub % ng;
+      const u32 sal = s_a & 3u, qal = q_a & 3u;
+#pragma unroll 1
+      for (u32 half = 0; half < 2; ++half) { /* steps g0 .. ng-1, then 0 .. g0-1 */
+        u32 g = half ? 0u : g0;
+        const u32 ge = half ? g0 : ng;
+        if (g >= ge) continue;
+        u32 sw = (s_a + 4 * g) - sal, qw = (q_a + 4 * g) - qal; /* aligned word addresses */
+        u32 s0 = lds_u32(sw), q0 = lds_u32(qw);
+        u32 rowbase = rb0 + (a + 4 * g) * Row::ROWB;
+        for (; g < ge; ++g, rowbase += 4 * Row::ROWB) {
+          sw += 4; qw += 4;
+          const u32 s1 = lds_u32(sw), q1 = lds_u32(qw);
+          const u32 vb = __funnelshift_r(s0, s1, sal * 8), vq = __funnelshift_r(q0, q1, qal * 8);
+          s0 = s1; q0 = q1;
+          const u32 z = (vb >> 1) & 0x03030303u;
+          const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
+          const u32 bad = __byte_perm(0x47544341u, 0, sel) ^ vb;
+          const u32 in_range = ((vq | 0x80808080u) - 0x21212121u) & ~vq & 0x80808080u; /* bit 7 of a byte: 33 <= byte <= 127 */
+          if (bad == 0 && in_range == 0x80808080u) {
+            ph |= __byte_perm(0x08040201u, 0, sel);
+            Row::template count<0>(rowbase, vq); Row::template count<1>(rowbase, vq);
+            Row::template count<2>(rowbase, vq); Row::template count<3>(rowbase, vq);
+          } else { /* rare: a base that is not A/C/G/T, or a quality byte outside 33..127 */
+#pragma unroll
+            for (u32 t = 0; t < 4; ++t) {
+              const u32 c = (vb >> (8 * t)) & 0xFFu, q = (vq >> (8 * t)) & 0xFFu, f = dlut[c];
+              if (!f) { badpos |= 1ull << (4 * g + t); continue; }
+              ph |= f;
+              if (q - 33u < 95u) Row::count_byte(rowbase + t * Row::ROWB, q);
+              else atomicAdd(raw + (size_t)(a + 4 * g + t + 1) * 256 + q, 1u);
+            }
+          }
         }
       }
-      const u32 namb_t = grp_add<G>(namb);
+    }
+    for (u32 j = 4 * ng; j < n; ++j) { /* the last positions of a read whose length is not a multiple of four */
+      const u32 c = lds_u8(s_a + j), q = lds_u8(q_a + j), f = dlut[c];
+      if (!f) { badpos |= 1ull << j; continue; }
+      ph |= f;
+      if (q - 33u < 95u) Row::count_byte(rb0 + (a + j) * Row::ROWB, q);
+      else atomicAdd(raw + (size_t)(a + j + 1) * 256 + q, 1u);
+    }
+    u32 xfer = 0, namb = 0;
+    if (__any_sync(0xFFFFFFFFu, badpos != 0)) { /* ambiguity transfer, decided per record (phyNGSC.cpp:549-588) */
+      u32 okf = 1, nul = 0;
+      for (u64 m = badpos; m; m &= m - 1) {
+        const u32 j = (u32)__ffsll((long long)m) - 1, c = lds_u8(s_a + j), q = lds_u8(q_a + j);
+        ++namb; nul |= c == 0 ? 1u : 0u;
+        if (xq[c] == 0 || q < 33 || q > 40) okf = 0;
+      }
+      namb = grp_add<G>(namb);
       okf = grp_add<G>(okf) == G ? 1u : 0u;
       nul = grp_or<G>(nul);
-      xfer = (namb_t && okf) ? 1u : 0u;
-      if (rec_bad && !xfer) for (u32 j = 0; j < n; ++j) { const u8 c = sp[j]; if (!dlut[c]) s_dna[c] = 1; } /* the byte stays in the DNA */
+      xfer = (namb && okf) ? 1u : 0u;
+      for (u64 m = badpos; m; m &= m - 1) { /* the quality byte under such a base: with the transferred code, or as it is */
+        const u32 j = (u32)__ffsll((long long)m) - 1, c = lds_u8(s_a + j);
+        const u32 q = lds_u8(q_a + j) + (xfer ? xq[c] : 0u);
+        if (!xfer) s_dna[c] = 1; /* the byte stays in the DNA */
+        if (q - 33u < 95u) Row::count_byte(rb0 + (a + j) * Row::ROWB, q);
+        else atomicAdd(raw + (size_t)(a + j + 1) * 256 + q, 1u);
+      }
       if (nul) err = E_UNSUPPORTED;
-      namb = namb_t;
     }
     ph |= ph >> 16; ph |= ph >> 8;
     w_pres |= ph & 0xFu;
@@ -156,21 +208,6 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
       const u32 kept = xfer ? L - namb : L;
       w_maxq = max(w_maxq, L); w_maxs = max(w_maxs, kept); w_invminq = max(w_invminq, ~L);
       if (part == 0) d.kx[P.first_rec + i] = (u16)(kept | (xfer << 15));
-    }
-    /* quality histogram of this lane's run, started at a staggered position */
-    if (n) {
-      u32 p = sub % n;
-      const u32 xm = xfer ? 0xFFu : 0u;
-      const u32 sp_a = q_a - 3 - L; /* the base under quality byte j is L + 3 bytes before it */
-#pragma unroll 2
-      for (u32 j = 0; j < n; ++j) {
-        u32 q = lds_u8(q_a + p);
-        if (xm) q += xq[lds_u8(sp_a + p)];
-        const u32 c = q - 33u, pos = a + p;
-        if (c < 95u) sm_red_add(hist_a + (pos * SQ_ROWW + (c >> 1)) * 4u, 1u << ((c & 1u) * 16u));
-        else atomicAdd(raw + (size_t)(pos + 1) * 256 + q, 1u);
-        if (++p == n) p = 0;
-      }
     }
     if (k + nbuf < nround) { /* every lane has left the stage */
       __syncwarp();
@@ -199,10 +236,17 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
   }
   for (u32 i = tid; i < 256; i += SQ_WARPS * 32) if (s_dna[i]) atomicAdd(&A->dna_occ[i], s_dna[i]);
   const u32 rows = min(d.sq_rows, s_maxq);
-  for (u32 i = tid; i < rows * (SQ_ROWW - 1); i += SQ_WARPS * 32) {
-    const u32 pr = i / (SQ_ROWW - 1), wd = i % (SQ_ROWW - 1), v = hist[pr * SQ_ROWW + wd];
-    if (v & 0xFFFFu) atomicAdd(raw + (size_t)(pr + 1) * 256 + 33 + 2 * wd, v & 0xFFFFu);
-    if (v >> 16) atomicAdd(raw + (size_t)(pr + 1) * 256 + 33 + 2 * wd + 1, v >> 16);
+  if (WIDE) {
+    for (u32 i = tid; i < rows * 95; i += SQ_WARPS * 32) {
+      const u32 pr = i / 95, c = i % 95, v = hist[pr * 97 + c];
+      if (v) atomicAdd(raw + (size_t)(pr + 1) * 256 + 33 + c, v);
+    }
+  } else {
+    for (u32 i = tid; i < rows * (SQ_ROWW - 1); i += SQ_WARPS * 32) {
+      const u32 pr = i / (SQ_ROWW - 1), wd = i % (SQ_ROWW - 1), v = hist[pr * SQ_ROWW + wd];
+      if (v & 0xFFFFu) atomicAdd(raw + (size_t)(pr + 1) * 256 + 33 + 2 * wd, v & 0xFFFFu);
+      if (v >> 16) atomicAdd(raw + (size_t)(pr + 1) * 256 + 33 + 2 * wd + 1, v >> 16);
+    }
   }
 }
 

@@ -50,17 +50,6 @@ static void die(int rank, int code, const char *msg, const char *detail) {
   exit(code);
 }
 
-/* how much of the rank's region the reader thread has delivered */
-struct Watermark {
-  std::mutex m; std::condition_variable cv; uint64_t have = 0; bool failed = false;
-  void publish(uint64_t upto, bool fail) { { std::lock_guard<std::mutex> g(m); if (upto > have) have = upto; failed = failed || fail; } cv.notify_all(); }
-  static void wait_cb(void *self, uint64_t upto) {
-    Watermark *w = (Watermark *)self;
-    std::unique_lock<std::mutex> g(w->m);
-    w->cv.wait(g, [&] { return w->have >= upto || w->failed; });
-  }
-};
-
 /* Block assembly of one rank, phyNGSC.cpp:842-928: appends the finished blocks to `file_bytes`. */
 struct BlockAssembler {
   int wrid, bewr;
@@ -152,50 +141,12 @@ int main(int argc, char **argv) {
   if (end > size) end = size;
   const uint64_t region_len = end - start;
 
-  /* Pinned buffers (the copies of the pipelined region call are asynchronous only from pinned memory).  Pinning costs
-   * about 0.6 s per GB on this box -- most of a one-shot run's wall time; PHY_DRIVER_PINNED=0 uses pageable memory
-   * instead (measured 2.1-5.4 s against 2.9 s on a 2 GB file: first-touch faults and synchronous staged copies). */
-  const bool pinned = !(getenv("PHY_DRIVER_PINNED") && atoi(getenv("PHY_DRIVER_PINNED")) == 0);
-  uint8_t *in = (uint8_t *)(pinned ? phy_host_alloc(region_len + 64) : malloc(region_len + 64));
-  uint64_t out_cap = region_len / 2 + (1u << 20);
-  uint8_t *out = (uint8_t *)(pinned ? phy_host_alloc(out_cap) : malloc(out_cap));
-  if (!in || !out) die(rank, 3, "cannot allocate host buffers", nullptr);
-  /* The rank's byte range is read by a helper thread in 32 MiB pieces while the GPU path already works on what has
-   * arrived (phy_compress_region_streamed waits on the watermark before it touches a byte).  The helper uses pread on
-   * the input path, not MPI-IO: MPI stays on the main thread (MPI_THREAD_FUNNELED, phyNGSC.cpp:57).
-   * PHY_DRIVER_STREAM=0 reads everything first with MPI_File_read_at, like the reference. */
-  const bool streamed = !(getenv("PHY_DRIVER_STREAM") && atoi(getenv("PHY_DRIVER_STREAM")) == 0);
-  Watermark wm;
-  std::thread reader;
-  if (streamed) {
-    reader = std::thread([&wm, in, start, region_len, path = std::string(argv[1])]() {
-      int fd = open(path.c_str(), O_RDONLY);
-      uint64_t o = 0;
-      while (fd >= 0 && o < region_len) {
-        uint64_t n = region_len - o < (32u << 20) ? region_len - o : (32u << 20);
-        ssize_t got = pread(fd, in + o, n, (off_t)(start + o));
-        if (got <= 0) break;
-        o += (uint64_t)got;
-        wm.publish(o, false);
-      }
-      if (fd >= 0) close(fd);
-      wm.publish(o, o < region_len); /* short read: wake the waiters up with the failure flag */
-    });
-  } else {
-    for (uint64_t o = 0; o < region_len; o += 1u << 30) { /* MPI counts are ints */
-      uint64_t n = region_len - o < (1u << 30) ? region_len - o : (1u << 30);
-      MPI_File_read_at(fin, (MPI_Offset)(start + o), in + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
-    }
-    wm.publish(region_len, false);
-  }
-  const double t_read = MPI_Wtime();
-
   const int ndev = phy_device_count();
   if (ndev < 1) die(rank, 3, "no CUDA device (this build has no CPU path)", nullptr);
   const char *lr = getenv("LOCAL_RANK");
   const int dev = (lr ? atoi(lr) : rank) % ndev; /* one rank per GPU; ranks wrap when there are fewer GPUs */
-  /* regions beyond 320 MiB are processed in 256 MiB batches so that upload, kernels and download overlap */
-  uint64_t batch = region_len <= (320ull << 20) ? region_len + (1u << 20) : (256ull << 20);
+  /* 64 MiB batches: upload of batch b+1, kernels of batch b and download of batch b-1 overlap inside the library */
+  const uint64_t batch = region_len <= (80ull << 20) ? region_len + (1u << 20) : (64ull << 20);
   phy_ctx *ctx = nullptr;
   int rc = phy_ctx_create(&ctx, dev, batch, (uint32_t)(batch / (READ_BUFFER_SIZE / 2)) + 16);
   if (rc) die(rank, 3, "cannot create the GPU context", phy_strerror(rc));
@@ -209,20 +160,61 @@ int main(int argc, char **argv) {
    * subblock here is one run of consecutive records, so the whole-window cap is used for every thread count. */
   prm.record_cap = 100000u;
   prm.threads = (uint32_t)threads; prm.reserved = 0;
-  std::vector<phy_subblock_desc> descs((size_t)(region_len / (READ_BUFFER_SIZE / 2)) + 64);
-  uint32_t nd_ = (uint32_t)descs.size();
-  phy_region_result res;
-  rc = phy_compress_region_streamed(ctx, in, region_len, &prm, &Watermark::wait_cb, &wm, out, out_cap, descs.data(), &nd_, &res);
-  if (reader.joinable()) reader.join();
-  if (wm.failed) die(rank, 3, "cannot read the input", argv[1]);
-  if (rc) die(rank, 4, phy_strerror(rc), phy_last_error(ctx));
-  const double t_comp = MPI_Wtime();
-  for (uint32_t i = 0; i < nd_; ++i)
-    if (descs[i].warnings & 1u) printf("[!] WARNING: rank %d subblock %u hit the record cap\n", rank, i);
 
+  /* The rank's byte range never sits in one host buffer.  Default: the library's reader threads pull it with pread straight
+   * into pinned staging memory (phy_compress_stream; the helpers use the input path, not MPI-IO: MPI stays on the main
+   * thread, MPI_THREAD_FUNNELED, phyNGSC.cpp:57) and every finished batch of subblocks goes into the block assembler while
+   * later batches are on the GPU.  PHY_DRIVER_STREAM=0 reads the whole region first with MPI_File_read_at into pageable
+   * memory, like the reference reads its windows, and makes one phy_compress_region call. */
+  const bool streamed = !(getenv("PHY_DRIVER_STREAM") && atoi(getenv("PHY_DRIVER_STREAM")) == 0);
   BlockAssembler ba(rank, np);
-  for (uint32_t i = 0; i < nd_; ++i)
-    if (!ba.add_subblock(out + descs[i].out_off, descs[i].out_len)) die(rank, 4, "block header does not fit", nullptr);
+  ba.file_bytes.reserve((size_t)(region_len / 3));
+  struct Emit { BlockAssembler *ba; int rank; uint32_t n; bool bad; } em = {&ba, rank, 0, false};
+  auto emit_cb = [](void *u, const phy_subblock_desc *d, uint32_t n, const uint8_t *bytes) -> int {
+    Emit *e = (Emit *)u;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (d[i].warnings & 1u) printf("[!] WARNING: rank %d subblock %u hit the record cap\n", e->rank, e->n + i);
+      if (d[i].status == 0 && !e->ba->add_subblock(bytes + d[i].out_off, d[i].out_len)) { e->bad = true; return 1; }
+    }
+    e->n += n;
+    return 0;
+  };
+  phy_region_result res;
+  const double t_read = MPI_Wtime();
+  if (streamed) {
+    struct Src { int fd; uint64_t start; } src = {open(argv[1], O_RDONLY), start};
+    if (src.fd < 0) die(rank, 2, "cannot open the input", argv[1]);
+    auto read_cb = [](void *u, uint64_t off, void *dst, uint64_t n) -> int64_t {
+      Src *s = (Src *)u;
+      uint64_t done = 0;
+      while (done < n) {
+        ssize_t got = pread(s->fd, (char *)dst + done, n - done, (off_t)(s->start + off + done));
+        if (got <= 0) break;
+        done += (uint64_t)got;
+      }
+      return (int64_t)done;
+    };
+    rc = phy_compress_stream(ctx, region_len, &prm, read_cb, &src, emit_cb, &em, &res);
+    close(src.fd);
+  } else {
+    uint8_t *in = (uint8_t *)malloc(region_len + 64);
+    uint64_t out_cap = region_len / 2 + (1u << 20);
+    uint8_t *out = (uint8_t *)malloc(out_cap);
+    if (!in || !out) die(rank, 3, "cannot allocate host buffers", nullptr);
+    for (uint64_t o = 0; o < region_len; o += 1u << 30) { /* MPI counts are ints */
+      uint64_t n = region_len - o < (1u << 30) ? region_len - o : (1u << 30);
+      MPI_File_read_at(fin, (MPI_Offset)(start + o), in + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
+    }
+    std::vector<phy_subblock_desc> descs((size_t)(region_len / (READ_BUFFER_SIZE / 2)) + 64);
+    uint32_t nd = (uint32_t)descs.size();
+    rc = phy_compress_region(ctx, in, region_len, &prm, out, out_cap, descs.data(), &nd, &res);
+    if (!rc) emit_cb(&em, descs.data(), nd, out);
+    free(in); free(out);
+  }
+  if (em.bad) die(rank, 4, "block header does not fit", nullptr);
+  if (rc) die(rank, 4, phy_strerror(rc), phy_last_error(ctx));
+  const uint32_t nd_ = em.n;
+  const double t_comp = MPI_Wtime();
   if (!ba.finish()) die(rank, 4, "block header does not fit", nullptr);
 
   /* file offsets: exclusive scan of the ranks' compressed sizes (the only cross-rank exchange on the data path) */
@@ -263,7 +255,7 @@ int main(int argc, char **argv) {
     if (r == rank) {
       if (rank == 0) printf("RANK\tCOMP_TIME\tN_BLOCK\tN_SUBBLOCKS\n");
       printf("%d\t%f\t%u\t%u\n", rank, t1 - t0, ba.n_blocks, nd_);
-      printf("[I] rank %d: read (issued) %.3fs, read + gpu path %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), assemble+write %.3fs, %llu -> %lld bytes\n",
+      printf("[I] rank %d: context %.3fs, read + gpu path + block assembly %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), exscan + write + footer %.3fs, %llu -> %lld bytes\n",
              rank, t_read - t0, t_comp - t_read, res.h2d_ms, res.kernel_ms, res.d2h_ms, res.kernel_launches, t1 - t_comp,
              (unsigned long long)res.bytes_in, mine);
       fflush(stdout);
@@ -271,7 +263,6 @@ int main(int argc, char **argv) {
   }
   MPI_Barrier(MPI_COMM_WORLD);
   phy_ctx_destroy(ctx);
-  if (pinned) { phy_host_free(in); phy_host_free(out); } else { free(in); free(out); }
   MPI_File_close(&fin); MPI_File_close(&fout);
   MPI_Finalize();
   return 0;
