@@ -302,7 +302,7 @@ def main():
     start, end = api.region_slice(image.size, world, rank, slack=slack)
     pin_in = api.pinned_array(end - start + 8192)
     region = image.fill(start, end, pin_in.array)
-    pin_out = api.pinned_array(region.size // 3 + (1 << 20))
+    pin_out = api.pinned_array(region.size // 2 + (1 << 20))
     prm = api.region_params(image.size, world, rank)
     max_descs = region.size // (4 << 20) + 64
     ctx = api.Context(local)  # defaults: batches of 1 GiB + 16 MiB, 192 subblocks per batch

@@ -87,7 +87,7 @@ def test_driver_threads_argument_matches_the_reference_at_the_same_thread_count(
     reference's last thread applies the stop rule (phyNGSC.cpp:261-266, 303, 315).  The driver's blocks must equal the
     oracle's at that thread count and -- keyed by rank -- the unmodified reference's (which is flaky with more than one
     thread, SURVEY.md Q16: it gets a few attempts)."""
-    data = synth.fastq("36bp", 700 + threads, target_bytes=40_000_000 + 977)
+    data = synth.fastq("36bp", 702, target_bytes=40_000_000 + 977)  # seed picked so that the last window differs from the one-thread result
     src, dst, ref = tmp_path / "in.fastq", tmp_path / "out.ngsc", tmp_path / "ref.ngsc"
     data.tofile(src)
     out = run_driver(src, dst, 2, threads=threads)
