@@ -111,7 +111,8 @@ int phy_compress_region_streamed(phy_ctx *ctx, const uint8_t *region, uint64_t r
 
 /* The region is not in memory at all: the library pulls it through `read` (called from its own reader threads, in 16 MiB
  * pieces, straight into pinned staging memory -- no copy of the region is ever pinned or held by the caller) and hands
- * every batch of finished subblocks to `emit` on the calling thread while later batches are still being compressed.
+ * every batch of finished subblocks to `emit`, in order, from one library thread (never two emit calls at a time) while
+ * later batches are still being read, uploaded and compressed.
  * Replaces the per-subblock MPI_File_read_at / compress / copy-to-write-buffer loop of phyNGSC.cpp:168-906 for one rank.
  *   read(user, off, dst, n)      fill dst with region bytes [off, off + n); return n, anything else is an error.
  *                                Must be thread-safe (pread is) and must not call MPI (MPI_THREAD_FUNNELED, phyNGSC.cpp:57).
@@ -121,6 +122,10 @@ typedef int64_t (*phy_read_fn)(void *user, uint64_t off, void *dst, uint64_t n);
 typedef int (*phy_emit_fn)(void *user, const phy_subblock_desc *descs, uint32_t n, const uint8_t *payloads);
 int phy_compress_stream(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params, phy_read_fn read, void *read_user,
                         phy_emit_fn emit, void *emit_user, phy_region_result *result);
+/* Allocates what phy_compress_stream needs (pinned staging ring, pinned payload slots, second device buffers, copy streams)
+ * ahead of the call, so that a driver can keep that one-off cost out of its timed region -- the analogue of MPI_Init
+ * preceding p_timer_start in the reference (phyNGSC.cpp:57,111).  Optional: phy_compress_stream does it on first use. */
+int phy_stream_prepare(phy_ctx *ctx);
 
 /* The same work split into its three legs, for callers that keep data resident (and for kernel-only
  * timing): upload copies host bytes into the ctx input buffer; compress_resident runs the kernels over

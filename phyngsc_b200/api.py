@@ -33,7 +33,7 @@ class RegionResult(C.Structure):
 
 EXPORTS = ["phy_device_count", "phy_ctx_create", "phy_ctx_destroy", "phy_compress_region", "phy_upload", "phy_compress_resident", "phy_download",
            "phy_find_first_record", "phy_device_input", "phy_device_output", "phy_host_alloc", "phy_host_free",
-           "phy_make_block_header", "phy_make_footer", "phy_debug_read", "phy_profile", "phy_profile_read", "phy_strerror", "phy_last_error", "phy_abi_version", "phy_decode_subblock", "phy_compress_region_streamed", "phy_compress_stream"]
+           "phy_make_block_header", "phy_make_footer", "phy_debug_read", "phy_profile", "phy_profile_read", "phy_strerror", "phy_last_error", "phy_abi_version", "phy_decode_subblock", "phy_compress_region_streamed", "phy_compress_stream", "phy_stream_prepare"]
 
 _lib = None
 

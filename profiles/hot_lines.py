@@ -40,7 +40,7 @@ src_cache = {}
 for key, v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
     f, ln = key
     text = ""
-    for cand in ("phyngsc_b200/csrc/" + f,):
+    for cand in ("phyngsc_b200/csrc/" + f,):  # noqa
         try:
             src_cache.setdefault(cand, open(cand).read().splitlines())
             text = src_cache[cand][ln - 1].strip()[:90]
