@@ -50,6 +50,7 @@ constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
 constexpr u32 PK_ESC = 0xF000u;   /* packed quality entries at or above this value: code longer than 12 bits, read the 64-bit entry */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
+constexpr u32 TP_SAME = 0xFFFFu;   /* Dev::tp start value: the token is record 0's                         */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
   u32 NL, NR;          /* newlines found, complete records                                      */
@@ -79,6 +80,11 @@ struct Dev {
   u32 *te, *se, *rstart; u32 maxrec;
   u16 *kx; u32 *qoff, *doff, *toff;
   u32 *chunk_first, *chunk_last; /* numeric token values of the first / last record of every 128-record chunk, [chunk][MAXF] */
+  /* Parsed titles (written by k_stat1, the only kernel that tokenises): per 128-record chunk the mask of fields some record
+   * of the chunk does not share with record 0 of its subblock, and for those fields one row of 128 entries each in tv (the
+   * token's numeric value, utils::to_num) and tp (token start inside the title line | length << 16; start = TP_SAME when
+   * the token -- bytes and separator -- is record 0's).  Row of (chunk, field): (chunk * nfs + field) * 128. */
+  u32 *chunk_mask, *tv, *tp; u32 nfs;
   u32 *tile_cnt, *tile_off; u32 ntiles;
   uint2 *nl_mask;             /* newline bit mask of the batch, 64 input bytes per element */
   PlanState *plan_state; SbPlan *plans; u32 max_sb;
@@ -625,6 +631,7 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
       }
     }
     vals[f * CH + tid] = t.v;
+    d.tp[(((size_t)P.chunk_base + c) * d.nfs + f) * CH + tid] = ok ? ((t.start - ts) | (len << 16)) : TP_SAME;
     u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
     u32 mx = __reduce_max_sync(0xFFFFFFFFu, ok ? len : 0u);
     u32 nn = __ballot_sync(0xFFFFFFFFu, ok && !t.num);
@@ -642,8 +649,15 @@ __global__ void __launch_bounds__(CH) k_stat1(Dev d) {
   __syncthreads();
   /* fields that some warp of the chunk tokenised need every record's value: the other warps fill in record 0's */
   const u32 ct = seed_ok ? S.chunk_touched : 0u;
-  for (u32 m = ct & ~my_done; m; m &= m - 1) { const u32 f = __ffs(m) - 1; vals[f * CH + tid] = S.v0[f]; }
+  for (u32 m = ct & ~my_done; m; m &= m - 1) {
+    const u32 f = __ffs(m) - 1;
+    vals[f * CH + tid] = S.v0[f];
+    d.tp[(((size_t)P.chunk_base + c) * d.nfs + f) * CH + tid] = TP_SAME | (S.len0[f] << 16);
+  }
   __syncthreads();
+  /* the chunk's parsed values leave for the later title kernels (k_stat2, k_enc_title): one coalesced row per touched field */
+  for (u32 m = ct; m; m &= m - 1) { const u32 f = __ffs(m) - 1; d.tv[(((size_t)P.chunk_base + c) * d.nfs + f) * CH + tid] = vals[f * CH + tid]; }
+  if (tid == 0) d.chunk_mask[P.chunk_base + c] = ct;
   /* deltas inside the chunk; the delta across the chunk boundary is folded in by k_xdelta from the values of
    * the chunk's first / last record, so that no thread has to parse the neighbouring chunk's record */
   if (seed_ok && tid < nf) {

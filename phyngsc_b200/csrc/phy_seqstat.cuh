@@ -138,40 +138,40 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) k_seqstat(Dev d) {
     u64 badpos = 0;
     const u32 ng = n >> 2;
     if (ng) {
+      /* steps g0, g0 + 1, .., ng - 1, 0, .., g0 - 1: every lane makes exactly ng steps (lanes with equal run lengths stay
+       * converged); the step counter wraps once, where the rolling words are reloaded */
       const u32 g0 = sub % ng;
       const u32 sal = s_a & 3u, qal = q_a & 3u;
+      u32 g = g0;
+      u32 sw = (s_a + 4 * g) - sal, qw = (q_a + 4 * g) - qal; /* aligned word addresses */
+      u32 s0 = lds_u32(sw), q0 = lds_u32(qw);
+      u32 rowbase = rb0 + (a + 4 * g) * Row::ROWB;
 #pragma unroll 1
-      for (u32 half = 0; half < 2; ++half) { /* steps g0 .. ng-1, then 0 .. g0-1 */
-        u32 g = half ? 0u : g0;
-        const u32 ge = half ? g0 : ng;
-        if (g >= ge) continue;
-        u32 sw = (s_a + 4 * g) - sal, qw = (q_a + 4 * g) - qal; /* aligned word addresses */
-        u32 s0 = lds_u32(sw), q0 = lds_u32(qw);
-        u32 rowbase = rb0 + (a + 4 * g) * Row::ROWB;
-        for (; g < ge; ++g, rowbase += 4 * Row::ROWB) {
-          sw += 4; qw += 4;
-          const u32 s1 = lds_u32(sw), q1 = lds_u32(qw);
-          const u32 vb = __funnelshift_r(s0, s1, sal * 8), vq = __funnelshift_r(q0, q1, qal * 8);
-          s0 = s1; q0 = q1;
-          const u32 z = (vb >> 1) & 0x03030303u;
-          const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
-          const u32 bad = __byte_perm(0x47544341u, 0, sel) ^ vb;
-          const u32 in_range = ((vq | 0x80808080u) - 0x21212121u) & ~vq & 0x80808080u; /* bit 7 of a byte: 33 <= byte <= 127 */
-          if (bad == 0 && in_range == 0x80808080u) {
-            ph |= __byte_perm(0x08040201u, 0, sel);
-            Row::template count<0>(rowbase, vq); Row::template count<1>(rowbase, vq);
-            Row::template count<2>(rowbase, vq); Row::template count<3>(rowbase, vq);
-          } else { /* rare: a base that is not A/C/G/T, or a quality byte outside 33..127 */
+      for (u32 t = 0; t < ng; ++t) {
+        sw += 4; qw += 4;
+        const u32 s1 = lds_u32(sw), q1 = lds_u32(qw);
+        const u32 vb = __funnelshift_r(s0, s1, sal * 8), vq = __funnelshift_r(q0, q1, qal * 8);
+        const u32 z = (vb >> 1) & 0x03030303u;
+        const u32 sel = __byte_perm(z | (z >> 4), 0, 0x4420);
+        const u32 bad = __byte_perm(0x47544341u, 0, sel) ^ vb;
+        const u32 in_range = ((vq | 0x80808080u) - 0x21212121u) & ~vq & 0x80808080u; /* bit 7 of a byte: 33 <= byte <= 127 */
+        if (bad == 0 && in_range == 0x80808080u) {
+          ph |= __byte_perm(0x08040201u, 0, sel);
+          Row::template count<0>(rowbase, vq); Row::template count<1>(rowbase, vq);
+          Row::template count<2>(rowbase, vq); Row::template count<3>(rowbase, vq);
+        } else { /* rare: a base that is not A/C/G/T, or a quality byte outside 33..127 */
 #pragma unroll
-            for (u32 t = 0; t < 4; ++t) {
-              const u32 c = (vb >> (8 * t)) & 0xFFu, q = (vq >> (8 * t)) & 0xFFu, f = dlut[c];
-              if (!f) { badpos |= 1ull << (4 * g + t); continue; }
-              ph |= f;
-              if (q - 33u < 95u) Row::count_byte(rowbase + t * Row::ROWB, q);
-              else atomicAdd(raw + (size_t)(a + 4 * g + t + 1) * 256 + q, 1u);
-            }
+          for (u32 u = 0; u < 4; ++u) {
+            const u32 c = (vb >> (8 * u)) & 0xFFu, q = (vq >> (8 * u)) & 0xFFu, f = dlut[c];
+            if (!f) { badpos |= 1ull << (4 * g + u); continue; }
+            ph |= f;
+            if (q - 33u < 95u) Row::count_byte(rowbase + u * Row::ROWB, q);
+            else atomicAdd(raw + (size_t)(a + 4 * g + u + 1) * 256 + q, 1u);
           }
         }
+        ++g; rowbase += 4 * Row::ROWB;
+        if (g == ng) { g = 0; sw = s_a - sal; qw = q_a - qal; s0 = lds_u32(sw); q0 = lds_u32(qw); rowbase = rb0 + a * Row::ROWB; }
+        else { s0 = s1; q0 = q1; }
       }
     }
     for (u32 j = 4 * ng; j < n; ++j) { /* the last positions of a read whose length is not a multiple of four */

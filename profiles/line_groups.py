@@ -8,7 +8,7 @@ import sys
 
 rep, kre, mangled, cubin = sys.argv[1:5]
 src = {}
-for f in ("phy_core.cuh", "phy_kernels.cuh"):
+for f in ("phy_core.cuh", "phy_kernels.cuh", "phy_encode.cuh", "phy_fast.cuh", "phy_seqstat.cuh"):
     src[f] = open("phyngsc_b200/csrc/" + f).read().splitlines()
 
 
