@@ -19,6 +19,7 @@
 #include "phy_kernels.cuh"
 #include "phy_encode.cuh"
 #include "phy_seqstat.cuh"
+#include "phy_title.cuh"
 
 using namespace phy;
 
@@ -40,6 +41,7 @@ struct phy_ctx {
   /* device buffers */
   u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr, *chunk_first = nullptr, *chunk_last = nullptr;
   u32 *tile_cnt = nullptr, *tile_off = nullptr; uint2 *nl_mask = nullptr;
+  u32 *chunk_mask = nullptr, *tv = nullptr, *tp = nullptr; u64 tv_cap = 0; /* parsed titles (k_stat1 -> k_stat2 / k_enc_title); tv / tp grow on demand */
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
   u32 *tmp = nullptr; u64 tmp_cap = 0; u64 *tmp_used = nullptr; /* temporary buffer of the single-walk encoder (words) */
@@ -120,7 +122,7 @@ extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->plan_state,
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->chunk_mask, ctx->tv, ctx->tp, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1], ctx->hout[2], ctx->hout[3]};
@@ -178,6 +180,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
     size_t rows = (size_t)ctx->maxrec / CH + ctx->max_sb + 2; /* every subblock rounds its chunk count up */
     CK(cudaMalloc(&ctx->chunk_first, rows * MAXF * 4));
     CK(cudaMalloc(&ctx->chunk_last, rows * MAXF * 4));
+    CK(cudaMalloc(&ctx->chunk_mask, rows * 4));
   }
   CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
@@ -205,7 +208,6 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
     CK(cudaMemcpyToSymbol(g_xq_lut, lut, sizeof lut));
   }
   CK(cudaFuncSetAttribute(k_stat1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
-  CK(cudaFuncSetAttribute(k_stat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_dnacount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPAN_MAX));
   CK(cudaFuncSetAttribute(k_seqstat<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_seqstat<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
@@ -258,6 +260,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   d.in = in; d.len = len; d.start_pos = start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
   d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff; d.chunk_first = ctx->chunk_first; d.chunk_last = ctx->chunk_last;
+  d.chunk_mask = ctx->chunk_mask;
   d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
@@ -312,6 +315,21 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
+  { /* parsed-title rows: one row of CH entries per (chunk, field) in each of tv and tp; grown when a batch needs more */
+    const SbPlan &PL = ctx->h_plans[S - 1];
+    const u64 chunks = (u64)PL.chunk_base + (PL.n_records + CH - 1) / CH;
+    d.nfs = d.max_nf ? d.max_nf : 1u;
+    const u64 need = chunks * d.nfs * CH;
+    if (need > ctx->tv_cap) {
+      if (ctx->tv) { CK(cudaFree(ctx->tv)); ctx->tv = nullptr; }
+      if (ctx->tp) { CK(cudaFree(ctx->tp)); ctx->tp = nullptr; }
+      ctx->tv_cap = 0;
+      const u64 cap = need + need / 4;
+      CK(cudaMalloc(&ctx->tv, cap * 4)); CK(cudaMalloc(&ctx->tp, cap * 4));
+      ctx->tv_cap = cap;
+    }
+    d.tv = ctx->tv; d.tp = ctx->tp;
+  }
   /* launch geometry shared by all subblock groups of the batch */
   {
     u32 es = (H.max_span32 + 16 + 255) & ~255u;
@@ -344,7 +362,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   d.sq_stage = d.qd_stage; d.sq_nbuf = sqbuf_env == 2 ? 2u : 1u; /* one stage: more resident CTAs hide the copy better (100 bp: 0.66 vs 0.76 ms per GB) */
   const bool sq_wide = d.sq_rows <= 126; /* 32-bit counters while the private table stays below 48 KB, else 16-bit pairs */
   const u32 sq_dyn = ((d.sq_rows * (sq_wide ? 97u : SQ_ROWW) * 4u + 15u) & ~15u) + SQ_WARPS * d.sq_nbuf * d.sq_stage;
-  const u32 title_stat_dyn = 2u * CH * d.ts + d.max_nf * CH * 4u; /* two stages of title slots + numeric values per field and record */
+  const u32 title_stat_dyn = 2u * CH * d.ts + d.max_nf * CH * 4u; /* k_stat1: two stages of title slots + numeric values per field and record */
   if (sq_dyn > ENC_DYN_MAX || title_stat_dyn > ENC_DYN_MAX) { ctx->err = "records too long for the statistics kernels' shared memory"; return PHY_ERR_UNSUPPORTED; }
   /* Subblock groups: the subblocks of the batch are split into G consecutive groups that run the rest of the pipeline on
    * their own streams.  Several of its stages are latency-bound (one warp per subblock in k_classify, one warp per table
@@ -405,7 +423,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     CK(cudaMemcpyAsync(ctx->h_hdr_g + g, ctx->hdr_g + g, sizeof(BatchHdr), cudaMemcpyDeviceToHost, gs));
     CK(cudaEventRecord(ctx->ev_rb[g], gs));
     k_zero_hist<<<dim3(8, Sg), 256, 0, gs>>>(e); GMARK();
-    k_stat2<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, title_stat_dyn, gs>>>(e);
+    k_stat2<<<dim3((H.max_chunks * (CH / 32) + S2W * S2B - 1) / (S2W * S2B), Sg), S2W * 32, 0, gs>>>(e);
     k_dnacount<<<dim3((H.max_chunks + S2G - 1) / S2G, Sg), CH, span, gs>>>(e); /* returns at once unless the DNA is Huffman coded */
     GMARK();
   }
@@ -427,7 +445,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     k_huff<<<dim3(16, Sg), 128, 4 * sizeof(HuffScratch), gs>>>(e); GMARK();
     /* single-walk encoder: slots, then title + info and quality + DNA of every task into the temporary buffer */
     e.fg.pk_bytes = e.pk_bytes;
-    const u32 title_dyn = ENC_WARPS * (2u * 32u * e.ts + (32u * LPW_T + CCW + 32u) * 4u);
+    const u32 title_dyn = ENC_WARPS * enc_title_warp_bytes();
     const u32 qd_dyn = e.fg.pk_bytes + ENC_WARPS * (e.qd_nbuf * e.qd_stage + (32u * e.fg.lpw_q + 2u * CCW) * 4u);
     if (e.fg.g && (title_dyn > ENC_DYN_MAX || qd_dyn > ENC_DYN_MAX || e.fg.pk_bytes == 0)) e.fg.g = 0; /* does not fit: two-walk kernels */
     k_slots<<<Sg, 32, 0, gs>>>(e); GMARK();

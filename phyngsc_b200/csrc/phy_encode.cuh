@@ -3,8 +3,8 @@
  *
  *   k_slots      per subblock: bounds from the tables' longest codes, slot sizes, region of the temporary buffer,
  *                and the decision single-walk (SbClass::fast) or two-walk (k_lengths + k_emit)
- *   k_enc_title  warp = task of 8 title blocks (32 records each, lane = record): info length bits and title tokens
- *                (phyNGSC.cpp:732-742, tasks.cpp:393-509); only the title lines are staged (16-byte cp.async per lane)
+ *   k_enc_title  (phy_title.cuh) warp = task of 8 title blocks (32 records each, lane = record): info length bits and
+ *                title tokens (phyNGSC.cpp:732-742, tasks.cpp:393-509) from the parsed title rows k_stat1 left
  *   k_enc_qd<G>  warp = task of 256 records, G lanes per record (each a run of read positions): quality and DNA codes
  *                (tasks.cpp:609-619, 544-557); record spans staged by the bulk-copy engine
  *   k_place      moves every task's run from the temporary buffer to its final bit position and writes the headers
@@ -126,98 +126,6 @@ __global__ void __launch_bounds__(32) k_slots(Dev d) {
     if (base + words > d.tmp_cap) fast = false; /* no room left in the temporary buffer: two-walk kernels */
   }
   C.fast = fast ? 1u : 0u;
-}
-
-/* ---- title + info -------------------------------------------------------------------------------------------------- */
-/* dynamic shared memory per warp: [2 title stages of 32 * ts bytes][32 * LPW_T staging words][CCW words][32 words for the info bits] */
-__device__ __forceinline__ u32 enc_title_warp_bytes(u32 ts) { return 2u * 32u * ts + (32u * LPW_T + CCW + 32u) * 4u; }
-
-__global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_title(Dev d) {
-  extern __shared__ uint4 dyn_smem[];
-  __shared__ TitleTabs TT;
-  __shared__ __align__(16) u8 lut[256];
-  const u32 s = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  SbClass &C = d.cls[s];
-  if (C.status || !C.fast) return;
-  const u32 task = blockIdx.x * ENC_WARPS + w;
-  if (blockIdx.x * ENC_WARPS >= C.ntask) return;
-  const SbPlan P = d.plans[s];
-  u32 *arena = d.arena + (size_t)s * d.arena_words;
-  const u32 R = C.R, nnc = C.nnc, nb_len = C.nb_len, ts = d.ts;
-  load_lut(lut);
-  load_title_tabs(C, TT);
-  __syncthreads();
-  if (task >= C.ntask) return;
-  u8 *wb = (u8 *)dyn_smem + (size_t)w * enc_title_warp_bytes(ts);
-  u8 *tstage = wb;
-  u32 *lp = (u32 *)(wb + 2u * 32u * ts), *cc = lp + 32 * LPW_T, *ci = cc + CCW;
-  const u32 tstage_a = (u32)__cvta_generic_to_shared(tstage), lp_a = (u32)__cvta_generic_to_shared(lp) + 4 * lane;
-  u32 *tmp = d.tmp + C.tmp_base;
-  WarpStream T;
-  T.init(cc, tmp + C.info_words + (size_t)task * (C.strd_q + C.strd_d + C.strd_t) + C.strd_q + C.strd_d, C.strd_t);
-  const u32 g0 = task * TASK_BLOCKS, g1 = min(g0 + TASK_BLOCKS, C.nblk);
-  const u32 *flag_p = arena + C.flagbits_off;
-  /* one lane's title line [rs, te] into its slot of stage `buf`: 16-byte pieces from the aligned address below rs */
-  auto stage_title = [&](u32 buf, u32 rs, u32 te) -> bool {
-    const u32 a0 = rs & ~15u, n = (te + 1 - a0 + 15u) >> 4;
-    if (n * 16u > ts) return false;
-    const u32 dst = tstage_a + (buf * 32u + lane) * ts;
-    for (u32 k = 0; k < n; ++k) cp_async16(dst + 16 * k, d.in + a0 + 16 * k);
-    return true;
-  };
-  /* record of this lane in block g (idle lanes shadow the block's last record so that the warp stays converged) */
-  u32 n_rs, n_te, n_se, n_fl;
-  {
-    const u32 r = P.first_rec + min(g0 * 32 + lane, R - 1);
-    n_rs = d.rstart[r]; n_te = d.te[r]; n_se = d.se[r]; n_fl = nnc ? flag_p[g0] : 0u;
-  }
-  bool fits = nnc ? stage_title(0, n_rs, n_te) : true; /* slots are sized for the longest title line of the batch: always true */
-  cp_async_commit();
-  for (u32 g = g0; g < g1; ++g) {
-    const u32 nrec = min(32u, R - g * 32), buf = (g - g0) & 1u;
-    const bool active = lane < nrec;
-    const u32 rs = n_rs, te = n_te, se = n_se, flags = n_fl;
-    if (g + 1 < g1) {
-      const u32 r = P.first_rec + min((g + 1) * 32 + lane, R - 1);
-      n_rs = d.rstart[r]; n_te = d.te[r]; n_se = d.se[r]; n_fl = nnc ? flag_p[g + 1] : 0u;
-      if (nnc) fits = stage_title(buf ^ 1u, n_rs, n_te) && fits;
-    }
-    cp_async_commit();
-    { /* info stream: the read length of every record in nb_len bits (phyNGSC.cpp:732-742; always present) */
-      ci[lane] = 0;
-      __syncwarp();
-      if (active && nb_len) {
-        const u32 L = se - te - 1, pos = lane * nb_len, sh = pos & 31, v = L << (32 - nb_len);
-        cc_or(ci, pos >> 5, v >> sh);
-        if (sh + nb_len > 32) cc_or(ci, (pos >> 5) + 1, v << (32 - sh));
-      }
-      __syncwarp();
-      if (lane < (nrec * nb_len + 31) / 32) tmp[g * nb_len + lane] = ci[lane];
-    }
-    if (!__all_sync(0xFFFFFFFFu, fits)) break; /* never walk a line that is not staged */
-    if (nnc) {
-      cp_async_wait<1>();
-      __syncwarp();
-      const u8 *b = tstage + (size_t)(buf * 32u + lane) * ts - (rs & ~15u); /* b[pos] is valid for the positions of this lane's title line */
-      LaneSink sk; sk.init(SmemStore{lp_a}, LPW_T);
-      if (lane == 0) {
-        u32 v = 0;
-        for (u32 k = 0; k < nnc; ++k) v = (v << 1) | ((flags >> TT.ncf[k]) & 1u);
-        sk.put(v, nnc);
-      }
-      title_record(b, lut, rs, te, C, TT.fc, TT.ncf, TT.ncskip, arena, flags, lane == 0, PrevShfl(), sk);
-      u32 nbits = sk.finish();
-      if (sk.over) T.over = true;
-      if (!active) nbits = 0;
-      __syncwarp();
-      T.append(lp + lane, nbits);
-      T.pad_to_byte(); /* FlushPartialWordBuffer per 32-record block (tasks.cpp:508) */
-    }
-  }
-  cp_async_wait<0>();
-  const u32 tbits = T.finish();
-  if (__any_sync(0xFFFFFFFFu, T.over || !fits)) { if (lane == 0) atomicMin(&C.status, (i32)E_CAPACITY); return; }
-  if (lane == 0) arena[C.task_off + 2 * C.ntask + task] = tbits >> 3;
 }
 
 /* ---- quality + DNA -------------------------------------------------------------------------------------------------- */

@@ -1021,126 +1021,6 @@ __global__ void __launch_bounds__(CH) k_dnacount(Dev d) {
   for (u32 i = tid; i < C.nsym; i += CH) if (dnah[i]) atomicAdd(arena + C.dnastat_off + i, dnah[i]);
 }
 
-/* Numeric / char histograms and 32-record block descriptors.  A CTA walks S2G consecutive chunks of one subblock,
- * thread = record, warp = 32-record block; only the title lines are staged (per-thread cp.async slots, the next chunk's
- * lines arrive while the current chunk is walked); tables are loaded and the private char histograms flushed once per CTA.
- * Only the non-constant fields are visited (SbClass::ncf / ncskip).
- * dynamic shared memory: [2 stages of CH slots of d.ts bytes][nnc x CH numeric values] */
-__global__ void __launch_bounds__(CH) k_stat2(Dev d) {
-  extern __shared__ uint4 dyn_smem[];
-  __shared__ TitleTabs T;
-  __shared__ u32 pvals[2][MAXF];
-  __shared__ __align__(16) u8 lut[256];
-  __shared__ u32 chist[CSLOTS * 256];
-  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const SbClass &C = d.cls[s];
-  if (C.status || C.nnc == 0) return; /* every field constant: no histogram, no block flag is ever read */
-  const u32 c0 = blockIdx.x * S2G, c1 = min(c0 + S2G, C.nchunk);
-  if (c0 >= C.nchunk) return;
-  const SbPlan P = d.plans[s];
-  u32 *arena = d.arena + (size_t)s * d.arena_words;
-  const u32 nnc = C.nnc, R = C.R, tsz = d.ts;
-  load_lut(lut);
-  const u8 *slots = (const u8 *)dyn_smem;
-  const u32 slots_a = (u32)__cvta_generic_to_shared(dyn_smem);
-  u32 *vals = (u32 *)((u8 *)dyn_smem + 2u * CH * tsz); /* vals[k * CH + tid], k = index in the non-constant list */
-  /* char histograms of the first CSLOTS per-position tables are privatised in shared memory */
-  const u32 ncs = min(C.ntab - C.tchr0, (u32)CSLOTS);
-  for (u32 i = tid; i < ncs * 256; i += CH) chist[i] = 0;
-  load_title_tabs(C, T);
-  if (tid < nnc && c0 > 0) pvals[0][tid] = d.chunk_last[((size_t)P.chunk_base + c0 - 1) * MAXF + C.ncf[tid]]; /* record before the first chunk */
-  u32 ts = 0, te = 0;
-  bool n_fits = true; /* the slots are sized for the longest title line of the batch: always true */
-  { const u32 i = c0 * CH + tid; if (i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; n_fits = stage_title_line(d.in, slots_a + tid * tsz, tsz, ts, te); } }
-  cp_async_commit();
-  __syncthreads();
-  for (u32 c = c0; c < c1; ++c) {
-    const u32 buf = (c - c0) & 1u, pb = buf;
-    const u32 nrec = min((u32)CH, R - c * CH);
-    const u32 my_ts = ts, my_te = te;
-    const bool active = tid < nrec && n_fits;
-    const u32 r = P.first_rec + c * CH + (tid < nrec ? tid : 0);
-    const u32 wbase = tid & ~31u;
-    { /* next chunk's record: its title line starts to arrive now */
-      const u32 i = (c + 1) * CH + tid;
-      if (c + 1 < c1 && i < R) { ts = d.rstart[P.first_rec + i]; te = d.te[P.first_rec + i]; n_fits = stage_title_line(d.in, slots_a + ((buf ^ 1u) * CH + tid) * tsz, tsz, ts, te); }
-      cp_async_commit();
-    }
-    cp_async_wait<1>();
-    const u8 *b = slots + (size_t)(buf * CH + tid) * tsz - (my_ts & ~15u);
-    __syncwarp(); /* string fields are compared with lane 0's token: its slot must have arrived as well */
-    u32 flags = 0;
-    /* one walk: string fields are finished here, numeric values are parked in shared memory */
-    TitleCursor cur; cur.init(b, my_ts, my_te, lut);
-    for (u32 k = 0; k < nnc; ++k) {
-      const u32 f = T.ncf[k];
-      const FieldClass &F = T.fc[f];
-      cur.pos += T.ncskip[k];
-      Tok t; t.start = t.end = 0; t.v = 0; t.num = false;
-      if (active) cur.next(t);
-      if (F.kind == K_NUM) { vals[k * CH + tid] = t.v; continue; }
-      u32 len = t.end - t.start;
-      /* lane 0's token of this field, addressed inside lane 0's slot */
-      const u32 len_lo = __shfl_sync(0xFFFFFFFFu, len, 0);
-      const u32 a0_off = (u32)__shfl_sync(0xFFFFFFFFu, (u32)((b + t.start) - slots), 0);
-      bool pred = true;
-      if (active) {
-        pred = len == len_lo;
-        const u8 *a = b + t.start, *a0 = slots + a0_off;
-        for (u32 j = 0; pred && j < len; ++j) pred = a[j] == a0[j];
-        const u16 *sm = (const u16 *)(arena + F.slotmap_off);
-        for (u32 j = 0; j < len; ++j)
-          if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
-            /* lanes of the warp that are at the same character of the same table add once, together */
-            u32 tab = sm[j < 128 ? j : 128], loc = tab - C.tchr0, ch = a[j];
-            u32 grp = __match_any_sync(__activemask(), (tab << 8) | ch);
-            if ((u32)(__ffs(grp) - 1) == lane) {
-              if (loc < ncs) atomicAdd(&chist[loc * 256 + ch], (u32)__popc(grp));
-              else atomicAdd(arena + C.chr_freq_off + loc * 256 + ch, (u32)__popc(grp));
-            }
-          }
-      }
-      if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
-    }
-    __syncthreads();
-    for (u32 k = 0; k < nnc; ++k) {
-      const u32 f = T.ncf[k];
-      const FieldClass &F = T.fc[f];
-      if (F.kind != K_NUM) continue;
-      i32 v = (i32)vals[k * CH + tid];
-      i32 pv = (i32)(tid > 0 ? vals[k * CH + tid - 1] : pvals[pb][k]);
-      if (tid == CH - 1) pvals[pb ^ 1u][k] = (u32)v; /* record before the next chunk */
-      i32 dl = wsub(v, pv);
-      const bool on = tid < nrec;
-      bool hasd = on && r > P.first_rec;
-      bool pred;
-      if (F.is_delta) {
-        /* tasks.cpp:127-147 and :415: delta of the block's 2nd record, all later deltas equal to it, and equal to min_delta */
-        i32 bd = __shfl_sync(0xFFFFFFFFu, dl, 1);
-        if (nrec - wbase < 2) bd = 0;
-        pred = !on || lane < 2 || dl == bd;
-        pred = __all_sync(0xFFFFFFFFu, pred) && bd == F.min_d;
-        if (F.has_table) warp_hist_add(arena + F.freq_off, (u32)wsub(dl, F.base), hasd);
-      } else {
-        i32 v_lo = __shfl_sync(0xFFFFFFFFu, v, 0);
-        pred = __all_sync(0xFFFFFFFFu, !on || v == v_lo);
-        if (F.has_table) {
-          warp_hist_add(arena + F.freq_off, (u32)wsub(v, F.base), on);
-          if (on && r == P.first_rec) atomicAdd(arena + F.freq_off + (u32)wsub(v, F.base), 1u); /* seed, phyNGSC.cpp:368 */
-        }
-      }
-      if (pred) flags |= 1u << f;
-    }
-    if (lane == 0 && wbase < nrec) arena[C.flagbits_off + (c * CH + wbase) / 32] = flags;
-    __syncthreads(); /* the value table is free again */
-  }
-  cp_async_wait<0>();
-  for (u32 i = tid; i < ncs * 256; i += CH) {
-    u32 v = chist[i];
-    if (v) atomicAdd(arena + C.chr_freq_off + i, v);
-  }
-}
-
 /* ---- Huffman build: one warp per table ------------------------------------------------------------------------- */
 struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 
