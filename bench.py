@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--mb", type=int, default=16000, help="size of the whole file image in MB (10^6 bytes), split over the ranks")
     ap.add_argument("--cpu-sample-mb", type=int, default=256)
     ap.add_argument("--e2e-batch-mb", type=int, default=64, help="batch size (MiB) of the pipelined end-to-end run")
-    ap.add_argument("--driver-mb", type=int, default=4000, help="file size of the file-to-file driver leg (0: skip it)")
+    ap.add_argument("--driver-mb", type=int, default=8000, help="file size of the file-to-file driver leg (0: skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-shapes", action="store_true", help="skip the 1 GB kernel-only probes of the other named shapes (N = 1 only)")
     return ap.parse_args()
@@ -348,6 +348,13 @@ def main():
            "overlap": "upload / kernels / download of consecutive batches run on three streams"}
     assert r2.bytes_out == bytes_out and r2.bytes_in == bytes_in, "pipelined and resident runs disagree"
     ctx_e.close()
+    # what the box's host <-> device path can move with no kernels at all (all ranks copying at once): the e2e leg's ceiling
+    ceil = pdist.copy_ceiling(1.0, float(r2.out_used) / max(1, region.size))
+    e2e["copy_ceiling"] = {"input_gbs_while_payloads_flow_back": ceil["both"]["aggregate_gbs"], "h2d_alone_gbs": ceil["h2d"]["aggregate_gbs"],
+                           "d2h_alone_gbs": ceil["d2h"]["aggregate_gbs"], "per_rank_min_gbs": ceil["both"]["per_rank_gbs_min"],
+                           "what": "copy-only probe on this box, all ranks at once: 1 GB per rank host -> device plus the payload fraction device -> host, "
+                                   "pinned memory, 64 MiB pieces, two streams (phyngsc_b200.dist.copy_ceiling)"}
+    e2e["frac_of_copy_ceiling"] = e2e["value"] / max(1e-9, ceil["both"]["aggregate_gbs"])
 
     # ---- per-kernel times -> roofline of the dominant kernel ---------------------------------------------------------
     ctx.profile(True)

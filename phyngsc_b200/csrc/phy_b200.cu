@@ -41,7 +41,7 @@ struct phy_ctx {
   /* device buffers */
   u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr, *chunk_first = nullptr, *chunk_last = nullptr;
   u32 *tile_cnt = nullptr, *tile_off = nullptr; uint2 *nl_mask = nullptr;
-  u32 *chunk_mask = nullptr, *tv = nullptr, *tp = nullptr; u64 tv_cap = 0; /* parsed titles (k_stat1 -> k_stat2 / k_enc_title); tv / tp grow on demand */
+  u32 *blk_mask = nullptr, *tv = nullptr, *tp = nullptr, *v0 = nullptr; u64 tv_cap = 0; /* parsed titles (k_stat1 -> k_stat2 / k_enc_title); tv / tp grow on demand */
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
   u32 *tmp = nullptr; u64 tmp_cap = 0; u64 *tmp_used = nullptr; /* temporary buffer of the single-walk encoder (words) */
@@ -122,7 +122,7 @@ extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->chunk_mask, ctx->tv, ctx->tp, ctx->plan_state,
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->blk_mask, ctx->tv, ctx->tp, ctx->v0, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1], ctx->hout[2], ctx->hout[3]};
@@ -180,7 +180,8 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
     size_t rows = (size_t)ctx->maxrec / CH + ctx->max_sb + 2; /* every subblock rounds its chunk count up */
     CK(cudaMalloc(&ctx->chunk_first, rows * MAXF * 4));
     CK(cudaMalloc(&ctx->chunk_last, rows * MAXF * 4));
-    CK(cudaMalloc(&ctx->chunk_mask, rows * 4));
+    CK(cudaMalloc(&ctx->blk_mask, rows * (CH / 32) * 4));
+    CK(cudaMalloc(&ctx->v0, (size_t)ctx->max_sb * MAXF * 4));
   }
   CK(cudaMalloc(&ctx->tile_cnt, (size_t)ctx->max_tiles * 4));
   CK(cudaMalloc(&ctx->tile_off, (size_t)ctx->max_tiles * 4));
@@ -260,7 +261,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   d.in = in; d.len = len; d.start_pos = start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
   d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff; d.chunk_first = ctx->chunk_first; d.chunk_last = ctx->chunk_last;
-  d.chunk_mask = ctx->chunk_mask;
+  d.blk_mask = ctx->blk_mask; d.v0 = ctx->v0;
   d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
@@ -315,7 +316,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
   d.span_bytes = span;
   d.max_nf = H.max_nf < (u32)MAXF ? H.max_nf : (u32)MAXF;
-  { /* parsed-title rows: one row of CH entries per (chunk, field) in each of tv and tp; grown when a batch needs more */
+  { /* parsed-title rows: one row of 32 entries per (block, field) in each of tv and tp; grown when a batch needs more */
     const SbPlan &PL = ctx->h_plans[S - 1];
     const u64 chunks = (u64)PL.chunk_base + (PL.n_records + CH - 1) / CH;
     d.nfs = d.max_nf ? d.max_nf : 1u;
@@ -362,7 +363,10 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   d.sq_stage = d.qd_stage; d.sq_nbuf = sqbuf_env == 2 ? 2u : 1u; /* one stage: more resident CTAs hide the copy better (100 bp: 0.66 vs 0.76 ms per GB) */
   const bool sq_wide = d.sq_rows <= 126; /* 32-bit counters while the private table stays below 48 KB, else 16-bit pairs */
   const u32 sq_dyn = ((d.sq_rows * (sq_wide ? 97u : SQ_ROWW) * 4u + 15u) & ~15u) + SQ_WARPS * d.sq_nbuf * d.sq_stage;
-  const u32 title_stat_dyn = 2u * CH * d.ts + d.max_nf * CH * 4u; /* k_stat1: two stages of title slots + numeric values per field and record */
+  /* k_stat1: two stages of one title slot per lane for every warp; fewer warps per CTA when the title lines are long */
+  u32 s1_warps = S1W;
+  while (s1_warps > 1 && s1_warps * 2u * 32u * d.ts > ENC_DYN_MAX) s1_warps /= 2;
+  const u32 title_stat_dyn = s1_warps * 2u * 32u * d.ts;
   if (sq_dyn > ENC_DYN_MAX || title_stat_dyn > ENC_DYN_MAX) { ctx->err = "records too long for the statistics kernels' shared memory"; return PHY_ERR_UNSUPPORTED; }
   /* Subblock groups: the subblocks of the batch are split into G consecutive groups that run the rest of the pipeline on
    * their own streams.  Several of its stages are latency-bound (one warp per subblock in k_classify, one warp per table
@@ -401,7 +405,7 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     CK(cudaMemcpyAsync(ctx->hdr_g + g, ctx->h_hdr_g + g, sizeof(BatchHdr), cudaMemcpyHostToDevice, gs));
     CK(cudaMemsetAsync(e.acc, 0, sizeof(SbAcc) * Sg, gs));
     GMARK();
-    k_stat1<<<dim3((H.max_chunks + S1G - 1) / S1G, Sg), CH, title_stat_dyn, gs>>>(e);
+    k_stat1<<<dim3((max_tasks + s1_warps - 1) / s1_warps, Sg), s1_warps * 32, title_stat_dyn, gs>>>(e);
     k_xdelta<<<Sg, 128, 0, gs>>>(e); GMARK();
     k_zero_raw<<<dim3(4, Sg), 256, 0, gs>>>(e);
     {

@@ -79,12 +79,13 @@ struct Dev {
   u32 start_pos;              /* first record start inside the batch                           */
   u32 *te, *se, *rstart; u32 maxrec;
   u16 *kx; u32 *qoff, *doff, *toff;
-  u32 *chunk_first, *chunk_last; /* numeric token values of the first / last record of every 128-record chunk, [chunk][MAXF] */
-  /* Parsed titles (written by k_stat1, the only kernel that tokenises): per 128-record chunk the mask of fields some record
-   * of the chunk does not share with record 0 of its subblock, and for those fields one row of 128 entries each in tv (the
-   * token's numeric value, utils::to_num) and tp (token start inside the title line | length << 16; start = TP_SAME when
-   * the token -- bytes and separator -- is record 0's).  Row of (chunk, field): (chunk * nfs + field) * 128. */
-  u32 *chunk_mask, *tv, *tp; u32 nfs;
+  u32 *chunk_first, *chunk_last; /* numeric token values of the first / last record of every k_stat1 task (256 records), row = chunk_base + 2 * task, [row][MAXF] */
+  /* Parsed titles (written by k_stat1, the only kernel that tokenises): per 32-record block the mask of fields in which
+   * some record of the block differs from record 0 of its subblock, and for those fields one row of 32 entries each in tv
+   * (the token's numeric value, utils::to_num) and tp (token start inside the title line | length << 16; start = TP_SAME
+   * for lanes without a record).  Block b of a subblock is block 4 * chunk_base + b of the batch; row of (block, field):
+   * (block * nfs + field) * 32.  v0[subblock][field]: numeric value of record 0's token (fields without a row carry it). */
+  u32 *blk_mask, *tv, *tp, *v0; u32 nfs;
   u32 *tile_cnt, *tile_off; u32 ntiles;
   uint2 *nl_mask;             /* newline bit mask of the batch, 64 input bytes per element */
   PlanState *plan_state; SbPlan *plans; u32 max_sb;
@@ -475,26 +476,7 @@ __device__ __forceinline__ bool eq_bytes(const u8 *x, const u8 *y, u32 n) {
   return diff == 0;
 }
 
-/* ---- stat1 ---------------------------------------------------------------------------------------------- */
-struct Stat1S {
-  u32 facc[MAXF][8];
-  u32 mism[MAXF][MASKW];
-  i32 err;
-  u32 nf, ts0, te0;
-  u32 off0[MAXF], len0[MAXF];
-  u32 v0[MAXF];     /* numeric value / is_num of record 0's tokens */
-  u8 num0[MAXF];
-  u32 touched, chunk_touched; /* fields some warp found to differ from record 0: so far in this CTA / in the current chunk */
-  u16 run_bytes[MAXF];        /* bytes (tokens and separators) of the run of untouched fields that starts at a field */
-  u8 run_end[MAXF];           /* first field behind that run; == field for a touched one */
-  u8 r0[R0_MAX];
-};
-
-#ifndef PHY_S1G
-#define PHY_S1G 8
-#endif
-constexpr int S1G = PHY_S1G; /* 128-record chunks per k_stat1 CTA */
-
+/* ---- title line staging (k_stat1, phy_title.cuh) ----------------------------------------------------------------- */
 /* per-thread staging of title lines: 16-byte cp.async pieces from the aligned address below the line's first byte into the
  * thread's slot (a stage holds one slot of `ts` bytes per thread) */
 __device__ __forceinline__ void cp_async16(u32 dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
@@ -507,221 +489,7 @@ __device__ __forceinline__ bool stage_title_line(const u8 *in, u32 slot_a, u32 t
   return true;
 }
 
-/* Title field reductions (tasks.cpp:22-223 as closed forms).  A CTA walks S1G consecutive 128-record chunks of one
- * subblock, thread = record; only the title lines are staged (two stages of one slot per thread, the next chunk's lines
- * arrive while the current chunk is walked).  Record 0 is tokenised and the shared-memory accumulators are flushed to the
- * subblock's once per CTA.  The sequence / quality side of the statistics is k_seqstat (phy_seqstat.cuh).
- * dynamic shared memory: [2 stages of CH slots of d.ts bytes][nf x CH numeric values] */
-__global__ void __launch_bounds__(CH) k_stat1(Dev d) {
-  extern __shared__ uint4 dyn_smem[];
-  __shared__ Stat1S S;
-  __shared__ __align__(16) u8 lut[256];
-  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const SbPlan P = d.plans[s];
-  const u32 R = P.n_records, nchunk = (R + CH - 1) / CH, c0 = blockIdx.x * S1G, c1 = min(c0 + S1G, nchunk);
-  if (P.status || c0 >= nchunk) return;
-  for (u32 i = tid; i < (sizeof(Stat1S) - R0_MAX) / 4; i += CH) ((u32 *)&S)[i] = 0; /* accumulators + seed */
-  load_lut(lut);
-  const u32 ts0 = d.rstart[P.first_rec], te0 = d.te[P.first_rec];
-  const u32 tsz = d.ts;
-  const u8 *slots = (const u8 *)dyn_smem;
-  const u32 slots_a = (u32)__cvta_generic_to_shared(dyn_smem);
-  u32 *vals = (u32 *)((u8 *)dyn_smem + 2u * CH * tsz); /* vals[f * CH + tid] */
-  /* seed from record 0 of the subblock (phyNGSC.cpp:345-379) */
-  const bool r0_ok = te0 - ts0 + 1 <= R0_MAX;
-  if (r0_ok) for (u32 i = tid; i <= te0 - ts0; i += CH) S.r0[i] = d.in[ts0 + i];
-  __syncthreads();
-  if (tid == 0) {
-    S.ts0 = ts0; S.te0 = te0;
-    if (!r0_ok) S.err = E_UNSUPPORTED;
-    else {
-      TitleCursor c; c.init(S.r0, 0, te0 - ts0, lut);
-      Tok t; u32 nf = 0;
-      while (c.next(t)) { if (nf < (u32)MAXF) { S.off0[nf] = t.start; S.len0[nf] = t.end - t.start; S.v0[nf] = t.v; S.num0[nf] = t.num ? 1 : 0; } ++nf; }
-      S.nf = nf;
-      if (nf == 0 || nf > (u32)MAXF || nf > d.max_nf) S.err = E_UNSUPPORTED;
-    }
-  }
-  /* this thread's record of the first chunk */
-  u32 n_ts = 0, n_te = 0;
-  bool fits = true, n_fits = true; /* the slots are sized for the longest title line of the batch (BatchHdr::max_tlen): always true */
-  { const u32 i = c0 * CH + tid; if (i < R) { const u32 r = P.first_rec + i; n_ts = d.rstart[r]; n_te = d.te[r]; n_fits = stage_title_line(d.in, slots_a + tid * tsz, tsz, n_ts, n_te); } }
-  cp_async_commit();
-  __syncthreads();
-  const u32 nf = S.nf;
-  const bool seed_ok = S.err == 0;
-  if (seed_ok && tid < nf) { /* record 0's own token lengths and values, folded in once per CTA (see the field loop) */
-    const u32 l0 = S.len0[tid], k0 = key_of((i32)S.v0[tid]);
-    atomicMax(&S.facc[tid][0], ~l0); atomicMax(&S.facc[tid][1], l0);
-    if (!S.num0[tid]) S.facc[tid][2] = 1;
-    atomicMax(&S.facc[tid][3], k0); atomicMax(&S.facc[tid][4], ~k0);
-  }
-  for (u32 c = c0; c < c1; ++c) {
-  const u32 nrec = min((u32)CH, R - c * CH), buf = (c - c0) & 1u;
-  const bool active = tid < nrec;
-  const u32 ts = n_ts, te = n_te;
-  const bool cur_fits = n_fits;
-  fits = fits && cur_fits;
-  { /* next chunk's record: its title line starts to arrive now */
-    const u32 i = (c + 1) * CH + tid;
-    if (c + 1 < c1 && i < R) { const u32 rn = P.first_rec + i; n_ts = d.rstart[rn]; n_te = d.te[rn]; n_fits = stage_title_line(d.in, slots_a + ((buf ^ 1u) * CH + tid) * tsz, tsz, n_ts, n_te); }
-    cp_async_commit();
-  }
-  cp_async_wait<1>();
-  const u8 *b = slots + (size_t)(buf * CH + tid) * tsz - (ts & ~15u); /* b[pos] is valid for the positions of this thread's title line */
-  i32 err = 0;
-  /* title: per-field reductions (tasks.cpp:22-223 as closed forms); the field count is checked on the way.
-   * Most tokens repeat record 0's: a token whose bytes AND separator equal record 0's is that token, so a warp
-   * whose 32 records all pass this comparison neither tokenises the field nor reduces anything -- record 0's own
-   * length and value are folded into the accumulators once per CTA instead.  Fields that no warp of the CTA has seen
-   * differ so far are compared as whole runs of consecutive fields, four bytes per step (S.run_end / run_bytes are
-   * rebuilt between chunks from the S.touched mask; they steer only how the comparison is done, not its result). */
-  if (tid == 0) {
-    S.chunk_touched = 0;
-    const u32 tm = S.touched;
-    for (u32 f = nf; f-- > 0;) {
-      if ((tm >> f) & 1u) { S.run_end[f] = (u8)f; S.run_bytes[f] = 0; continue; }
-      const bool ext = f + 1 < nf && !((tm >> (f + 1)) & 1u);
-      S.run_end[f] = ext ? S.run_end[f + 1] : (u8)(f + 1);
-      S.run_bytes[f] = (u16)(S.len0[f] + 1 + (ext ? S.run_bytes[f + 1] : 0u));
-    }
-  }
-  __syncthreads();
-  const bool walk = active && seed_ok && cur_fits;
-  bool fields_ok = true;
-  u32 my_done = 0; /* fields this warp tokenised in this chunk (their values are in the table) */
-  TitleCursor cur; cur.init(b, ts, te, lut);
-  for (u32 f = 0; f < nf && seed_ok;) {
-    u32 fe = f + 1;
-    if (S.run_end[f] > f) { /* a run of fields that have matched record 0 everywhere so far */
-      fe = S.run_end[f];
-      const u32 rl = S.run_bytes[f];
-      const bool ok = walk && fields_ok;
-      const bool same = ok && cur.pos + rl - 1 <= te && eq_bytes(b + cur.pos, S.r0 + S.off0[f], rl);
-      if (__all_sync(0xFFFFFFFFu, same || !ok)) { if (same) cur.pos += rl; f = fe; continue; }
-    }
-    for (; f < fe; ++f) {
-    const u32 len0 = S.len0[f];
-    const u8 *d0 = S.r0 + S.off0[f];
-    bool ok = walk && fields_ok;
-    const bool same = ok && cur.pos + len0 <= te && eq_bytes(b + cur.pos, d0, len0 + 1);
-    if (__all_sync(0xFFFFFFFFu, same || !ok)) {
-      if (same) cur.pos += len0 + 1;
-      continue;
-    }
-    my_done |= 1u << f;
-    if (lane == 0 && !((S.chunk_touched >> f) & 1u)) { atomicOr(&S.chunk_touched, 1u << f); atomicOr(&S.touched, 1u << f); }
-    Tok t; t.start = t.end = 0; t.v = 0; t.num = true;
-    u32 len = 0;
-    if (ok && !cur.next(t)) { fields_ok = false; ok = false; t.start = t.end = 0; t.v = 0; t.num = true; }
-    if (ok) {
-      len = t.end - t.start;
-      const u32 m = len < len0 ? len : len0;
-      const u8 *dp = b + t.start;
-      if (len0 <= 32) { /* Hamming mask of the field in one register */
-        u32 mm = 0;
-        for (u32 p = 0; p < m; ++p) mm |= (dp[p] != d0[p] ? 1u : 0u) << p;
-        if (mm & ~S.mism[f][0]) atomicOr(&S.mism[f][0], mm);
-      } else {
-        u32 diff = 0;
-        for (u32 p = 0; p < m; ++p) diff |= (u32)(dp[p] ^ d0[p]);
-        if (diff)
-          for (u32 p = 0; p < m; ++p)
-            if (dp[p] != d0[p]) { u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
-      }
-    }
-    vals[f * CH + tid] = t.v;
-    d.tp[(((size_t)P.chunk_base + c) * d.nfs + f) * CH + tid] = ok ? ((t.start - ts) | (len << 16)) : TP_SAME;
-    u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
-    u32 mx = __reduce_max_sync(0xFFFFFFFFu, ok ? len : 0u);
-    u32 nn = __ballot_sync(0xFFFFFFFFu, ok && !t.num);
-    u32 kv = key_of((i32)t.v);
-    u32 kmax = __reduce_max_sync(0xFFFFFFFFu, ok ? kv : 0u);
-    u32 kinv = __reduce_max_sync(0xFFFFFFFFu, ok ? ~kv : 0u);
-    if (lane == 0) {
-      atomicMax(&S.facc[f][0], inv_min); atomicMax(&S.facc[f][1], mx);
-      if (nn) S.facc[f][2] = 1;
-      atomicMax(&S.facc[f][3], kmax); atomicMax(&S.facc[f][4], kinv);
-    }
-    }
-  }
-  if (walk && (!fields_ok || cur.pos <= cur.lim)) err = E_FIELDS; /* fewer or more separators than record 0 */
-  __syncthreads();
-  /* fields that some warp of the chunk tokenised need every record's value: the other warps fill in record 0's */
-  const u32 ct = seed_ok ? S.chunk_touched : 0u;
-  for (u32 m = ct & ~my_done; m; m &= m - 1) {
-    const u32 f = __ffs(m) - 1;
-    vals[f * CH + tid] = S.v0[f];
-    d.tp[(((size_t)P.chunk_base + c) * d.nfs + f) * CH + tid] = TP_SAME | (S.len0[f] << 16);
-  }
-  __syncthreads();
-  /* the chunk's parsed values leave for the later title kernels (k_stat2, k_enc_title): one coalesced row per touched field */
-  for (u32 m = ct; m; m &= m - 1) { const u32 f = __ffs(m) - 1; d.tv[(((size_t)P.chunk_base + c) * d.nfs + f) * CH + tid] = vals[f * CH + tid]; }
-  if (tid == 0) d.chunk_mask[P.chunk_base + c] = ct;
-  /* deltas inside the chunk; the delta across the chunk boundary is folded in by k_xdelta from the values of
-   * the chunk's first / last record, so that no thread has to parse the neighbouring chunk's record */
-  if (seed_ok && tid < nf) {
-    const size_t row = ((size_t)P.chunk_base + c) * MAXF + tid;
-    const bool in_table = (ct >> tid) & 1u;
-    d.chunk_first[row] = in_table ? vals[tid * CH] : S.v0[tid];
-    d.chunk_last[row] = in_table ? vals[tid * CH + nrec - 1] : S.v0[tid];
-    if (!in_table && nrec >= 2) { atomicMax(&S.facc[tid][5], key_of(0)); atomicMax(&S.facc[tid][6], ~key_of(0)); } /* every delta inside the chunk is 0 */
-  }
-  for (u32 m = ct; m; m &= m - 1) {
-    const u32 f = __ffs(m) - 1;
-    const bool hasd = walk && tid > 0;
-    u32 pv = tid > 0 ? vals[f * CH + tid - 1] : 0u;
-    u32 kd = key_of((i32)(vals[f * CH + tid] - pv));
-    u32 kmax = __reduce_max_sync(0xFFFFFFFFu, hasd ? kd : 0u);
-    u32 kinv = __reduce_max_sync(0xFFFFFFFFu, hasd ? ~kd : 0u);
-    if (lane == 0) { atomicMax(&S.facc[f][5], kmax); atomicMax(&S.facc[f][6], kinv); }
-  }
-  if (err) atomicMin(&S.err, err);
-  __syncthreads(); /* every thread has left the value table */
-  } /* chunk loop */
-  cp_async_wait<0>();
-  if (!__syncthreads_and(fits) && tid == 0) atomicMin(&S.err, (i32)E_UNSUPPORTED); /* a title line longer than the slots */
-  __syncthreads();
-  /* flush to the subblock accumulators */
-  SbAcc *A = d.acc + s;
-  if (tid == 0 && S.err) atomicMin(&A->status, S.err);
-  if (seed_ok)
-    for (u32 i = tid; i < nf * 8; i += CH) {
-      u32 f = i >> 3, k = i & 7, v = S.facc[f][k];
-      u32 *dst = &A->f[f].inv_min_len + k;
-      if (v) atomicMax(dst, v);
-    }
-  if (seed_ok)
-    for (u32 i = tid; i < nf * MASKW; i += CH) {
-      u32 f = i / MASKW, k = i % MASKW, v = S.mism[f][k];
-      if (v) atomicOr(&A->f[f].mism[k], v);
-    }
-}
-
 __device__ __forceinline__ u32 *raw_table(const Dev &d, u32 s) { return d.arena + (size_t)(s + 1) * d.arena_words - RAW_WORDS; }
-
-/* min / max of the numeric deltas that cross a chunk boundary (tasks.cpp:149-166 runs over all records) */
-__global__ void __launch_bounds__(128) k_xdelta(Dev d) {
-  __shared__ u32 mx[MAXF], mn[MAXF], nf_s;
-  const u32 s = blockIdx.x, tid = threadIdx.x;
-  const SbPlan P = d.plans[s];
-  SbAcc *A = d.acc + s;
-  if (P.status || A->status) return;
-  if (A->max_qlen + 1 > RAW_ROWS) { if (tid == 0) atomicMin(&A->status, (i32)E_UNSUPPORTED); return; } /* the raw per-position quality table has RAW_ROWS rows */
-  const u32 nchunk = (P.n_records + CH - 1) / CH;
-  if (tid < MAXF) { mx[tid] = 0; mn[tid] = 0; }
-  if (tid == 0) nf_s = min((u32)MAXF, count_seps(d.in, d.rstart[P.first_rec], d.te[P.first_rec]));
-  __syncthreads();
-  const u32 nf = nf_s;
-  for (u32 i = tid; i < (nchunk - 1) * nf; i += 128) {
-    u32 c = 1 + i / nf, f = i % nf;
-    u32 a = d.chunk_first[((size_t)P.chunk_base + c) * MAXF + f], b = d.chunk_last[((size_t)P.chunk_base + c - 1) * MAXF + f];
-    u32 kd = key_of((i32)(a - b));
-    atomicMax(&mx[f], kd); atomicMax(&mn[f], ~kd);
-  }
-  __syncthreads();
-  if (tid < nf) { if (mx[tid]) atomicMax(&A->f[tid].kmax_d, mx[tid]); if (mn[tid]) atomicMax(&A->f[tid].kinvmin_d, mn[tid]); }
-}
 
 /* ---- classify + zero ------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(32) k_classify(Dev d) {
