@@ -458,22 +458,43 @@ __device__ __forceinline__ u32 ld4u(const u8 *p) {
   return __funnelshift_r(w[0], w[1], 8 * a);
 }
 /* n >= 1 bytes equal?  Both sides in shared memory, any alignment (may read up to three bytes past either side).
- * Each side keeps the previous aligned word, so a step of four bytes is two loads, two funnel shifts and one LOP3. */
+ * Each side keeps the previous aligned word, so a step of four bytes is two loads, two funnel shifts and one LOP3; the loop
+ * is kept rolled (two steps per trip): the runs are short and the set-up of a deeper unrolling costs more than it saves. */
+__device__ __forceinline__ u32 lds_w(u32 addr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ bool eq_bytes(const u8 *x, const u8 *y, u32 n) {
-  const u32 ax = (u32)(size_t)x & 3u, ay = (u32)(size_t)y & 3u;
-  const u32 *wx = (const u32 *)(x - ax), *wy = (const u32 *)(y - ay);
-  const u32 sx = 8 * ax, sy = 8 * ay;
-  u32 x0 = *wx, y0 = *wy, diff = 0;
+  u32 xa = (u32)__cvta_generic_to_shared(x), ya = (u32)__cvta_generic_to_shared(y);
+  const u32 sx = (xa & 3u) * 8u, sy = (ya & 3u) * 8u;
+  xa &= ~3u; ya &= ~3u;
+  u32 x0 = lds_w(xa), y0 = lds_w(ya), diff = 0;
+#pragma unroll 2
   for (; n >= 4; n -= 4) {
-    const u32 x1 = *++wx, y1 = *++wy;
+    xa += 4; ya += 4;
+    const u32 x1 = lds_w(xa), y1 = lds_w(ya);
     diff |= __funnelshift_r(x0, x1, sx) ^ __funnelshift_r(y0, y1, sy);
     x0 = x1; y0 = y1;
   }
   if (n) {
-    const u32 x1 = wx[1], y1 = wy[1];
+    const u32 x1 = lds_w(xa + 4), y1 = lds_w(ya + 4);
     diff |= (__funnelshift_r(x0, x1, sx) ^ __funnelshift_r(y0, y1, sy)) & (0xFFFFFFFFu >> (8 * (4 - n)));
   }
   return diff == 0;
+}
+/* bit p set iff x[p] != y[p], p < n <= 32 (both sides in shared memory, any alignment; may read up to three bytes past either side) */
+__device__ __forceinline__ u32 neq_mask(const u8 *x, const u8 *y, u32 n) {
+  u32 xa = (u32)__cvta_generic_to_shared(x), ya = (u32)__cvta_generic_to_shared(y);
+  const u32 sx = (xa & 3u) * 8u, sy = (ya & 3u) * 8u;
+  xa &= ~3u; ya &= ~3u;
+  u32 x0 = lds_w(xa), y0 = lds_w(ya), mm = 0;
+#pragma unroll 1
+  for (u32 p = 0; p < n; p += 4) {
+    xa += 4; ya += 4;
+    const u32 x1 = lds_w(xa), y1 = lds_w(ya);
+    const u32 v = __funnelshift_r(x0, x1, sx) ^ __funnelshift_r(y0, y1, sy);
+    const u32 t = (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u; /* bit 7 of a byte: the byte is not zero */
+    mm |= ((t * 0x00204081u) >> 28) << p;
+    x0 = x1; y0 = y1;
+  }
+  return n >= 32 ? mm : mm & ((1u << n) - 1u);
 }
 
 /* ---- title line staging (k_stat1, phy_title.cuh) ----------------------------------------------------------------- */

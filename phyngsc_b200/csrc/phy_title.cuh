@@ -120,19 +120,21 @@ __global__ void __launch_bounds__(S1W * 32) k_stat1(Dev d) {
     u32 touched = 0, prev_bm = 0, first_bm = 0, zero_d = 0;
     i32 err = 0;
     bool fits = true, n_fits = true; /* the slots are sized for the longest title line of the batch (BatchHdr::max_tlen): always true */
-    u32 n_ts = 0, n_te = 0;
+    u32 n_ts = 0, n_te = 0, nn_ts = 0, nn_te = 0; /* title line of this lane's record in the next block, and in the one after it */
     { const u32 i = g0 * 32 + lane; if (i < R) { const u32 r = P.first_rec + i; n_ts = d.rstart[r]; n_te = d.te[r]; n_fits = stage_title_line(d.in, slots_a + lane * tsz, tsz, n_ts, n_te); } }
     cp_async_commit();
+    { const u32 i = (g0 + 1) * 32 + lane; if (g0 + 1 < g1 && i < R) { const u32 r = P.first_rec + i; nn_ts = d.rstart[r]; nn_te = d.te[r]; } }
     for (u32 g = g0; g < g1; ++g) {
       const u32 nrec = min(32u, R - g * 32), buf = (g - g0) & 1u;
       const bool active = lane < nrec;
       const u32 ts = n_ts, te = n_te;
       const bool cur_fits = n_fits;
       fits = fits && cur_fits;
-      { /* next block's record: its title line starts to arrive now */
-        const u32 i = (g + 1) * 32 + lane;
-        if (g + 1 < g1 && i < R) { const u32 rn = P.first_rec + i; n_ts = d.rstart[rn]; n_te = d.te[rn]; n_fits = stage_title_line(d.in, slots_a + ((buf ^ 1u) * 32 + lane) * tsz, tsz, n_ts, n_te); }
+      { /* next block's record: its title line starts to arrive now (its position was loaded one block earlier) */
+        if (g + 1 < g1 && (g + 1) * 32 + lane < R) { n_ts = nn_ts; n_te = nn_te; n_fits = stage_title_line(d.in, slots_a + ((buf ^ 1u) * 32 + lane) * tsz, tsz, n_ts, n_te); }
         cp_async_commit();
+        const u32 i2 = (g + 2) * 32 + lane;
+        if (g + 2 < g1 && i2 < R) { const u32 rn = P.first_rec + i2; nn_ts = d.rstart[rn]; nn_te = d.te[rn]; }
       }
       cp_async_wait<1>();
       const u8 *b = slots + (size_t)(buf * 32 + lane) * tsz - (ts & ~15u); /* b[pos] is valid for the positions of this lane's title line */
@@ -165,8 +167,7 @@ __global__ void __launch_bounds__(S1W * 32) k_stat1(Dev d) {
             const u32 m = len < len0 ? len : len0;
             const u8 *dp = b + t.start;
             if (len0 <= 32) { /* Hamming mask of the field in one register */
-              u32 mm = 0;
-              for (u32 p = 0; p < m; ++p) mm |= (dp[p] != d0[p] ? 1u : 0u) << p;
+              const u32 mm = m ? neq_mask(dp, d0, m) : 0u;
               if (mm & ~S.mism[f][0]) atomicOr(&S.mism[f][0], mm);
             } else {
               u32 diff = 0;
