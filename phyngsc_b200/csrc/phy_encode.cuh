@@ -52,7 +52,9 @@ struct WarpStream {
     const u32 nf = st.full_words(bits);
     const bool room = st.tpos + nf + 1 <= slot_words;
     if (!room) over = true;
-    for (u32 j = lane; j < nf; j += 32) { const u32 v = cc[j]; if (room) slot[st.tpos + j] = v; cc[j] = 0; }
+    u32 *dst = slot + st.tpos;
+#pragma unroll 1
+    for (u32 j = lane; j < nf; j += 32) { const u32 v = cc[j]; if (room) dst[j] = v; cc[j] = 0; } /* a few trips: kept rolled */
     const u32 rem = cc[nf]; /* no lane clears this word in the loop above */
     __syncwarp();
     if (lane == 0) { cc[nf] = 0; cc[0] = rem; }

@@ -84,7 +84,10 @@ PHY_HD void lane_concat(u32 *cc, u32 pos, const u32 *lp, u32 stride, u32 nbits) 
   const u32 sh = pos & 31, nw = (nbits + 31) >> 5;
   const u32 own_lo = (pos + 31) >> 5, own_hi = (pos + nbits) >> 5; /* words [own_lo, own_hi) hold bits of this lane only: plain stores */
   u32 idx = pos >> 5, prev = 0;
-  for (u32 k = 0; k < nw; ++k, ++idx) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (u32 k = 0; k < nw; ++k, ++idx) { /* a few trips: kept rolled */
     const u32 w = lp[k * stride];
     const u32 v = shr_c(w, prev, sh); /* (prev:w) >> sh: the tail of the previous source word and the head of this one */
     if (idx >= own_lo && idx < own_hi) cc[idx] = v; else cc_or(cc, idx, v);
