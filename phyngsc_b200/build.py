@@ -35,7 +35,8 @@ def build_lib(force=False, verbose=False):
     src = [os.path.join(CSRC, f) for f in ("phy_b200.cu", "phy_container.cpp")]
     deps = src + [os.path.join(CSRC, f) for f in ("phy_core.cuh", "phy_kernels.cuh", "phy_fast.cuh", "phy_encode.cuh", "phy_seqstat.cuh", "phy_title.cuh")] + [os.path.join(HERE, "..", "include", "phyngsc_b200.h"), os.path.join(HOST, "phy_decode.hpp")]
     if force or _newer(LIB, deps):
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + src
+        extra = os.environ.get("PHY_NVCC_EXTRA", "").split()  # experiment switches (-DPHY_...=n); empty in normal builds
+        cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + src
         subprocess.check_call(cmd)
     return LIB
 

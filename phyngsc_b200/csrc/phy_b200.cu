@@ -24,7 +24,7 @@
 using namespace phy;
 
 #define NKERN 20
-#define GROUPS_MAX 4
+#define GROUPS_MAX 8
 
 static_assert(sizeof(phy_subblock_desc) == 72, "phy_subblock_desc layout is part of the ABI");
 static_assert(sizeof(phy_region_params) == 40, "phy_region_params layout is part of the ABI");
@@ -80,7 +80,6 @@ struct phy_ctx {
   } while (0)
 
 static const u32 SPAN_MAX = 96 * 1024;
-static const u32 QH_DYN_MAX = 200 * 1024; /* private rows + span buffers of k_qhist */
 static const u32 ENC_STAGE_MAX = 24 * 1024; /* a warp's stage in the encoder kernels: 32 records of up to 768 bytes on average */
 static const u32 ENC_DYN_MAX = 200 * 1024;  /* dynamic shared memory of the single-walk encoder kernels */
 static const u32 PK_SMEM_MAX = 24 * 1024; /* packed quality code tables kept in shared memory by k_lengths / k_emit */

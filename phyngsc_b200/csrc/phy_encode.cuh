@@ -135,8 +135,11 @@ __global__ void __launch_bounds__(32) k_slots(Dev d) {
  * words][CCW words quality][CCW words DNA] */
 __device__ __forceinline__ u32 enc_qd_warp_bytes(const Dev &d) { return d.qd_nbuf * d.qd_stage + (32u * d.fg.lpw_q + 2u * CCW) * 4u; }
 
+#ifndef PHY_QD_MINB
+#define PHY_QD_MINB 1
+#endif
 template <int G>
-__global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_qd(Dev d) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, PHY_QD_MINB) k_enc_qd(Dev d) {
   constexpr u32 RW = 32 / G; /* records per round of a warp */
   extern __shared__ uint4 dyn_smem[];
   __shared__ __align__(16) u8 codes[512];

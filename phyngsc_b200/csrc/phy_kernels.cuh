@@ -14,18 +14,22 @@
  * Stages (every launch covers all subblocks of the batch, or of one subblock group -- see run_batch in phy_b200.cu):
  *   nl_count -> nl_scan -> nl_emit      record splitter            (phyNGSC.cpp:254-331)
  *   plan, spanmax                       window chaining, shared-memory sizing (phyNGSC.cpp:168-250, 744-755)
- *   stat1, xdelta                       validation, ambiguity transfer, DNA alphabet, title field reductions
- *                                                                  (phyNGSC.cpp:383-423, 462-653; tasks.cpp:22-223)
- *   qhist                               raw per-position quality histogram (tasks.cpp:260-286)
+ *   stat1, xdelta (phy_title.cuh)       the one tokeniser pass: title field reductions, parsed title rows (phyNGSC.cpp:383-423, tasks.cpp:22-223)
+ *   seqstat (phy_seqstat.cuh)           validation, ambiguity transfer, DNA alphabet, raw per-position quality histogram
+ *                                                                  (phyNGSC.cpp:462-653; tasks.cpp:260-286)
  *   classify, zero_hist                 coding decisions, arena layout, coded quality tables (tasks.cpp:196-257)
- *   stat2                               numeric / char histograms, 32-record block descriptors (tasks.cpp:64-93,127-182),
+ *   stat2 (phy_title.cuh), dnacount     numeric / char histograms, 32-record block descriptors (tasks.cpp:64-93,127-182),
  *                                       exact DNA symbol counts when the DNA is Huffman coded (tasks.cpp:233-236)
  *   huff                                one warp per table         (huffman.cpp:18-118)
- *   lengths -> layout -> outscan        bit lengths, scans, header assembly, payload offsets
- *   zero_out -> emit                    BitStream emission         (tasks.cpp:393-509,544-557,609-619)
+ *   slots, enc_title, enc_qd            single-walk encoder (phy_encode.cuh, phy_title.cuh): every task's streams into a temporary buffer
+ *   lengths -> layout -> outscan        bit lengths of the subblocks the single-walk kernels could not take, scans, header
+ *                                       assembly, payload offsets
+ *   zero_out -> place, emit             final placement of the tasks' runs / BitStream emission of the two-walk path
+ *                                                                  (tasks.cpp:393-509,544-557,609-619)
  *
- * The kernels that read record bytes (stat1, qhist, stat2, lengths, emit) stream them into shared memory with the
- * bulk-copy engine (cp.async.bulk + mbarrier): span_request / ChunkStage / WarpStage below.
+ * The kernels that read whole records (seqstat, enc_qd, dnacount, lengths, emit) stream them into shared memory with the
+ * bulk-copy engine (cp.async.bulk + mbarrier): span_request / ChunkStage / WarpStage below; k_stat1 stages title lines only
+ * (16-byte cp.async per lane).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -41,11 +45,6 @@ constexpr int CH = 128;            /* records per work item (4 warps; one warp =
 constexpr int NLT = PHY_NLT;        /* threads per CTA of the record splitter                               */
 constexpr int TILE = NLT * 64;     /* bytes per newline-index tile (NLT threads x 64 bytes)                */
 constexpr int SUPER = 64;          /* tiles per supertile: the single-CTA scan runs over supertiles         */
-#ifndef PHY_QCH
-#define PHY_QCH 2048
-#endif
-constexpr int QCH = PHY_QCH;          /* records per quality-histogram work item (16 chunks)                  */
-constexpr u32 QR_ROWW = 97;        /* words per row of k_qhist's private table (odd: neighbouring rows start in different banks) */
 constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at the end of a subblock's arena      */
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
 constexpr u32 PK_ESC = 0xF000u;   /* packed quality entries at or above this value: code longer than 12 bits, read the 64-bit entry */
@@ -61,7 +60,7 @@ struct BatchHdr {      /* device -> host after the plan kernel and again after o
   u64 total_out;       /* end of the output used (byte offset in d.out)                          */
   u64 out_begin;       /* where this group's payloads start (= the previous group's total_out)   */
   u64 next_pos;        /* region-relative position where the next window starts                 */
-  u32 max_qchunks;
+  u32 pad_q;
   u32 max_nf;          /* max over subblocks of the separator count of the first title        */
   u32 max_pk_bytes;    /* max over subblocks of the packed quality code tables ((max_qlen + 1) * n_qualities u16) */
   u32 max_len;         /* longest sequence line of the batch's subblocks */
@@ -98,11 +97,7 @@ struct Dev {
   u32 span_bytes;             /* dynamic shared memory available for record spans              */
   u32 max_nf;                 /* title fields (sizes the numeric-value table behind the span)  */
   u32 pk_bytes;               /* shared memory behind the span for the packed quality code tables */
-  u32 qh_nbuf;                /* span buffers (pipeline stages) of a k_qhist CTA, 1..8 */
-  u32 s2_nbuf;                /* stage buffers of a k_stat2 CTA (1 or 2) */
-  u32 qh_rows;                /* rows of a k_qhist CTA's private table */
   u32 enc_stage;              /* bytes of one warp's stage buffer in the encoder kernels (a 32-record block) */
-  u32 qh_recs, qh_stage;      /* records per pipeline stage of k_qhist (128, 64 or 32) and the bytes of a stage buffer */
   /* single-walk encoder (phy_encode.cuh) */
   u32 *tmp; u64 tmp_cap;      /* temporary buffer of the tasks' runs (words) */
   u64 *tmp_used;              /* words handed out so far in this batch */
@@ -199,7 +194,7 @@ __global__ void __launch_bounds__(1024) k_nl_scan(Dev d) {
   if (threadIdx.x == 0) {
     const u32 total = carry;
     d.hdr->NL = total; d.hdr->NR = total / 4;
-    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->max_qchunks = 0; d.hdr->max_rec = 0; d.hdr->max_tlen = 0; d.hdr->max_qcode = 0; d.hdr->pad_hdr = 0;
+    d.hdr->status = 0; d.hdr->S = 0; d.hdr->max_chunks = 0; d.hdr->max_span = 0; d.hdr->max_nf = 0; d.hdr->max_pk_bytes = 0; d.hdr->max_len = 0; d.hdr->max_span64 = 0; d.hdr->max_span32 = 0; d.hdr->total_out = 0; d.hdr->pad_q = 0; d.hdr->max_rec = 0; d.hdr->max_tlen = 0; d.hdr->max_qcode = 0; d.hdr->pad_hdr = 0;
     if (total / 4 + 1 > d.maxrec) d.hdr->status = E_CAPACITY;
     d.rstart[0] = d.start_pos;
   }
@@ -271,9 +266,15 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
   u32 lane = threadIdx.x;
   if (H->status || st.done || st.status) { if (lane == 0) { H->S = 0; H->next_pos = (u64)st.bytes_read; } return; }
   const u32 NR = H->NR, NL = H->NL;
-  u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0, max_qchunks = 0;
+  u32 F = 0, S = 0, chunk_base = 0, max_chunks = 0;
   i64 avg_n = 1;
   float dens = 1.0f / 128.0f;
+  /* Software pipeline over the windows: the probe of window k + 1 (its position is predictable: one window's worth of records
+   * behind this window's) is loaded into registers while window k is resolved, and the title newline of window k + 1's second
+   * record is taken from window k's probe, so that in the common case no memory latency is left on the chain. */
+  u32 nte = 0xFFFFFFFFu, nte_idx = 0xFFFFFFFFu; /* te[nte_idx], kept from the previous window's probe */
+  u32 npbase = 0xFFFFFFFFu;                     /* base index of the pre-loaded probe (0xFFFFFFFF: none) */
+  uint4 nprs = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), npte = nprs;
   while (!st.done && S < d.max_sb) {
     i64 ws = st.bytes_read - d.batch_base; /* batch-relative window start */
     if (!d.batch_is_final && ws + st.rsize + (i64)d.slack > (i64)d.len) break;
@@ -303,25 +304,39 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     /* One round trip in the common case: the title newline of the second record, and a 128-wide probe (four table
      * entries per lane) of the record table around the interpolated position of the last record, are loaded together. */
     u32 pbase;
-    { i64 gb = guess - 64; pbase = gb < (i64)Fs + 2 ? Fs + 2 : (u32)gb; pbase = (pbase + 3u) & ~3u; }
+    uint4 prs = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), pte = prs;
+    bool have = npbase != 0xFFFFFFFFu && npbase >= Fs + 2;
+    if (have) { /* loaded while the previous window was resolved: usable when it brackets the target */
+      pbase = npbase; prs = nprs; pte = npte;
+      const i64 lo = (i64)__shfl_sync(0xFFFFFFFFu, prs.x, 0), hi = pbase + 127u > NR ? (i64)0xFFFFFFFFu : (i64)__shfl_sync(0xFFFFFFFFu, prs.w, 31);
+      have = lo < target && hi >= target;
+    }
+    if (!have) {
+      i64 gb = guess - 64; pbase = gb < (i64)Fs + 2 ? Fs + 2 : (u32)gb; pbase = (pbase + 3u) & ~3u;
+      const u32 pi = pbase + 4 * lane;
+      prs = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); pte = prs;
+      if (pi <= NR) { prs = *(const uint4 *)(d.rstart + pi); pte = *(const uint4 *)(d.te + pi); } /* the tables have four entries of slack behind the last record */
+    }
     const u32 pidx = pbase + 4 * lane;
-    /* the probe regions of the next two windows are predictable: bring them into L2 while this window is resolved */
-#pragma unroll
-    for (u32 a = 1; a <= 2; ++a) {
-      const u64 nidx = (u64)pidx + a * (u64)avg_n;
+    if (pidx > NR) prs.x = 0xFFFFFFFFu;
+    if (pidx + 1 > NR) prs.y = 0xFFFFFFFFu;
+    if (pidx + 2 > NR) prs.z = 0xFFFFFFFFu;
+    if (pidx + 3 > NR) prs.w = 0xFFFFFFFFu;
+    { /* the next window's probe: about as many records behind this window's last as this window holds */
+      const i64 gn = 2 * guess - (i64)F - 64;
+      npbase = 0xFFFFFFFFu;
+      if (S > 0 && gn > (i64)pbase && gn + 4 * 31 + 3 <= (i64)d.maxrec) {
+        npbase = ((u32)gn + 3u) & ~3u;
+        nprs = *(const uint4 *)(d.rstart + npbase + 4 * lane); npte = *(const uint4 *)(d.te + npbase + 4 * lane);
+      }
+      /* and the probe region of the window after it into L2 */
+      const u64 nidx = (u64)pidx + 2 * (u64)avg_n;
       if (S > 0 && nidx + 3 <= (u64)d.maxrec) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(d.rstart + nidx));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(d.te + nidx));
       }
     }
-    const u32 te_f1 = 4ull * (Fs + 1) < NL ? d.te[Fs + 1] : 0xFFFFFFFFu;
-    uint4 prs = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), pte = prs;
-    if (pidx <= NR) { /* the tables have four entries of slack behind the last record */
-      prs = *(const uint4 *)(d.rstart + pidx); pte = *(const uint4 *)(d.te + pidx);
-      if (pidx + 1 > NR) prs.y = 0xFFFFFFFFu;
-      if (pidx + 2 > NR) prs.z = 0xFFFFFFFFu;
-      if (pidx + 3 > NR) prs.w = 0xFFFFFFFFu;
-    }
+    const u32 te_f1 = Fs + 1 == nte_idx ? nte : 4ull * (Fs + 1) < NL ? d.te[Fs + 1] : 0xFFFFFFFFu;
     last = Fs;
     if ((i64)te_f1 < size_lim) {
       u32 m;
@@ -354,6 +369,15 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     }
     P.n_records = last - F + 1;
     P.warnings = capped ? 1u : 0u;
+    { /* the title newline of the next window's second record usually sits in this window's probe */
+      const u32 q = last + 2 - pbase;
+      nte_idx = 0xFFFFFFFFu;
+      if (last + 2 >= pbase && q < 128u) {
+        const u32 qk = q & 3u, tsel = qk == 0 ? pte.x : qk == 1 ? pte.y : qk == 2 ? pte.z : pte.w;
+        nte = 4ull * (last + 2) < NL ? __shfl_sync(0xFFFFFFFFu, tsel, q >> 2) : 0xFFFFFFFFu;
+        nte_idx = last + 2;
+      }
+    }
     if (rs_next == 0xFFFFFFFFu) rs_next = d.rstart[last + 1];
     P.bytes_consumed = (u64)((i64)rs_next - ws);
     if (lane == 0) d.plans[S] = P;
@@ -361,7 +385,6 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     u32 nch = (P.n_records + CH - 1) / CH;
     chunk_base += nch;
     max_chunks = max(max_chunks, nch);
-    max_qchunks = max(max_qchunks, (P.n_records + QCH - 1) / QCH);
     avg_n = (i64)P.n_records; dens = (float)P.n_records / (float)max((i64)1, (i64)P.bytes_consumed); /* the previous window predicts best: record sizes drift along a file */
     ++S; F = last + 1;
     /* phyNGSC.cpp:745-755 */
@@ -372,7 +395,7 @@ __global__ void __launch_bounds__(32) k_plan(Dev d) {
     st.n_subblocks_total++;
   }
   if (lane == 0) {
-    H->S = S; H->max_chunks = max_chunks; H->max_qchunks = max_qchunks;
+    H->S = S; H->max_chunks = max_chunks;
     H->next_pos = (u64)st.bytes_read;
     if (st.status) H->status = st.status;
     *d.plan_state = st;
@@ -557,153 +580,7 @@ __global__ void __launch_bounds__(256) k_zero_hist(Dev d) {
   }
 }
 
-/* ---- per-position quality histogram (tasks.cpp:260-286) ----------------------------------------------------- */
-/* Runs BEFORE the classification: it counts raw quality bytes (after the ambiguity transfer, phyNGSC.cpp:575-580)
- * per read position into the subblock's raw table raw[position + 1][byte] (row 0 = totals); the quality alphabet
- * and the coded tables are derived from it afterwards (k_classify, k_zero_hist).
- * Row (position) p of a private copy in shared memory is owned by exactly one thread, so the increments need no
- * atomics.  A CTA counts at most QCH = 1024 records, so the private counters are 16 bits wide; a private row holds
- * the bytes 33..127 (anything else -- transferred ambiguity codes, garbage -- goes straight to the global table).
- * `slots` copies of the rows work on different records.  The records are first split into a plain list and the
- * (rare) list of records with an ambiguity transfer; the plain loop keeps eight quality bytes in flight per thread
- * and has no per-symbol test at all when every plain record is at least as long as the row range. */
-constexpr int QU = 8;          /* records in flight per thread */
 __device__ __forceinline__ u32 lds_u8(u32 addr) { u16 v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ void sm_red_inc(u32 addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
-/* dynamic shared memory: [qh_rows * QR_ROWW words: the CTA's private table][qh_nbuf span buffers] */
-__global__ void __launch_bounds__(512) k_qhist(Dev d) { /* 256 threads for short reads, 512 for long ones (more record slots per private table) */
-  extern __shared__ uint4 dyn_smem[];
-  __shared__ __align__(8) u64 bars[8];
-  __shared__ u32 m_qs[CH + 64];  /* shared-memory address of the quality line: plain records from the front (padded with */
-  __shared__ u16 m_len[CH + 64]; /* dummies), records with an ambiguity transfer from the back                           */
-  __shared__ u32 n_plain, n_x;
-  __shared__ u32 c_lo[QCH / 32 + 1]; /* first byte of each of the CTA's record groups (and the end of the last) */
-  const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
-  const SbPlan P = d.plans[s];
-  if (P.status || d.acc[s].status) return;
-  const u32 QS = d.qh_recs; /* records per pipeline stage */
-  const u32 nchunk = (P.n_records + QS - 1) / QS, c0 = blockIdx.x * (QCH / QS), c1 = min(c0 + QCH / QS, nchunk);
-  if (c0 >= nchunk) return;
-  if (tid <= c1 - c0) c_lo[tid] = d.rstart[P.first_rec + min((c0 + tid) * QS, P.n_records)];
-  const u32 Lp = d.acc[s].max_qlen;
-  if (Lp == 0) return;
-  u32 *raw = raw_table(d, s);
-  const u32 RP = Lp < d.qh_rows ? Lp : d.qh_rows;  /* rows (read positions) per pass */
-  const u32 slots = RP < NT ? min(NT / RP, 64u / QU) : 1u; /* records the CTA counts side by side (the list padding holds QU * slots dummies) */
-  u32 *hist = (u32 *)dyn_smem;
-  const u32 nbuf = d.qh_nbuf;
-  const u32 hist_a = (u32)__cvta_generic_to_shared(hist), buf_a0 = hist_a + ((d.qh_rows * (QR_ROWW * 4) + 15u) & ~15u), bar_a0 = (u32)__cvta_generic_to_shared(&bars[0]);
-  if (tid == 0) { for (u32 k = 0; k < nbuf; ++k) mbar_init(bar_a0 + 8 * k, 1); mbar_fence_init(); }
-  /* one thread: request chunk c into stage (c - c0) % nbuf */
-  auto request = [&](u32 c) {
-    const u32 st = (c - c0) % nbuf;
-    span_request(d.in, c_lo[c - c0], c_lo[c - c0 + 1], buf_a0 + st * d.qh_stage, bar_a0 + 8 * st);
-  };
-  const u32 slot = tid / RP, p = tid % RP;
-  const bool owner = slot < slots;
-  u32 phases = 0; /* bit b: parity to wait for on barrier b */
-  /* row p of the private table: counters 0..94 = bytes 33..127, 95 = "some other byte" (those go to the global table one
-   * by one), 96 = no symbol.  Rows are QR_ROWW = 97 words apart, so the 32 positions a warp works on fall into 32 banks. */
-  for (u32 p0 = 0; p0 < Lp; p0 += RP) {
-    for (u32 i = tid; i < RP * QR_ROWW; i += NT) hist[i] = 0;
-    __syncthreads(); /* also: barriers initialised, c_lo filled, previous pass has left the buffers */
-    if (tid == 0) for (u32 c = c0; c < c1 && c < c0 + (nbuf > 1 ? nbuf - 1 : 1u); ++c) request(c); /* fill the pipeline */
-    /* this thread's record of the first chunk */
-    u32 te = 0, se = 0, kx = 0;
-    { const u32 i = c0 * QS + tid; if (tid < QS && i < P.n_records) { te = d.te[P.first_rec + i]; se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; } }
-    for (u32 c = c0; c < c1; ++c) {
-      const u32 b = (c - c0) % nbuf;
-      const u32 buf_b = buf_a0 + b * d.qh_stage, bar_b = bar_a0 + 8 * b;
-      const u32 nrec = min(QS, P.n_records - c * QS);
-      if (tid == 0) { n_plain = 0; n_x = 0; }
-      if (nbuf > 1 && tid == 0 && c + nbuf - 1 < c1) request(c + nbuf - 1); /* into the stage that iteration c-1 has left */
-      const u32 alo = c_lo[c - c0] & ~15u;
-      __syncthreads();
-      /* record lists of this chunk (order is irrelevant for a histogram) */
-      bool covers = true;
-      if (tid < ((QS + 31u) & ~31u)) {
-        const bool on = tid < nrec, x = on && (kx & 0x8000u);
-        const u32 L = se - te - 1;
-        const u32 bx = __ballot_sync(0xFFFFFFFFu, x), bp = __ballot_sync(0xFFFFFFFFu, on && !x);
-        u32 basex = 0, basep = 0;
-        if (lane == 0) { if (bx) basex = atomicAdd(&n_x, (u32)__popc(bx)); if (bp) basep = atomicAdd(&n_plain, (u32)__popc(bp)); }
-        basex = __shfl_sync(0xFFFFFFFFu, basex, 0); basep = __shfl_sync(0xFFFFFFFFu, basep, 0);
-        if (on) {
-          const u32 below = (1u << lane) - 1u;
-          const u32 k = x ? CH + 63 - (basex + __popc(bx & below)) : basep + __popc(bp & below);
-          m_qs[k] = buf_b + (se + 3 - alo); m_len[k] = (u16)L;
-          covers = x || L >= p0 + RP;
-        }
-        /* next chunk's record, in flight while this chunk is counted */
-        const u32 i = (c + 1) * QS + tid;
-        te = se = kx = 0;
-        if (tid < QS && c + 1 < c1 && i < P.n_records) { te = d.te[P.first_rec + i]; se = d.se[P.first_rec + i]; kx = d.kx[P.first_rec + i]; }
-      }
-      const bool uniform = __syncthreads_and(covers);
-      const u32 np = n_plain, nx = n_x;
-      const u32 np_pad = (np + QU * slots - 1) / (QU * slots) * (QU * slots);
-      for (u32 i = np + tid; i < np_pad; i += NT) { m_qs[i] = buf_b; m_len[i] = 0; } /* dummies: a valid address, no symbols */
-      mbar_wait(bar_b, (phases >> b) & 1u); phases ^= 1u << b;
-      __syncthreads();
-      if (owner)
-        for (u32 pr = p; pr < RP; pr += NT) { /* more rows per pass than threads: a thread takes several positions */
-          const u32 pos = p0 + pr, row_a = hist_a + pr * (QR_ROWW * 4);
-          if (uniform) { /* every plain record covers this row range: no per-symbol length test */
-            const u32 full = np / (QU * slots) * (QU * slots);
-            for (u32 i0 = slot; i0 < full; i0 += QU * slots) {
-              u32 q[QU];
-#pragma unroll
-              for (int k = 0; k < QU; ++k) q[k] = lds_u8(m_qs[i0 + k * slots] + pos);
-#pragma unroll
-              for (int k = 0; k < QU; ++k) sm_red_inc(row_a + 4 * min(q[k] - 33u, 95u));
-            }
-            for (u32 i = full + slot; i < np; i += slots) sm_red_inc(row_a + 4 * min(lds_u8(m_qs[i] + pos) - 33u, 95u));
-          } else {
-            for (u32 i0 = slot; i0 < np; i0 += QU * slots) {
-              u32 q[QU];
-#pragma unroll
-              for (int k = 0; k < QU; ++k) {
-                const u32 i = i0 + k * slots;
-                q[k] = 96u;
-                if (pos < (u32)m_len[i]) q[k] = min(lds_u8(m_qs[i] + pos) - 33u, 95u);
-              }
-#pragma unroll
-              for (int k = 0; k < QU; ++k) sm_red_inc(row_a + 4 * q[k]);
-            }
-          }
-          /* ambiguity-transfer records: the base under a transferred quality byte selects the offset */
-          for (u32 i = slot; i < nx; i += slots) {
-            const u32 L = m_len[CH + 63 - i], qa = m_qs[CH + 63 - i];
-            if (pos >= L) continue;
-            const u32 qq = lds_u8(qa + pos) + g_xq_lut[lds_u8(qa - 3 - L + pos)], cc = qq - 33u;
-            if (cc < 95u) sm_red_inc(row_a + 4 * cc);
-            else atomicAdd(raw + (pos + 1) * 256 + qq, 1u);
-          }
-        }
-      __syncthreads(); /* the chunk's buffer and lists are free again */
-      if (nbuf == 1 && tid == 0 && c + 1 < c1) request(c + 1);
-    }
-    const u32 rows = min(RP, Lp - p0);
-    { /* bytes outside 33..127 in plain records (counter 95 of a row): rare; recount them exactly from global memory */
-      bool any = false;
-      for (u32 pr = tid; pr < rows; pr += NT) any = any || hist[pr * QR_ROWW + 95] != 0;
-      if (__syncthreads_or(any)) {
-        const u32 i_end = min(c1 * QS, P.n_records);
-        for (u32 i = c0 * QS + tid; i < i_end; i += NT) {
-          const u32 r = P.first_rec + i;
-          if (d.kx[r] & 0x8000u) continue;
-          const u32 tei = d.te[r], sei = d.se[r], L = sei - tei - 1;
-          for (u32 pr = 0; pr < rows && p0 + pr < L; ++pr)
-            if (hist[pr * QR_ROWW + 95]) { const u32 v = d.in[sei + 3 + p0 + pr]; if (v - 33u >= 95u) atomicAdd(raw + (p0 + pr + 1) * 256 + v, 1u); }
-        }
-      }
-    }
-    for (u32 i = tid; i < rows * 95; i += NT) {
-      const u32 pr = i / 95, c = i % 95, v = hist[pr * QR_ROWW + c];
-      if (v) atomicAdd(raw + (p0 + pr + 1) * 256 + 33 + c, v);
-    }
-  }
-}
 
 /* ---- shared pieces of the per-record title kernels ------------------------------------------------------------ */
 
@@ -724,7 +601,7 @@ constexpr int CSLOTS = 8; /* per-position char tables whose histogram a CTA keep
 #ifndef PHY_S2G
 #define PHY_S2G 8
 #endif
-constexpr int S2G = PHY_S2G;    /* 128-record chunks per k_stat2 CTA */
+constexpr int S2G = PHY_S2G;    /* 128-record chunks per k_dnacount CTA */
 
 /* field classes and the list of non-constant fields of a subblock, copied to shared memory once per CTA */
 struct TitleTabs { FieldClass fc[MAXF]; u16 ncskip[MAXF]; u8 ncf[MAXF]; };
