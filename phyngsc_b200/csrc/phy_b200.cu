@@ -360,7 +360,8 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   d.sq_rows = H.max_len < 1 ? 1u : H.max_len > RAW_ROWS - 1 ? RAW_ROWS - 1 : H.max_len;
   static const int sqbuf_env = getenv("PHY_SQ_NBUF") ? atoi(getenv("PHY_SQ_NBUF")) : 0;
   d.sq_stage = d.qd_stage; d.sq_nbuf = sqbuf_env == 2 ? 2u : 1u; /* one stage: more resident CTAs hide the copy better (100 bp: 0.66 vs 0.76 ms per GB) */
-  const bool sq_wide = d.sq_rows <= 126; /* 32-bit counters while the private table stays below 48 KB, else 16-bit pairs */
+  static const int sqwide_env = getenv("PHY_SQ_WIDE") ? atoi(getenv("PHY_SQ_WIDE")) : 126;
+  const bool sq_wide = d.sq_rows <= (u32)sqwide_env; /* 32-bit counters while the private table stays below 48 KB, else 16-bit pairs */
   const u32 sq_dyn = ((d.sq_rows * (sq_wide ? 97u : SQ_ROWW) * 4u + 15u) & ~15u) + SQ_WARPS * d.sq_nbuf * d.sq_stage;
   /* k_stat1: two stages of one title slot per lane for every warp; fewer warps per CTA when the title lines are long */
   u32 s1_warps = S1W;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(32) k_slots(Dev d) {
 __device__ __forceinline__ u32 enc_qd_warp_bytes(const Dev &d) { return d.qd_nbuf * d.qd_stage + (32u * d.fg.lpw_q + 2u * CCW) * 4u; }
 
 #ifndef PHY_QD_MINB
-#define PHY_QD_MINB 1
+#define PHY_QD_MINB 3
 #endif
 template <int G>
 __global__ void __launch_bounds__(ENC_WARPS * 32, PHY_QD_MINB) k_enc_qd(Dev d) {

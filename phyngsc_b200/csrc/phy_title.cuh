@@ -413,7 +413,7 @@ __device__ __forceinline__ void title_record_parsed(const Dev &d, const BlockRow
 /* dynamic shared memory per warp: [32 * LPW_T staging words][CCW words][32 words for the info bits] */
 __host__ __device__ __forceinline__ u32 enc_title_warp_bytes() { return (32u * LPW_T + CCW + 32u) * 4u; }
 
-__global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_title(Dev d) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_enc_title(Dev d) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ TitleTabs TT;
   const u32 s = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
