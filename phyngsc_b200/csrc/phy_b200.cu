@@ -41,7 +41,7 @@ struct phy_ctx {
   /* device buffers */
   u8 *in = nullptr; u32 *te = nullptr, *se = nullptr, *rstart = nullptr; u16 *kx = nullptr; u32 *qoff = nullptr, *doff = nullptr, *toff = nullptr, *chunk_first = nullptr, *chunk_last = nullptr;
   u32 *tile_cnt = nullptr, *tile_off = nullptr; uint2 *nl_mask = nullptr;
-  u32 *blk_mask = nullptr, *tv = nullptr, *tp = nullptr, *v0 = nullptr; u64 tv_cap = 0; /* parsed titles (k_stat1 -> k_stat2 / k_enc_title); tv / tp grow on demand */
+  u32 *blk_mask = nullptr, *tv = nullptr, *tc = nullptr, *tp = nullptr, *v0 = nullptr; u64 tv_cap = 0; /* parsed titles (k_stat1 -> k_stat2 / k_enc_title); tv / tp grow on demand */
   PlanState *plan_state = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
   SbAcc *acc = nullptr; SbClass *cls = nullptr; SbOut *sbout = nullptr; u32 *arena = nullptr; u8 *out = nullptr;
   u32 *tmp = nullptr; u64 tmp_cap = 0; u64 *tmp_used = nullptr; /* temporary buffer of the single-walk encoder (words) */
@@ -121,7 +121,7 @@ extern "C" void phy_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->blk_mask, ctx->tv, ctx->tp, ctx->v0, ctx->plan_state,
+  void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->blk_mask, ctx->tv, ctx->tc, ctx->tp, ctx->v0, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1], ctx->hout[2], ctx->hout[3]};
@@ -323,12 +323,13 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     if (need > ctx->tv_cap) {
       if (ctx->tv) { CK(cudaFree(ctx->tv)); ctx->tv = nullptr; }
       if (ctx->tp) { CK(cudaFree(ctx->tp)); ctx->tp = nullptr; }
+      if (ctx->tc) { CK(cudaFree(ctx->tc)); ctx->tc = nullptr; }
       ctx->tv_cap = 0;
       const u64 cap = need + need / 4;
-      CK(cudaMalloc(&ctx->tv, cap * 4)); CK(cudaMalloc(&ctx->tp, cap * 4));
+      CK(cudaMalloc(&ctx->tv, cap * 4)); CK(cudaMalloc(&ctx->tp, cap * 4)); CK(cudaMalloc(&ctx->tc, cap * 4));
       ctx->tv_cap = cap;
     }
-    d.tv = ctx->tv; d.tp = ctx->tp;
+    d.tv = ctx->tv; d.tp = ctx->tp; d.tc = ctx->tc;
   }
   /* launch geometry shared by all subblock groups of the batch */
   {
@@ -833,8 +834,9 @@ static int compress_region_impl(phy_ctx *ctx, const uint8_t *region, uint64_t re
       if (carry > blen) carry = blen;
       CK(cudaMemcpyAsync(inb[slot], inb[up_slot] + (base - up_base), carry, cudaMemcpyDeviceToDevice, ctx->s_in));
     }
-    /* host bytes in pieces: with a reader still filling the region (streamed variant) a piece crosses PCIe as soon as it is there */
-    const u64 piece = 16ull << 20;
+    /* host bytes in pieces: with a reader still filling the region (streamed variants) a piece crosses PCIe as soon as it is
+     * there; a region that is already complete goes in one copy per batch (every copy call costs the engine a few microseconds) */
+    const u64 piece = (wait || io) ? (16ull << 20) : (1ull << 30);
     u8 last_byte = '\n';
     for (u64 o = carry; o < blen;) {
       u64 n = blen - o < piece ? blen - o : piece;

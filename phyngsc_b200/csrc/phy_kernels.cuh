@@ -49,7 +49,8 @@ constexpr u32 RAW_ROWS = 512;      /* rows of the raw per-position table kept at
 constexpr u32 RAW_WORDS = RAW_ROWS * 256;
 constexpr u32 PK_ESC = 0xF000u;   /* packed quality entries at or above this value: code longer than 12 bits, read the 64-bit entry */
 constexpr u32 R0_MAX = 1024;       /* longest title line of record 0 kept in shared memory                 */
-constexpr u32 TP_SAME = 0xFFFFu;   /* Dev::tp start value: the token is record 0's                         */
+constexpr u32 TP_SAME = 0x7FFFu;   /* Dev::tp start value (15 bits) of lanes without a record              */
+constexpr u32 TP_NUM = 0x8000u;    /* Dev::tp bit 15: the token is numeric (utils::is_num), tv holds its value; else tv / tc hold its first 4 / next 4 characters */
 
 struct BatchHdr {      /* device -> host after the plan kernel and again after outscan */
   u32 NL, NR;          /* newlines found, complete records                                      */
@@ -81,10 +82,12 @@ struct Dev {
   u32 *chunk_first, *chunk_last; /* numeric token values of the first / last record of every k_stat1 task (256 records), row = chunk_base + 2 * task, [row][MAXF] */
   /* Parsed titles (written by k_stat1, the only kernel that tokenises): per 32-record block the mask of fields in which
    * some record of the block differs from record 0 of its subblock, and for those fields one row of 32 entries each in tv
-   * (the token's numeric value, utils::to_num) and tp (token start inside the title line | length << 16; start = TP_SAME
-   * for lanes without a record).  Block b of a subblock is block 4 * chunk_base + b of the batch; row of (block, field):
-   * (block * nfs + field) * 32.  v0[subblock][field]: numeric value of record 0's token (fields without a row carry it). */
-  u32 *blk_mask, *tv, *tp, *v0; u32 nfs;
+   * (a numeric token's value, utils::to_num; else the token's first four characters), tc (characters 4..7 of a non-numeric
+   * token of 5..8 characters) and tp (token start inside the title line, 15 bits | TP_NUM | length << 16; start = TP_SAME
+   * for lanes without a record).  Short tokens are thus complete in the rows (a numeric token is the decimal form of its
+   * value) and the later kernels never go back to the input for them.  Block b of a subblock is block 4 * chunk_base + b of
+   * the batch; row of (block, field): (block * nfs + field) * 32.  v0[subblock][field]: numeric value of record 0's token. */
+  u32 *blk_mask, *tv, *tc, *tp, *v0; u32 nfs;
   u32 *tile_cnt, *tile_off; u32 ntiles;
   uint2 *nl_mask;             /* newline bit mask of the batch, 64 input bytes per element */
   PlanState *plan_state; SbPlan *plans; u32 max_sb;

@@ -35,16 +35,31 @@ __device__ __forceinline__ BlockRows block_rows(const Dev &d, const SbPlan &P, u
 __device__ __forceinline__ u32 parsed_value(const Dev &d, const BlockRows &c, u32 f, u32 lane) {
   return ((c.mask >> f) & 1u) ? d.tv[c.row0 + (size_t)f * 32 + lane] : c.v0[f]; /* no row: every record of the block has record 0's token */
 }
-/* token of field f of the block's record `lane`: offset of its first character in the batch, and its length */
-struct TokRef { u32 off, len; bool same0; };
+/* token of field f of the block's record `lane`: its length and its characters -- in a register when the rows hold them
+ * (inreg: character j in bits 8j.. of `chars`, tokens of up to 8 characters), else at offset `off` of the batch input */
+struct TokRef { u32 off, len; u64 chars; bool inreg, same0; };
+__device__ __forceinline__ u64 decimal_chars(u32 v, u32 len) { /* the len-digit decimal form of v, first digit in the low byte */
+  u64 c = 0;
+  for (u32 j = len; j-- > 0;) { const u32 q = v / 10u; c |= (u64)(v - 10u * q + '0') << (8 * j); v = q; }
+  return c;
+}
 __device__ __forceinline__ TokRef parsed_token(const Dev &d, const BlockRows &c, const SbClass &C, const FieldClass &F, u32 f, u32 lane, u32 ts) {
-  TokRef t; t.off = C.ts0 + F.off0; t.len = F.len0; t.same0 = true;
+  TokRef t; t.off = C.ts0 + F.off0; t.len = F.len0; t.same0 = true; t.inreg = false; t.chars = 0;
   if ((c.mask >> f) & 1u) {
-    const u32 e = d.tp[c.row0 + (size_t)f * 32 + lane];
-    if ((e & 0xFFFFu) != TP_SAME) { t.off = ts + (e & 0xFFFFu); t.len = e >> 16; t.same0 = false; }
+    const size_t i = c.row0 + (size_t)f * 32 + lane;
+    const u32 e = d.tp[i];
+    if ((e & 0x7FFFu) != TP_SAME) {
+      t.off = ts + (e & 0x7FFFu); t.len = e >> 16; t.same0 = false;
+      if (t.len <= 8) {
+        t.inreg = true;
+        if (e & TP_NUM) t.chars = decimal_chars(d.tv[i], t.len);
+        else { t.chars = d.tv[i]; if (t.len > 4) t.chars |= (u64)d.tc[i] << 32; }
+      }
+    }
   }
   return t;
 }
+__device__ __forceinline__ u32 token_char(const Dev &d, const TokRef &t, u32 j) { return t.inreg ? (u32)(t.chars >> (8 * j)) & 0xFFu : (u32)d.in[t.off + j]; }
 
 /* ---- stat1 ---------------------------------------------------------------------------------------------------------- */
 constexpr u32 S1W = 8; /* warps (tasks) per CTA */
@@ -177,10 +192,15 @@ __global__ void __launch_bounds__(S1W * 32) k_stat1(Dev d) {
                   if (dp[p] != d0[p]) { const u32 bit = 1u << (p & 31); if (p < (u32)MAXLEN0 && !(S.mism[f][p >> 5] & bit)) atomicOr(&S.mism[f][p >> 5], bit); }
             }
           }
-          { /* the block's row of this field */
+          { /* the block's row of this field: a numeric token leaves its value, any other token its first characters */
             const size_t row = ((blk_base + g) * d.nfs + f) * 32 + lane;
-            d.tv[row] = t.v;
-            d.tp[row] = ok ? ((t.start - ts) | (len << 16)) : TP_SAME;
+            u32 rv = t.v;
+            if (ok && !t.num) {
+              rv = ld4u(b + t.start);
+              if (len > 4 && len <= 8) d.tc[row] = ld4u(b + t.start + 4);
+            }
+            d.tv[row] = rv;
+            d.tp[row] = ok ? ((t.start - ts) | (t.num ? TP_NUM : 0u) | (len << 16)) : TP_SAME;
           }
           const u32 inv_min = __reduce_max_sync(0xFFFFFFFFu, ok ? ~len : 0u);
           const u32 mx = __reduce_max_sync(0xFFFFFFFFu, ok ? len : 0u);
@@ -345,14 +365,21 @@ __global__ void __launch_bounds__(S2W * 32) k_stat2(Dev d) {
         flags |= 1u << f;
         continue;
       }
-      const u32 len_lo = __shfl_sync(0xFFFFFFFFu, t.len, 0), off_lo = __shfl_sync(0xFFFFFFFFu, t.off, 0);
-      bool pred = !on || t.len == len_lo;
+      TokRef t0; /* the block's first token */
+      t0.len = __shfl_sync(0xFFFFFFFFu, t.len, 0); t0.off = __shfl_sync(0xFFFFFFFFu, t.off, 0);
+      t0.inreg = __shfl_sync(0xFFFFFFFFu, (u32)t.inreg, 0) != 0; t0.same0 = false;
+      t0.chars = (u64)__shfl_sync(0xFFFFFFFFu, (u32)t.chars, 0) | (u64)__shfl_sync(0xFFFFFFFFu, (u32)(t.chars >> 32), 0) << 32;
+      bool pred = !on || t.len == t0.len;
+      const bool cmp_reg = t.inreg && t0.inreg; /* both tokens in registers: one comparison */
+      if (on && pred && cmp_reg) pred = ((t.chars ^ t0.chars) & (t.len >= 8 ? ~0ull : (1ull << (8 * t.len)) - 1ull)) == 0;
       const u32 maxlen = __reduce_max_sync(0xFFFFFFFFu, on ? t.len : 0u);
       for (u32 j = 0; j < maxlen; ++j) {
         const bool in_tok = on && j < t.len;
-        const u32 ch = in_tok ? d.in[t.off + j] : 0u;
-        if (in_tok && pred && ch != d.in[off_lo + j]) pred = false;
         const bool need = in_tok && (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u));
+        const bool cmp = in_tok && pred && !cmp_reg;
+        u32 ch = 0;
+        if (need || cmp) ch = token_char(d, t, j);
+        if (cmp && ch != token_char(d, t0, j)) pred = false;
         if (!__any_sync(0xFFFFFFFFu, need)) continue;
         /* lanes of the warp that are at the same character of the same table add once, together */
         const u32 loc = (u32)sm[j < 128 ? j : 128] - C.tchr0;
@@ -400,11 +427,10 @@ __device__ __forceinline__ void title_record_parsed(const Dev &d, const BlockRow
     const TokRef t = parsed_token(d, cr, C, F, f, i, ts);
     if (!F.is_len_const) s.put(t.len - F.min_len, F.bits_len);
     const u16 *sm = (const u16 *)(arena + F.slotmap_off);
-    const u8 *a = d.in + t.off;
     for (u32 j = 0; j < t.len; ++j)
       if (j >= F.len0 || ((F.mism[j >> 5] >> (j & 31)) & 1u)) {
         const u32 tid = sm[j < 128 ? j : 128];
-        const u64 e = ((const u64 *)(arena + C.chr_cl_off + (tid - C.tchr0) * 512u))[a[j]];
+        const u64 e = ((const u64 *)(arena + C.chr_cl_off + (tid - C.tchr0) * 512u))[token_char(d, t, j)];
         s.put((u32)e, (u32)(e >> 32));
       }
   }
