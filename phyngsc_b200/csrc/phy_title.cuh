@@ -31,11 +31,28 @@ __device__ __forceinline__ BlockRows block_rows(const Dev &d, const SbPlan &P, u
   c.row0 = blk * d.nfs * 32; c.v0 = d.v0 + (size_t)s * MAXF; c.mask = d.blk_mask[blk];
   return c;
 }
-/* numeric value of field f of the block's record `lane` (utils::to_num of its token) */
-__device__ __forceinline__ u32 parsed_value(const Dev &d, const BlockRows &c, u32 f, u32 lane) {
-  return ((c.mask >> f) & 1u) ? d.tv[c.row0 + (size_t)f * 32 + lane] : c.v0[f]; /* no row: every record of the block has record 0's token */
+/* One lane's entries of a (block, field) row, loaded ahead of their use (the walkers below fetch field k + 1's entries while
+ * they work on field k: the rows are the only global memory they depend on).  Meaningless when the block has no row. */
+struct RawRow { u32 e, v, c; }; /* tp, tv and -- string fields -- tc; numeric fields carry the block before's last value in c (lane 0) */
+template <bool AHEAD> /* AHEAD: fetched before the entries are looked at, so tc comes along unconditionally; else only when the token needs it */
+__device__ __forceinline__ RawRow load_row(const Dev &d, const BlockRows &c, const BlockRows &prev, bool have_prev, u32 f, u32 lane, bool numeric) {
+  RawRow r; r.e = r.v = r.c = 0;
+  const size_t i = c.row0 + (size_t)f * 32 + lane;
+  if ((c.mask >> f) & 1u) {
+    r.v = d.tv[i];
+    if (!numeric) {
+      r.e = d.tp[i];
+      if (AHEAD || (!(r.e & TP_NUM) && (r.e >> 16) > 4 && (r.e >> 16) <= 8 && (r.e & 0x7FFFu) != TP_SAME)) r.c = d.tc[i];
+    }
+  }
+  if (numeric && have_prev && lane == 0 && ((prev.mask >> f) & 1u)) r.c = d.tv[prev.row0 + (size_t)f * 32 + 31];
+  return r;
 }
-/* token of field f of the block's record `lane`: its length and its characters -- in a register when the rows hold them
+/* numeric value of field f of this lane's record (utils::to_num of its token) */
+__device__ __forceinline__ u32 parsed_value(const BlockRows &c, u32 f, const RawRow &r) { return ((c.mask >> f) & 1u) ? r.v : c.v0[f]; } /* no row: record 0's token */
+/* ... and of the last record of the block before (lane 0) */
+__device__ __forceinline__ u32 parsed_prev_value(const BlockRows &prev, u32 f, const RawRow &r) { return ((prev.mask >> f) & 1u) ? r.c : prev.v0[f]; }
+/* token of field f of this lane's record: its length and its characters -- in a register when the rows hold them
  * (inreg: character j in bits 8j.. of `chars`, tokens of up to 8 characters), else at offset `off` of the batch input */
 struct TokRef { u32 off, len; u64 chars; bool inreg, same0; };
 __device__ __forceinline__ u64 decimal_chars(u32 v, u32 len) { /* the len-digit decimal form of v, first digit in the low byte */
@@ -43,18 +60,14 @@ __device__ __forceinline__ u64 decimal_chars(u32 v, u32 len) { /* the len-digit 
   for (u32 j = len; j-- > 0;) { const u32 q = v / 10u; c |= (u64)(v - 10u * q + '0') << (8 * j); v = q; }
   return c;
 }
-__device__ __forceinline__ TokRef parsed_token(const Dev &d, const BlockRows &c, const SbClass &C, const FieldClass &F, u32 f, u32 lane, u32 ts) {
+__device__ __forceinline__ TokRef parsed_token(const BlockRows &c, const SbClass &C, const FieldClass &F, u32 f, const RawRow &r, u32 ts) {
   TokRef t; t.off = C.ts0 + F.off0; t.len = F.len0; t.same0 = true; t.inreg = false; t.chars = 0;
-  if ((c.mask >> f) & 1u) {
-    const size_t i = c.row0 + (size_t)f * 32 + lane;
-    const u32 e = d.tp[i];
-    if ((e & 0x7FFFu) != TP_SAME) {
-      t.off = ts + (e & 0x7FFFu); t.len = e >> 16; t.same0 = false;
-      if (t.len <= 8) {
-        t.inreg = true;
-        if (e & TP_NUM) t.chars = decimal_chars(d.tv[i], t.len);
-        else { t.chars = d.tv[i]; if (t.len > 4) t.chars |= (u64)d.tc[i] << 32; }
-      }
+  if (((c.mask >> f) & 1u) && (r.e & 0x7FFFu) != TP_SAME) {
+    t.off = ts + (r.e & 0x7FFFu); t.len = r.e >> 16; t.same0 = false;
+    if (t.len <= 8) {
+      t.inreg = true;
+      if (r.e & TP_NUM) t.chars = decimal_chars(r.v, t.len);
+      else { t.chars = r.v; if (t.len > 4) t.chars |= (u64)r.c << 32; }
     }
   }
   return t;
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(128) k_xdelta(Dev d) {
 constexpr u32 S2W = 8;  /* warps per CTA */
 constexpr u32 S2B = 8;  /* 32-record blocks per warp */
 
-__global__ void __launch_bounds__(S2W * 32) k_stat2(Dev d) {
+__global__ void __launch_bounds__(S2W * 32, 6) k_stat2(Dev d) {
   __shared__ TitleTabs T;
   __shared__ u32 chist[CSLOTS * 256];
   const u32 s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -316,19 +329,22 @@ __global__ void __launch_bounds__(S2W * 32) k_stat2(Dev d) {
   load_title_tabs(C, T);
   __syncthreads();
   const u32 g0 = min((blockIdx.x * S2W + w) * S2B, C.nblk), g1 = min(g0 + S2B, C.nblk);
+  BlockRows cr = block_rows(d, P, s, g0 < g1 ? g0 : 0), prev = cr;
+  if (g0 > 0 && g0 < g1) prev = block_rows(d, P, s, g0 - 1);
   for (u32 g = g0; g < g1; ++g) {
     const u32 nrec = min(32u, R - g * 32), rec = g * 32 + lane;
     const bool on = lane < nrec;
-    const BlockRows cr = block_rows(d, P, s, g);
+    const BlockRows nextb = g + 1 < g1 ? block_rows(d, P, s, g + 1) : cr; /* the next block's mask is on its way */
     const u32 ts = d.rstart[P.first_rec + min(rec, R - 1)];
     u32 flags = 0;
     for (u32 k = 0; k < nnc; ++k) {
       const u32 f = T.ncf[k];
       const FieldClass &F = T.fc[f];
+      const RawRow row = load_row<false>(d, cr, prev, g > 0, f, lane, F.kind == K_NUM); /* fetching a field ahead did not pay here (measured) */
       if (F.kind == K_NUM) {
-        const i32 v = on ? (i32)parsed_value(d, cr, f, lane) : 0;
+        const i32 v = on ? (i32)parsed_value(cr, f, row) : 0;
         i32 pv = __shfl_up_sync(0xFFFFFFFFu, v, 1);
-        if (lane == 0 && g > 0) pv = (i32)parsed_value(d, block_rows(d, P, s, g - 1), f, 31); /* last record of the block before */
+        if (lane == 0 && g > 0) pv = (i32)parsed_prev_value(prev, f, row); /* last record of the block before */
         const i32 dl = wsub(v, pv);
         const bool hasd = on && rec > 0;
         bool pred;
@@ -352,7 +368,7 @@ __global__ void __launch_bounds__(S2W * 32) k_stat2(Dev d) {
       }
       /* string field: block flag = every token of the block equals the block's first (tasks.cpp:64-81); per-position char
        * histogram of the positions that are not constant over the subblock (tasks.cpp:83-93) */
-      const TokRef t = parsed_token(d, cr, C, F, f, lane, ts);
+      const TokRef t = parsed_token(cr, C, F, f, row, ts);
       const u16 *sm = (const u16 *)(arena + F.slotmap_off);
       if (__all_sync(0xFFFFFFFFu, !on || t.same0)) {
         /* every record of the block carries record 0's token: one addition per counted position for the whole block */
@@ -392,6 +408,7 @@ __global__ void __launch_bounds__(S2W * 32) k_stat2(Dev d) {
       if (__all_sync(0xFFFFFFFFu, pred)) flags |= 1u << f;
     }
     if (lane == 0) arena[C.flagbits_off + g] = flags;
+    prev = cr; cr = nextb;
   }
   __syncthreads();
   for (u32 i = tid; i < ncs * 256; i += S2W * 32) {
@@ -406,12 +423,15 @@ __global__ void __launch_bounds__(S2W * 32) k_stat2(Dev d) {
 template <class Sink>
 __device__ __forceinline__ void title_record_parsed(const Dev &d, const BlockRows &cr, const SbClass &C, const TitleTabs &T, const u32 *arena, u32 i, u32 ts,
                                                     u32 flags, bool first, Sink &s) {
+  RawRow nx = load_row<true>(d, cr, cr, false, T.ncf[0], i, T.fc[T.ncf[0]].kind == K_NUM);
   for (u32 k = 0; k < C.nnc; ++k) {
     const u32 f = T.ncf[k];
     const FieldClass &F = T.fc[f];
     const bool flag = (flags >> f) & 1u;
+    const RawRow row = nx;
+    if (k + 1 < C.nnc) nx = load_row<true>(d, cr, cr, false, T.ncf[k + 1], i, T.fc[T.ncf[k + 1]].kind == K_NUM);
     if (F.kind == K_NUM) {
-      const i32 v = (i32)parsed_value(d, cr, f, i);
+      const i32 v = (i32)parsed_value(cr, f, row);
       const i32 pv = __shfl_up_sync(0xFFFFFFFFu, v, 1);
       if (first) s.put((u32)wsub(v, F.min_v), F.bits_val);
       else if (!flag) {
@@ -424,7 +444,7 @@ __device__ __forceinline__ void title_record_parsed(const Dev &d, const BlockRow
       continue;
     }
     if (!first && flag) continue;
-    const TokRef t = parsed_token(d, cr, C, F, f, i, ts);
+    const TokRef t = parsed_token(cr, C, F, f, row, ts);
     if (!F.is_len_const) s.put(t.len - F.min_len, F.bits_len);
     const u16 *sm = (const u16 *)(arena + F.slotmap_off);
     for (u32 j = 0; j < t.len; ++j)
