@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--shape", default="100bp", choices=sorted(WORKLOADS))
     ap.add_argument("--mb", type=int, default=16000, help="size of the whole file image in MB (10^6 bytes), split over the ranks")
     ap.add_argument("--cpu-sample-mb", type=int, default=256)
-    ap.add_argument("--e2e-batch-mb", type=int, default=64, help="batch size (MiB) of the pipelined end-to-end run")
+    ap.add_argument("--e2e-batch-mb", type=int, default=128, help="batch size (MiB) of the pipelined end-to-end run")
     ap.add_argument("--driver-mb", type=int, default=8000, help="file size of the file-to-file driver leg (0: skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-shapes", action="store_true", help="skip the 1 GB kernel-only probes of the other named shapes (N = 1 only)")

@@ -219,8 +219,9 @@ int main(int argc, char **argv) {
   if (ndev < 1) die(rank, 3, "no CUDA device (this build has no CPU path)", nullptr);
   const char *lr = getenv("LOCAL_RANK");
   const int dev = (lr ? atoi(lr) : rank) % ndev; /* one rank per GPU; ranks wrap when there are fewer GPUs */
-  /* 64 MiB batches: upload of batch b+1, kernels of batch b and download of batch b-1 overlap inside the library */
-  const uint64_t batch = 64ull << 20;
+  /* 128 MiB batches: upload of batch b+1, kernels of batch b and download of batch b-1 overlap inside the library (at 64 MiB
+   * the latency-bound kernels of a batch take longer than its upload: 43 vs 51 GB/s end to end on one GPU) */
+  const uint64_t batch = getenv("PHY_DRIVER_BATCH_MB") ? (uint64_t)atoi(getenv("PHY_DRIVER_BATCH_MB")) << 20 : 128ull << 20;
   phy_ctx *ctx = nullptr;
   int rc = phy_ctx_create(&ctx, dev, batch + (2u << 20), (uint32_t)(batch / (READ_BUFFER_SIZE / 2)) + 16);
   if (rc) die(rank, 3, "cannot create the GPU context", phy_strerror(rc));
