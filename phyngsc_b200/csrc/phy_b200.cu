@@ -342,11 +342,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   static const int enc_env = getenv("PHY_ENC") ? atoi(getenv("PHY_ENC")) : 1;
   static const int encg_env = getenv("PHY_ENC_G") ? atoi(getenv("PHY_ENC_G")) : 0;
   static const int qdbuf_env = getenv("PHY_QD_NBUF") ? atoi(getenv("PHY_QD_NBUF")) : 0;
-  u32 encG = H.max_len <= 64 ? 1u : H.max_len <= 192 ? 4u : 8u;
+  u32 encG = H.max_len <= 64 ? 1u : H.max_len <= 256 ? 4u : 8u; /* measured per shape (36 / 100 / 150 / 50-205 bp): 1, 4, 4, 4 */
   if (encg_env == 1 || encg_env == 2 || encg_env == 4 || encg_env == 8) encG = (u32)encg_env;
   while (encG < 8 && seg_len(H.max_len, encG) > 64) encG *= 2; /* a lane keeps one bit per position of its run (k_seqstat) */
-  if (!(encg_env == 1 || encg_env == 2 || encg_env == 4 || encg_env == 8))
-    while (encG < 8 && seg_len(H.max_len, encG) * (ctx->qcode_hint > 12 ? ctx->qcode_hint : 12u) > 32u * 18u) encG *= 2; /* long codes: shorter runs keep the lane-private staging small (50-205 bp, skewed quality: 1.76 vs 2.24 ms per GB) */
   d.fg.g = enc_env ? encG : 0u;
   /* lane-private staging: a lane's run of positions times the longest quality code -- 12 bits unless the previous batch
    * of this context saw longer ones (subblocks that need more than the kernels were launched with take the two-walk path) */
