@@ -53,6 +53,14 @@ struct phy_ctx {
   u8 *h_nl = nullptr;
   /* pinned host mirrors */
   BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; SbOut *h_sbout = nullptr; PlanState *h_state = nullptr;
+  /* Front part of a batch (record splitter + window plan) ahead of its back part: the front part writes the "next" set of its
+   * outputs (record table, window plans, header, host mirrors); prefix_finish() swaps that set with the current one, which the
+   * back part (every other kernel) reads.  So the front part of batch b + 1 can run beside the back part of batch b. */
+  struct PrefixSet { u32 *te = nullptr, *se = nullptr, *rstart = nullptr; SbPlan *plans = nullptr; BatchHdr *hdr = nullptr;
+                     BatchHdr *h_hdr = nullptr; SbPlan *h_plans = nullptr; PlanState *h_state = nullptr; } nxt;
+  struct BatchArgs { const u8 *in = nullptr; u32 len = 0, start_pos = 0; i64 batch_base = 0, region_len = 0; bool is_final = false; } cur_args, nxt_args;
+  cudaStream_t s_prefix = nullptr; cudaEvent_t ev_prefix = nullptr;
+  int pi = 0; /* next profiling event of the batch */
   u32 launches = 0;
   u64 resident_len = 0, resident_out = 0;
   u8 *ring = nullptr, *hout[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_ring[8] = {}, ev_hout[4] = {}; /* pinned staging of phy_compress_stream */
@@ -124,6 +132,12 @@ extern "C" void phy_ctx_destroy(phy_ctx *ctx) {
   void *dev[] = {ctx->in, ctx->te, ctx->se, ctx->rstart, ctx->kx, ctx->qoff, ctx->doff, ctx->toff, ctx->chunk_first, ctx->chunk_last, ctx->tile_cnt, ctx->tile_off, ctx->nl_mask, ctx->blk_mask, ctx->tv, ctx->tc, ctx->tp, ctx->v0, ctx->plan_state,
                  ctx->plans, ctx->hdr, ctx->acc, ctx->cls, ctx->sbout, ctx->arena, ctx->out, ctx->in2, ctx->out2, ctx->tmp, ctx->tmp_used, ctx->big_in, ctx->big_out};
   for (void *p : dev) if (p) cudaFree(p);
+  void *dev2[] = {ctx->nxt.te, ctx->nxt.se, ctx->nxt.rstart, ctx->nxt.plans, ctx->nxt.hdr};
+  for (void *p : dev2) if (p) cudaFree(p);
+  void *host2[] = {ctx->nxt.h_hdr, ctx->nxt.h_plans, ctx->nxt.h_state};
+  for (void *p : host2) if (p) cudaFreeHost(p);
+  if (ctx->s_prefix) cudaStreamDestroy(ctx->s_prefix);
+  if (ctx->ev_prefix) cudaEventDestroy(ctx->ev_prefix);
   void *host[] = {ctx->h_hdr, ctx->h_plans, ctx->h_sbout, ctx->h_state, ctx->h_nl, ctx->ring, ctx->hout[0], ctx->hout[1], ctx->hout[2], ctx->hout[3]};
   for (auto &e : ctx->ev_ring) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->ev_hout) if (e) cudaEventDestroy(e);
@@ -161,7 +175,11 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   ctx->out_cap = ctx->max_batch / 2 + (1u << 20);
   ctx->slack = 64 * 1024;
   ctx->max_tiles = (u32)((ctx->max_batch + TILE - 1) / TILE) + 1;
-  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0; /* the back part's streams outrank the front part's: a front part running ahead only fills gaps */
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+  CK(cudaStreamCreateWithPriority(&ctx->s_prefix, cudaStreamNonBlocking, prio_lo));
+  CK(cudaEventCreateWithFlags(&ctx->ev_prefix, cudaEventDisableTiming));
   CK(cudaMalloc(&ctx->hdr_g, sizeof(BatchHdr) * GROUPS_MAX));
   CK(cudaHostAlloc(&ctx->h_hdr_g, sizeof(BatchHdr) * GROUPS_MAX, cudaHostAllocDefault));
   CK(cudaEventCreateWithFlags(&ctx->ev_rb[0], cudaEventDisableTiming));
@@ -171,6 +189,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaMalloc(&ctx->te, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->se, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->rstart, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->nxt.te, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->nxt.se, (size_t)(ctx->maxrec + 4) * 4));
+  CK(cudaMalloc(&ctx->nxt.rstart, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->kx, (size_t)(ctx->maxrec + 4) * 2));
   CK(cudaMalloc(&ctx->qoff, (size_t)(ctx->maxrec + 4) * 4));
   CK(cudaMalloc(&ctx->doff, (size_t)(ctx->maxrec + 4) * 4));
@@ -188,6 +209,8 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaMalloc(&ctx->plan_state, sizeof(PlanState)));
   CK(cudaMalloc(&ctx->plans, sizeof(SbPlan) * ctx->max_sb));
   CK(cudaMalloc(&ctx->hdr, sizeof(BatchHdr)));
+  CK(cudaMalloc(&ctx->nxt.plans, sizeof(SbPlan) * ctx->max_sb));
+  CK(cudaMalloc(&ctx->nxt.hdr, sizeof(BatchHdr)));
   CK(cudaMalloc(&ctx->acc, sizeof(SbAcc) * ctx->max_sb));
   CK(cudaMalloc(&ctx->cls, sizeof(SbClass) * ctx->max_sb));
   CK(cudaMalloc(&ctx->sbout, sizeof(SbOut) * ctx->max_sb));
@@ -200,6 +223,9 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaHostAlloc(&ctx->h_plans, sizeof(SbPlan) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_sbout, sizeof(SbOut) * ctx->max_sb, cudaHostAllocDefault));
   CK(cudaHostAlloc(&ctx->h_state, sizeof(PlanState), cudaHostAllocDefault));
+  CK(cudaHostAlloc(&ctx->nxt.h_hdr, sizeof(BatchHdr), cudaHostAllocDefault));
+  CK(cudaHostAlloc(&ctx->nxt.h_plans, sizeof(SbPlan) * ctx->max_sb, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&ctx->nxt.h_state, sizeof(PlanState), cudaHostAllocDefault));
   {
     u8 lut[256];
     fill_char_lut(lut);
@@ -252,20 +278,79 @@ extern "C" int64_t phy_find_first_record(const uint8_t *b, uint64_t lim) {
   return (int64_t)((b[c + 1] == '@') ? c + 1 : first_at);
 }
 
-/* Runs every kernel over the batch that is resident in ctx->in[0..len).  `start_pos` = first record of the
- * next window inside the batch.  On return h_hdr / h_plans / h_sbout describe the batch. */
-static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
+static const bool dbg_sync = getenv("PHY_DEBUG_SYNC") != nullptr; /* fault isolation: synchronise after every launch */
+#define PMARK()                                                                                                   \
+  do {                                                                                                            \
+    if (ctx->profile) cudaEventRecord(ctx->pev[ctx->pi], st);                                                     \
+    if (dbg_sync) {                                                                                               \
+      cudaError_t e_ = cudaStreamSynchronize(st);                                                                 \
+      if (e_ == cudaSuccess) e_ = cudaGetLastError();                                                             \
+      if (e_ != cudaSuccess) {                                                                                    \
+        ctx->err = std::string("after stage ") + (ctx->pi ? KERNEL_NAMES[ctx->pi - 1] : "start") + ": " + cudaGetErrorString(e_); \
+        return PHY_ERR_CUDA;                                                                                      \
+      }                                                                                                           \
+    }                                                                                                             \
+    ++ctx->pi;                                                                                                    \
+  } while (0)
+
+/* Front part of a batch on stream `st`: record splitter, window chain, sizes; its results go to the "next" set and are copied
+ * to that set's host mirrors.  Does not wait.  `start_pos` = first record of the next window inside the batch. */
+static int prefix_launch(phy_ctx *ctx, cudaStream_t st, const u8 *in, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
   Dev d;
   memset(&d, 0, sizeof d);
   d.in = in; d.len = len; d.start_pos = start_pos;
+  d.te = ctx->nxt.te; d.se = ctx->nxt.se; d.rstart = ctx->nxt.rstart; d.maxrec = ctx->maxrec;
+  d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (len + TILE - 1) / TILE;
+  d.plan_state = ctx->plan_state; d.plans = ctx->nxt.plans; d.max_sb = ctx->max_sb; d.hdr = ctx->nxt.hdr;
+  d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
+  ctx->nxt_args.in = in; ctx->nxt_args.len = len; ctx->nxt_args.start_pos = start_pos; ctx->nxt_args.batch_base = batch_base;
+  ctx->nxt_args.region_len = region_len; ctx->nxt_args.is_final = is_final;
+  if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
+  ctx->pi = 0;
+  PMARK();
+  CK(cudaMemsetAsync(ctx->tile_off, 0, (size_t)((d.ntiles + SUPER - 1) / SUPER) * 4, st));
+  k_nl_count<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
+  k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
+  k_nl_emit<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
+  k_plan<<<1, 32, 0, st>>>(d);
+  k_spanmax<<<dim3(8, ctx->max_sb), 256, 0, st>>>(d); PMARK();
+  ctx->launches += 5;
+  CK(cudaMemcpyAsync(ctx->nxt.h_hdr, ctx->nxt.hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->nxt.h_state, ctx->plan_state, sizeof(PlanState), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->nxt.h_plans, ctx->nxt.plans, sizeof(SbPlan) * ctx->max_sb, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev_prefix, st));
+  return PHY_OK;
+}
+
+/* Waits for the front part launched last and makes its results the current set: h_hdr / h_state / h_plans describe the batch. */
+static int prefix_finish(phy_ctx *ctx) {
+  CK(cudaEventSynchronize(ctx->ev_prefix));
+  std::swap(ctx->te, ctx->nxt.te); std::swap(ctx->se, ctx->nxt.se); std::swap(ctx->rstart, ctx->nxt.rstart);
+  std::swap(ctx->plans, ctx->nxt.plans); std::swap(ctx->hdr, ctx->nxt.hdr);
+  std::swap(ctx->h_hdr, ctx->nxt.h_hdr); std::swap(ctx->h_plans, ctx->nxt.h_plans); std::swap(ctx->h_state, ctx->nxt.h_state);
+  ctx->cur_args = ctx->nxt_args;
+  ctx->last_S = 0;
+  const BatchHdr &H = *ctx->h_hdr;
+  if (H.status) { ctx->err = std::string("batch failed while splitting records: ") + phy_strerror(H.status); return H.status; }
+  ctx->last_S = H.S;
+  return PHY_OK;
+}
+
+/* Back part of the current batch (everything after the window plan) on the context's main stream and its group streams.
+ * On return (after the caller has synchronised the main stream) h_sbout and h_hdr->total_out describe the payloads. */
+static int run_body(phy_ctx *ctx, u8 *out, u64 out_cap) {
+  const phy_ctx::BatchArgs &A = ctx->cur_args;
+  Dev d;
+  memset(&d, 0, sizeof d);
+  d.in = A.in; d.len = A.len; d.start_pos = A.start_pos;
   d.te = ctx->te; d.se = ctx->se; d.rstart = ctx->rstart; d.maxrec = ctx->maxrec;
   d.kx = ctx->kx; d.qoff = ctx->qoff; d.doff = ctx->doff; d.toff = ctx->toff; d.chunk_first = ctx->chunk_first; d.chunk_last = ctx->chunk_last;
   d.blk_mask = ctx->blk_mask; d.v0 = ctx->v0;
-  d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (len + TILE - 1) / TILE;
+  d.tile_cnt = ctx->tile_cnt; d.tile_off = ctx->tile_off; d.nl_mask = ctx->nl_mask; d.ntiles = (A.len + TILE - 1) / TILE;
   d.plan_state = ctx->plan_state; d.plans = ctx->plans; d.max_sb = ctx->max_sb; d.hdr = ctx->hdr;
   d.acc = ctx->acc; d.cls = ctx->cls; d.sbout = ctx->sbout; d.arena = ctx->arena; d.arena_words = ctx->arena_words;
   d.out = out; d.out_cap = out_cap;
-  d.batch_base = batch_base; d.region_len = region_len; d.batch_is_final = is_final ? 1 : 0; d.slack = ctx->slack;
+  d.batch_base = A.batch_base; d.region_len = A.region_len; d.batch_is_final = A.is_final ? 1 : 0; d.slack = ctx->slack;
   d.span_bytes = 0;
   d.tmp = ctx->tmp; d.tmp_cap = ctx->tmp_cap; d.tmp_used = ctx->tmp_used;
   cudaStream_t st = ctx->stream;
@@ -276,40 +361,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
     if (ctx->prev_max_len) ctx->nq_hint = mx / 2 / (ctx->prev_max_len + 1);
     ctx->prev_groups = 0;
   }
-  ctx->last_S = 0;
-  if (d.ntiles == 0) { ctx->err = "empty batch"; return PHY_ERR_ARG; }
-  int pi = 0;
-  static const bool dbg_sync = getenv("PHY_DEBUG_SYNC") != nullptr; /* fault isolation: synchronise after every launch */
-#define PMARK()                                                                                                   \
-  do {                                                                                                            \
-    if (ctx->profile) cudaEventRecord(ctx->pev[pi], st);                                                          \
-    if (dbg_sync) {                                                                                               \
-      cudaError_t e_ = cudaStreamSynchronize(st);                                                                 \
-      if (e_ == cudaSuccess) e_ = cudaGetLastError();                                                             \
-      if (e_ != cudaSuccess) {                                                                                    \
-        ctx->err = std::string("after stage ") + (pi ? KERNEL_NAMES[pi - 1] : "start") + ": " + cudaGetErrorString(e_); \
-        return PHY_ERR_CUDA;                                                                                      \
-      }                                                                                                           \
-    }                                                                                                             \
-    ++pi;                                                                                                         \
-  } while (0)
-  PMARK();
-  CK(cudaMemsetAsync(ctx->tile_off, 0, (size_t)((d.ntiles + SUPER - 1) / SUPER) * 4, st));
   CK(cudaMemsetAsync(ctx->tmp_used, 0, sizeof(u64), st));
-  k_nl_count<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
-  k_nl_scan<<<1, 1024, 0, st>>>(d); PMARK();
-  k_nl_emit<<<d.ntiles, NLT, 0, st>>>(d); PMARK();
-  k_plan<<<1, 32, 0, st>>>(d);
-  k_spanmax<<<dim3(8, ctx->max_sb), 256, 0, st>>>(d); PMARK();
-  ctx->launches += 5;
-  CK(cudaMemcpyAsync(ctx->h_hdr, ctx->hdr, sizeof(BatchHdr), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ctx->h_state, ctx->plan_state, sizeof(PlanState), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ctx->h_plans, ctx->plans, sizeof(SbPlan) * ctx->max_sb, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
   const BatchHdr H = *ctx->h_hdr;
-  if (H.status) { ctx->err = std::string("batch failed while splitting records: ") + phy_strerror(H.status); return H.status; }
   const u32 S = H.S;
-  ctx->last_S = S;
   if (S == 0) return PHY_OK;
   u32 span = (H.max_span + 16 + 1023) & ~1023u; /* exact: every 128-record span of the batch fits (k_spanmax) */
   if (span > SPAN_MAX) span = SPAN_MAX;         /* longer spans fail their subblock with PHY_ERR_UNSUPPORTED */
@@ -375,7 +429,9 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   static const int groups_env = getenv("PHY_GROUPS") ? atoi(getenv("PHY_GROUPS")) : 3; /* measured on 1 GB: 3.25 / 3.13 / 3.01 / 3.05 ms for 1..4 groups */
   u32 G = (ctx->profile || dbg_sync || S < 16) ? 1u : (u32)(groups_env < 1 ? 1 : groups_env > GROUPS_MAX ? GROUPS_MAX : groups_env);
   if (G > 1 && !ctx->gstream[1]) {
-    for (int g = 1; g < GROUPS_MAX; ++g) CK(cudaStreamCreateWithFlags(&ctx->gstream[g], cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int g = 1; g < GROUPS_MAX; ++g) CK(cudaStreamCreateWithPriority(&ctx->gstream[g], cudaStreamNonBlocking, prio_hi));
     for (int g = 0; g < GROUPS_MAX; ++g) {
       if (g) CK(cudaEventCreateWithFlags(&ctx->ev_rb[g], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ctx->ev_scan[g], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done[g], cudaEventDisableTiming));
@@ -491,10 +547,19 @@ static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, 
   CK(cudaGetLastError());
   if (ctx->profile) {
     CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < NKERN && i + 1 < pi; ++i) { float t = 0; cudaEventElapsedTime(&t, ctx->pev[i], ctx->pev[i + 1]); ctx->pms[i] += t; }
+    for (int i = 0; i < NKERN && i + 1 < ctx->pi; ++i) { float t = 0; cudaEventElapsedTime(&t, ctx->pev[i], ctx->pev[i + 1]); ctx->pms[i] += t; }
     ctx->pcount++;
   }
   return PHY_OK;
+}
+
+/* Front and back part of one batch one after the other on the main stream (the pipelined region call; profiling). */
+static int run_batch(phy_ctx *ctx, const u8 *in, u8 *out, u64 out_cap, u32 len, u32 start_pos, i64 batch_base, i64 region_len, bool is_final) {
+  int rc = prefix_launch(ctx, ctx->stream, in, len, start_pos, batch_base, region_len, is_final);
+  if (rc) return rc;
+  rc = prefix_finish(ctx);
+  if (rc) return rc;
+  return run_body(ctx, out, out_cap);
 }
 
 static void fill_descs(phy_ctx *ctx, u32 S, u64 out_base, phy_subblock_desc *descs) {
@@ -590,26 +655,31 @@ extern "C" int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const ph
   cudaStream_t s = ctx->stream;
   CK(cudaMemcpyAsync(ctx->plan_state, ctx->h_state, sizeof(PlanState), cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(ctx->ev[0], s));
+  /* The front part of batch b + 1 (record splitter, window chain: bandwidth- and latency-bound, 0.5 ms per GB) runs on a
+   * lower-priority stream beside the back part of batch b (issue-bound record kernels); it only needs to know where batch
+   * b's chain stopped, which batch b's own front part has already told the host. */
+  static const bool pipe_env = !(getenv("PHY_PIPE") && atoi(getenv("PHY_PIPE")) == 0);
+  const bool pipelined = pipe_env && !ctx->profile && !dbg_sync;
+  cudaStream_t sp = pipelined ? ctx->s_prefix : s;
+  if (pipelined) { CK(cudaEventRecord(ctx->ev[2], s)); CK(cudaStreamWaitEvent(sp, ctx->ev[2], 0)); } /* the plan state is on the device first */
   const u32 cap_descs = *inout_n_descs;
   u32 nd = 0, nb = 0;
   u64 base = 0, next_pos = 0, out_used = 0;
   bool done = false;
+  u64 blen = len_total < ctx->max_batch ? len_total : ctx->max_batch;
+  bool final = blen == len_total;
+  rc = prefix_launch(ctx, sp, rin, (u32)blen, first, 0, (i64)len_total, final);
+  if (rc) return rc;
   while (!done) {
-    u64 blen = len_total - base;
-    if (blen > ctx->max_batch) blen = ctx->max_batch;
-    const bool final = base + blen == len_total;
-    const u32 start_pos = (u32)(next_pos - base) + (nb == 0 ? first : 0u);
-    rc = run_batch(ctx, rin + base, rout + out_used, rout_cap - out_used, (u32)blen, start_pos, (i64)base, (i64)len_total, final);
+    rc = prefix_finish(ctx);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(s));
     const u32 S = ctx->last_S;
     const PlanState hs = *ctx->h_state;
     if (hs.status) { ctx->err = std::string("window chaining failed: ") + phy_strerror(hs.status); return hs.status; }
     if (nd + S > cap_descs) { ctx->err = "descriptor array too small"; return PHY_ERR_CAPACITY; }
-    fill_descs(ctx, S, out_used, descs + nd);
-    nd += S; ++nb;
-    if (S) out_used += ctx->h_hdr->total_out;
     done = hs.done != 0;
+    u64 nbase = base, nblen = 0;
+    bool nfinal = false;
     if (!done) {
       if (S == 0 && (u64)hs.bytes_read == next_pos && (final || (u64)hs.bytes_read < base + blen - back)) {
         ctx->err = final ? "region exhausted before the working region was covered" : "a window does not fit one batch (raise max_batch_bytes)";
@@ -618,9 +688,21 @@ extern "C" int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const ph
       next_pos = (u64)hs.bytes_read;
       /* the chain stops early when the batch's subblock capacity is used up: the next round starts where it stopped,
        * in the same bytes; otherwise the next batch starts one window + slack before this one's end */
-      const u64 nbase = final ? base : (base + blen - back) & ~(u64)255;
-      if (next_pos >= nbase) base = nbase;
+      const u64 cand = final ? base : (base + blen - back) & ~(u64)255;
+      if (next_pos >= cand) nbase = cand;
+      nblen = len_total - nbase;
+      if (nblen > ctx->max_batch) nblen = ctx->max_batch;
+      nfinal = nbase + nblen == len_total;
+      if (pipelined) { rc = prefix_launch(ctx, sp, rin + nbase, (u32)nblen, (u32)(next_pos - nbase), (i64)nbase, (i64)len_total, nfinal); if (rc) return rc; }
     }
+    rc = run_body(ctx, rout + out_used, rout_cap - out_used);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    fill_descs(ctx, S, out_used, descs + nd);
+    nd += S; ++nb;
+    if (S) out_used += ctx->h_hdr->total_out;
+    if (!done && !pipelined) { rc = prefix_launch(ctx, sp, rin + nbase, (u32)nblen, (u32)(next_pos - nbase), (i64)nbase, (i64)len_total, nfinal); if (rc) return rc; }
+    base = nbase; blen = nblen; final = nfinal;
   }
   CK(cudaEventRecord(ctx->ev[1], s));
   CK(cudaStreamSynchronize(s));
