@@ -7,13 +7,22 @@
  * blocks in file order keyed by WRID, subblocks that were split across two blocks of a rank (BCSS bits LSBS / FSBS,
  * phyNGSC.cpp:857-894) joined again -- and decodes every subblock with phy_decode.hpp on a pool of threads
  * (subblocks are independent; rank order, then subblock order, is file order of the FASTQ).
+ * The container is memory-mapped, subblocks are decoded at most a bounded window ahead of the writer and written in order
+ * as they complete, so neither the .ngsc nor the FASTQ is ever held in memory as a whole.
  * Plain C++: decoding needs no GPU and no MPI.
  */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -22,9 +31,11 @@
 
 namespace {
 
+struct Image { const uint8_t *p; uint64_t n; uint64_t size() const { return n; } uint8_t operator[](uint64_t i) const { return p[i]; } const uint8_t *data() const { return p; } };
+
 struct Bits { /* MSB-first reader over the whole file image */
-  const std::vector<uint8_t> &d; uint64_t bit;
-  Bits(const std::vector<uint8_t> &data, uint64_t byte_pos) : d(data), bit(byte_pos * 8) {}
+  const Image &d; uint64_t bit;
+  Bits(const Image &data, uint64_t byte_pos) : d(data), bit(byte_pos * 8) {}
   uint64_t get(unsigned n) {
     uint64_t v = 0;
     for (unsigned i = 0; i < n; ++i, ++bit) {
@@ -46,14 +57,12 @@ struct Piece { uint64_t off, len; };
 int main(int argc, char **argv) {
   if (argc < 3) { fprintf(stderr, "usage: %s in.ngsc out.fastq [threads]\n", argv[0]); return 1; }
   const int threads = argc > 3 ? atoi(argv[3]) : (int)std::thread::hardware_concurrency();
-  FILE *f = fopen(argv[1], "rb");
-  if (!f) { fprintf(stderr, "[E] cannot open %s\n", argv[1]); return 2; }
-  fseek(f, 0, SEEK_END);
-  const long fsz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<uint8_t> data((size_t)(fsz > 0 ? fsz : 0));
-  if (fsz < 4 || fread(data.data(), 1, data.size(), f) != data.size()) { fprintf(stderr, "[E] cannot read %s\n", argv[1]); return 2; }
-  fclose(f);
+  const int fd = open(argv[1], O_RDONLY);
+  struct stat sb;
+  if (fd < 0 || fstat(fd, &sb) != 0 || sb.st_size < 4) { fprintf(stderr, "[E] cannot read %s\n", argv[1]); return 2; }
+  void *map = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  if (map == MAP_FAILED) { fprintf(stderr, "[E] cannot map %s\n", argv[1]); return 2; }
+  const Image data = {(const uint8_t *)map, (uint64_t)sb.st_size};
   try {
     /* footer (tasks.cpp:1104-1176 / 1203-1292): the last two bytes hold its length */
     const uint64_t flen = ((uint64_t)data[data.size() - 2] << 8) | data[data.size() - 1];
@@ -95,41 +104,65 @@ int main(int argc, char **argv) {
     if (pos != fstart || nb != n_blocks) throw phydec::Error{"blocks do not tile the file"};
     for (uint64_t w = 0; w < np; ++w) if (open_split[w]) throw phydec::Error{"dangling split subblock"};
     /* flatten: payload list in rank order */
-    struct Job { std::vector<Piece> pieces; std::string text; const char *err = nullptr; };
+    struct Job { std::vector<Piece> pieces; std::string text; const char *err = nullptr; bool ready = false; };
     std::vector<Job> jobs;
     for (uint64_t w = 0; w < np; ++w) {
       size_t k = 0;
       for (uint32_t n : parts[w]) { Job j; for (uint32_t i = 0; i < n; ++i) j.pieces.push_back(subs[w][k++]); jobs.push_back(std::move(j)); }
     }
-    std::atomic<size_t> next(0);
+    /* workers decode at most `window` subblocks ahead of the writer; the writer (this thread) writes them in order and frees them */
+    const int nthreads = threads < 1 ? 1 : threads;
+    const size_t window = (size_t)nthreads * 3 + 2;
+    std::mutex m; std::condition_variable cv;
+    size_t next = 0, written = 0;
+    bool stop = false;
     auto work = [&]() {
       std::vector<uint8_t> joined;
       for (;;) {
-        const size_t i = next.fetch_add(1);
-        if (i >= jobs.size()) return;
+        size_t i;
+        {
+          std::unique_lock<std::mutex> g(m);
+          cv.wait(g, [&] { return stop || next >= jobs.size() || next < written + window; });
+          if (stop || next >= jobs.size()) return;
+          i = next++;
+        }
         Job &j = jobs[i];
         const uint8_t *p = data.data() + j.pieces[0].off;
         size_t n = j.pieces[0].len;
         if (j.pieces.size() > 1) {
           joined.clear();
-          for (auto &pc : j.pieces) joined.insert(joined.end(), data.begin() + pc.off, data.begin() + pc.off + pc.len);
+          for (auto &pc : j.pieces) joined.insert(joined.end(), data.data() + pc.off, data.data() + pc.off + pc.len);
           p = joined.data(); n = joined.size();
         }
-        try { j.text.reserve(n * 6); phydec::decode_subblock(p, n, j.text); } catch (const phydec::Error &e) { j.err = e.what; } catch (...) { j.err = "decoder failure"; }
+        try { j.text.reserve(n * 6); phydec::decode_subblock(p, n, j.text, (size_t)256 << 20); } catch (const phydec::Error &e) { j.err = e.what; } catch (...) { j.err = "decoder failure"; }
+        { std::lock_guard<std::mutex> g(m); j.ready = true; }
+        cv.notify_all();
       }
     };
     std::vector<std::thread> pool;
-    for (int t = 0; t < (threads < 1 ? 1 : threads); ++t) pool.emplace_back(work);
-    for (auto &t : pool) t.join();
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
     FILE *o = fopen(argv[2], "wb");
-    if (!o) { fprintf(stderr, "[E] cannot create %s\n", argv[2]); return 2; }
     uint64_t total = 0;
-    for (size_t i = 0; i < jobs.size(); ++i) {
-      if (jobs[i].err) { fprintf(stderr, "[E] subblock %zu: %s\n", i, jobs[i].err); fclose(o); return 4; }
-      fwrite(jobs[i].text.data(), 1, jobs[i].text.size(), o);
-      total += jobs[i].text.size();
+    const char *fail = o ? nullptr : "cannot create the output";
+    size_t fail_at = 0;
+    for (size_t i = 0; i < jobs.size() && !fail; ++i) {
+      { std::unique_lock<std::mutex> g(m); cv.wait(g, [&] { return jobs[i].ready; }); }
+      Job &j = jobs[i];
+      if (j.err) { fail = j.err; fail_at = i; break; }
+      size_t n = j.text.size();
+      /* a FASTQ that does not end in a newline: the decoder closes its last record with one; the footer knows the size */
+      if (i + 1 == jobs.size() && total + n == fastq_size + 1 && n && j.text[n - 1] == '\n') --n;
+      if (fwrite(j.text.data(), 1, n, o) != n) { fail = "write error"; fail_at = i; break; }
+      total += n;
+      std::string().swap(j.text);
+      { std::lock_guard<std::mutex> g(m); written = i + 1; }
+      cv.notify_all();
     }
-    fclose(o);
+    { std::lock_guard<std::mutex> g(m); stop = true; }
+    cv.notify_all();
+    for (auto &t : pool) t.join();
+    if (o) fclose(o);
+    if (fail) { fprintf(stderr, "[E] subblock %zu: %s\n", fail_at, fail); return o ? 4 : 2; }
     printf("[I] %s: %llu rank(s), %llu block(s), %zu subblock(s) -> %llu bytes of FASTQ%s\n", argv[1], (unsigned long long)np, (unsigned long long)nb,
            jobs.size(), (unsigned long long)total, total == fastq_size ? "" : " (footer states a different size!)");
     return total == fastq_size ? 0 : 5;

@@ -91,7 +91,9 @@ struct Field {
 inline int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
 /* Decodes one subblock payload; appends the FASTQ text of its records to `out`. */
-inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out) {
+/* `limit`: most text bytes a subblock may decode to (a window of the reference is 8 MiB of FASTQ; a damaged payload -- e.g. a
+ * long constant token times a huge record count -- must not be allowed to ask for unbounded memory) */
+inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out, size_t limit = (size_t)1 << 30) {
   static const char amb_of_code[17] = {0, 0, 'Y', 'R', 'W', 'S', 'K', 'M', 'D', 'V', 'H', 'B', 'N', 'X', 'U', '.', '-'}; /* phyNGSC.cpp:184-206 */
   BitReader r(payload, len);
   /* ---- info (phyNGSC.cpp:717-742) */
@@ -118,7 +120,13 @@ inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out
     Field &x = F[f];
     x.sep = (uint8_t)r.byte();
     x.constant = r.byte() != 0;
-    if (x.constant) { const uint32_t l = r.word(); x.tok0.resize(l); for (uint32_t j = 0; j < l; ++j) x.tok0[j] = (char)r.byte(); continue; }
+    if (x.constant) {
+      const uint32_t l = r.word();
+      if (l > r.n - r.pos) throw Error{"payload truncated"}; /* the token's bytes follow: a damaged length must not size a buffer */
+      x.tok0.resize(l);
+      for (uint32_t j = 0; j < l; ++j) x.tok0[j] = (char)r.byte();
+      continue;
+    }
     ++nnc;
     x.numeric = r.byte() != 0;
     if (x.numeric) {
@@ -135,7 +143,7 @@ inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out
     }
     x.len_const = r.byte() != 0;
     x.len0 = r.word(); x.max_len = r.word(); x.min_len = r.word();
-    if (x.len0 > (1u << 20) || x.max_len > (1u << 20) || x.min_len > x.max_len) throw Error{"bad string field"};
+    if (x.len0 > (1u << 20) || x.max_len > (1u << 20) || x.min_len > x.max_len || x.len0 > r.n - r.pos) throw Error{"bad string field"};
     x.tok0.resize(x.len0);
     for (uint32_t j = 0; j < x.len0; ++j) x.tok0[j] = (char)r.byte();
     x.same.resize(x.len0);
@@ -155,8 +163,10 @@ inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out
   std::vector<int32_t> prev(nf, 0);
   std::vector<std::string> blk_tok(nf);
   std::vector<uint8_t> flag(nf, 0);
+  size_t title_bytes = 0;
   for (uint32_t lo = 0; lo < R; lo += 32) {
     const uint32_t hi = lo + 32 < R ? lo + 32 : R;
+    if (title_bytes > limit) throw Error{"subblock text exceeds the limit"};
     for (uint32_t f = 0; f < nf; ++f) if (!F[f].constant) flag[f] = (uint8_t)r.bit();
     for (uint32_t i = lo; i < hi; ++i) {
       std::string &t = titles[i];
@@ -192,6 +202,7 @@ inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out
         }
         t += tok; t += (char)x.sep;
       }
+      title_bytes += t.size();
     }
     r.align();
   }
@@ -225,6 +236,7 @@ inline void decode_subblock(const uint8_t *payload, size_t len, std::string &out
   if (!plain) dt.load(r);
   r.align();
   for (uint32_t i = 0; i < R; ++i) {
+    if (out.size() > limit) throw Error{"subblock text exceeds the limit"};
     out += titles[i]; /* ends with its '\n' separator */
     std::string &q = qual[i];
     for (uint32_t k = 0; k < qlen[i]; ++k) {

@@ -58,3 +58,38 @@ def test_garbage_is_an_error_not_a_crash():
             api.decode_subblock(rng.integers(0, 256, n, dtype=np.uint8))
     good = synth.fastq("36bp", 3, target_bytes=100_000)
     assert container is not None and good.size > 0
+
+
+def test_cpp_decompressor_file_without_trailing_newline(tmp_path, oracle):
+    """A FASTQ whose last line has no newline: the encoder sees a virtual one, the decoder writes one, the footer knows the
+    real size -- the decompressor drops the extra byte instead of reporting a size mismatch.  The container is put together
+    from the oracle's blocks and footer (rank-major order, as the driver writes it)."""
+    import subprocess
+    from phyngsc_b200 import build
+    data = synth.fastq("100bp", 17, target_bytes=700_000)
+    assert data[-1] == 10
+    data = data[:-1]
+    ranks = [oracle.compress_rank(data, 2, r, window_bytes=256 * 1024) for r in range(2)]
+    order = [r for r in range(2) for _ in ranks[r]["blocks"]]
+    foot = oracle.make_footer(2, data.size, len(order), sum(len(x["subblocks"]) for x in ranks), [x["wr_overlap"] for x in ranks], order,
+                              [x["last_block_size"] for x in ranks])
+    src, out = tmp_path / "in.ngsc", tmp_path / "out.fastq"
+    src.write_bytes(b"".join(b for r in range(2) for b in ranks[r]["blocks"]) + foot)
+    p = subprocess.run([build.build_decompressor(), str(src), str(out), "2"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert out.read_bytes() == data.tobytes()
+
+
+def test_damaged_lengths_do_not_size_buffers():
+    """A constant title token whose length word is damaged must fail on the truncation check, not allocate gigabytes."""
+    data = synth.fastq("36bp", 3, target_bytes=60_000)
+    from oracle import phy_oracle
+    sb = bytearray(phy_oracle.compress_rank(data, 1, 0)["subblocks"][0])
+    # info: R, max_qlen, max_slen words, 3 bytes, flags word, length bits; the title header follows: nf word, then per field
+    # sep byte, constant byte, (constant:) length word.  Field 0 ("@ERR...") is constant: blow up its length word.
+    R = int.from_bytes(sb[0:4], "big"); mq = int.from_bytes(sb[4:8], "big")
+    off = 19 + (R * mq.bit_length() + 7) // 8 + 4
+    assert sb[off + 1] == 1  # field 0 is constant
+    sb[off + 2:off + 6] = (0xF0000000).to_bytes(4, "big")
+    with pytest.raises(api.PhyError):
+        api.decode_subblock(np.frombuffer(bytes(sb), dtype=np.uint8))
