@@ -693,10 +693,10 @@ extern "C" int phy_compress_resident(phy_ctx *ctx, uint64_t region_len, const ph
       nblen = len_total - nbase;
       if (nblen > ctx->max_batch) nblen = ctx->max_batch;
       nfinal = nbase + nblen == len_total;
-      if (pipelined) { rc = prefix_launch(ctx, sp, rin + nbase, (u32)nblen, (u32)(next_pos - nbase), (i64)nbase, (i64)len_total, nfinal); if (rc) return rc; }
     }
-    rc = run_body(ctx, rout + out_used, rout_cap - out_used);
+    rc = run_body(ctx, rout + out_used, rout_cap - out_used); /* first, so that the GPU is busy again as early as possible ... */
     if (rc) return rc;
+    if (!done && pipelined) { rc = prefix_launch(ctx, sp, rin + nbase, (u32)nblen, (u32)(next_pos - nbase), (i64)nbase, (i64)len_total, nfinal); if (rc) return rc; } /* ... the next front part fills in beside it */
     CK(cudaStreamSynchronize(s));
     fill_descs(ctx, S, out_used, descs + nd);
     nd += S; ++nb;
