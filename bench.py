@@ -373,6 +373,7 @@ def main():
         f = bytes_in / image.segment.size  # this rank's share, in segments
         nrec, title_b, seq_b = nrec_s * f, title_s * f, seq_s * f
         # algorithmic bytes per step of each stage on this rank: what it must read + must write
+        # (stat2 / enc_title read the parsed title rows k_stat1 left, not the title bytes: the title bytes are an upper bound for them)
         alg = {"nl_count": bytes_in + bytes_in / 8, "nl_emit": bytes_in / 8 + 12 * nrec, "stat1": title_b + 4 * nrec, "seqstat": 2 * seq_b + 2 * nrec,
                "stat2": title_b + 8 * nrec, "enc_title": title_b + 0.12 * bytes_out, "enc_qd": 2 * seq_b + 0.88 * bytes_out, "place": 2 * bytes_out,
                "lengths": bytes_in + 8 * nrec, "emit": bytes_in + bytes_out}

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PHY_ABI_VERSION 2
+#define PHY_ABI_VERSION 3 /* 3: phy_stream_prepare, emit callbacks come from a library thread */
 
 enum {
   PHY_OK = 0,

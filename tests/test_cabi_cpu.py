@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = api.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.phy_abi_version() == 2
+    assert L.phy_abi_version() == 3
 
 
 def test_block_header_and_footer_match_oracle(oracle):
