@@ -247,7 +247,7 @@ static int ctx_init(phy_ctx *ctx, int device, u64 max_batch, u32 max_sb) {
   CK(cudaFuncSetAttribute(k_lengths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EW * ENC_STAGE_MAX + PK_SMEM_MAX)));
   CK(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EP * ENC_STAGE_MAX + PK_SMEM_MAX)));
-  CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
+  CK(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HUFF_SMEM));
   CK(cudaFuncSetAttribute(k_enc_title, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_enc_qd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
   CK(cudaFuncSetAttribute(k_enc_qd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_DYN_MAX));
@@ -501,7 +501,7 @@ static int run_body(phy_ctx *ctx, u8 *out, u64 out_cap) {
     if (nq_hint) pk = ((H.max_len + 1) * (nq_hint + 8 > 256 ? 256u : nq_hint + 8) * 2u + 15u) & ~15u;
     else { CK(cudaEventSynchronize(ctx->ev_rb[g])); pk = (ctx->h_hdr_g[g].max_pk_bytes + 15u) & ~15u; }
     e.pk_bytes = pk <= PK_SMEM_MAX ? pk : 0u; /* larger tables stay in global memory (L1) */
-    k_huff<<<dim3(16, Sg), 128, 4 * sizeof(HuffScratch), gs>>>(e); GMARK();
+    k_huff<<<dim3(HUFF_LARGE + 32, Sg), HUFF_WARPS * 32, HUFF_SMEM, gs>>>(e); GMARK();
     /* single-walk encoder: slots, then title + info and quality + DNA of every task into the temporary buffer */
     e.fg.pk_bytes = e.pk_bytes;
     const u32 title_dyn = ENC_WARPS * enc_title_warp_bytes();

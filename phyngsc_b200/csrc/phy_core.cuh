@@ -257,21 +257,26 @@ constexpr u32 INFO_FIXED = 19;
 /* ---- Huffman (huffman.cpp:18-118, 191-205; huffman.h:57-60, 134-147) ----------------------- */
 /* One table is built by `nl` cooperating lanes (a warp on the GPU, 1 on the host).  Phases that are
  * inherently serial run on lane 0.  SYNC() is __syncwarp on the device and nothing on the host. */
-struct HuffScratch {
-  u32 key_f[512];
-  u16 key_id[512];
-  u32 in_f[512];
-  u16 left[512], right[512];
-  u32 code[1024];
-  u8 len[1024];
+template <int N> /* N >= number of symbols; the last slot of in_f doubles as the warp's broadcast word */
+struct HuffScratchT {
+  static constexpr u32 CAP = N;
+  u32 key_f[N];
+  u16 key_id[N];
+  u32 in_f[N];
+  u16 left[N], right[N];
+  u32 code[2 * N];
+  u8 len[2 * N];
 };
+typedef HuffScratchT<512> HuffScratch;     /* any table of the format (numeric tables reach 512 symbols) */
+typedef HuffScratchT<64> HuffScratchSmall; /* quality and DNA tables: eight times as many tables fit an SM's shared memory */
 
 struct NoSync { PHY_HD void operator()() const {} };
 
 /* freq[n] -> cl[n] (len << 32 | code) and tree blob [word mem_size][mem] at `tree`; returns blob bytes,
  * or 0 when a code would exceed 32 bits (the reference's 32-bit code word would overflow). */
-template <class Sync>
-PHY_HD u32 huff_table(const u32 *freq, u32 n, u64 *cl, u8 *tree, HuffScratch &S, u32 lane, u32 nl, Sync sync) {
+template <class Scratch, class Sync>
+PHY_HD u32 huff_table(const u32 *freq, u32 n, u64 *cl, u8 *tree, Scratch &S, u32 lane, u32 nl, Sync sync) {
+  constexpr u32 BC = Scratch::CAP - 1; /* broadcast slot: the queue holds at most n - 1 <= CAP - 1 internal nodes, index <= CAP - 2 */
   /* rank sort by the strict total order (frequency, id), huffman.h:57-60 */
   for (u32 i = lane; i < n; i += nl) S.code[i] = freq[i];
   sync();
@@ -291,13 +296,13 @@ PHY_HD u32 huff_table(const u32 *freq, u32 n, u64 *cl, u8 *tree, HuffScratch &S,
   u32 lo = 0;
   if (lane == 0) {
     while (n - lo > 2 && S.key_f[lo] == 0) ++lo;
-    S.in_f[511] = lo; /* broadcast slot (in_f[511] is never used by the queue: at most n-1 <= 511 internals, index <= 510) */
+    S.in_f[BC] = lo;
   }
   sync();
-  lo = S.in_f[511];
+  lo = S.in_f[BC];
   sync();
   u32 p = n - lo;
-  for (u32 i = lane; i < 2 * n; i += nl) { if (i < 1024) { S.code[i] = 0; S.len[i] = 0; } }
+  for (u32 i = lane; i < 2 * n; i += nl) { if (i < 2 * Scratch::CAP) { S.code[i] = 0; S.len[i] = 0; } }
   sync();
   u32 ok = 1;
   if (lane == 0) {
@@ -327,10 +332,10 @@ PHY_HD u32 huff_table(const u32 *freq, u32 n, u64 *cl, u8 *tree, HuffScratch &S,
         if (i == n) break;
       }
     }
-    S.in_f[511] = ok;
+    S.in_f[BC] = ok;
   }
   sync();
-  ok = S.in_f[511];
+  ok = S.in_f[BC];
   if (!ok) return 0;
   for (u32 i = lane; i < n; i += nl) cl[i] = ((u64)S.len[i] << 32) | S.code[i];
   /* serialisation, huffman.cpp:88-118 + huffman.h:134-147 + huffman.cpp:191-205 */
@@ -358,10 +363,10 @@ PHY_HD u32 huff_table(const u32 *freq, u32 n, u64 *cl, u8 *tree, HuffScratch &S,
     if (nb) m[o++] = (u8)(acc << (8 - nb));
     tree[0] = (u8)(o >> 24); tree[1] = (u8)(o >> 16); tree[2] = (u8)(o >> 8); tree[3] = (u8)o;
     blob = o + 4;
-    S.in_f[511] = blob;
+    S.in_f[BC] = blob;
   }
   sync();
-  blob = S.in_f[511];
+  blob = S.in_f[BC];
   sync();
   return blob;
 }

@@ -693,34 +693,58 @@ __global__ void __launch_bounds__(CH) k_dnacount(Dev d) {
 /* ---- Huffman build: one warp per table ------------------------------------------------------------------------- */
 struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 
-__global__ void __launch_bounds__(128) k_huff(Dev d) {
+/* Tables of up to 64 symbols (the per-position quality tables, the DNA table: nearly all of them) are built with the small
+ * scratch by CTAs of 8 warps, so that an SM's warp slots -- not its shared memory -- bound how many are under way at once (the
+ * build is serial on lane 0 inside a table); the few larger ones (numeric tables up to 512 symbols, per-position character
+ * tables of 256) by the first HUFF_LARGE CTAs of the same launch, one warp each with the large scratch. */
+constexpr u32 HUFF_LARGE = 16, HUFF_WARPS = 8;
+constexpr u32 HUFF_SMEM = sizeof(HuffScratch) > HUFF_WARPS * sizeof(HuffScratchSmall) ? sizeof(HuffScratch) : HUFF_WARPS * sizeof(HuffScratchSmall);
+
+/* what follows a table's build: its blob length, its longest code, the packed copy of a quality table */
+__device__ __forceinline__ void huff_finish(SbClass &C, u32 *arena, TableDesc *td, u32 t, const TableDesc &D, u32 blob, u32 lane) {
+  if (lane == 0) td[t].tree_len = blob;
+  __syncwarp();
+  { /* longest code: bounds the staging of the single-walk encoder (phy_fast.cuh) */
+    const u64 *cl = (const u64 *)(arena + D.cl_off);
+    u32 ml = 0;
+    for (u32 i = lane; i < D.n && blob; i += 32) ml = max(ml, (u32)(cl[i] >> 32));
+    ml = __reduce_max_sync(0xFFFFFFFFu, ml);
+    if (lane == 0) td[t].maxlen = ml;
+  }
+  if (t - C.tq0 <= C.max_qlen) { /* quality table: 16-bit copy (len << 12 | code, PK_ESC for the rare codes beyond 12 bits) for the shared-memory walkers */
+    u16 *pk = (u16 *)(arena + C.qpk_off) + (size_t)(t - C.tq0) * D.n;
+    const u64 *cl = (const u64 *)(arena + D.cl_off);
+    bool esc = false;
+    for (u32 i = lane; i < D.n && blob; i += 32) { u16 e; if (!qpack_entry(cl[i], e)) { e = (u16)PK_ESC; esc = true; } pk[i] = e; } /* longer than 12 bits: escape to the 64-bit entry */
+    if (blob == 0) atomicOr(&C.qpk_bad, 1u);
+    if (esc) atomicOr(&C.qpk_esc, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(HUFF_WARPS * 32) k_huff(Dev d) {
   extern __shared__ uint4 dyn_smem[];
-  HuffScratch *HS = (HuffScratch *)dyn_smem;
   const u32 s = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SbClass &C = d.cls[s];
   if (C.status) return;
   u32 *arena = d.arena + (size_t)s * d.arena_words;
   TableDesc *td = (TableDesc *)(arena + C.tabdesc_off);
-  for (u32 t = blockIdx.x * 4 + w; t < C.ntab; t += gridDim.x * 4) {
-    TableDesc D = td[t];
-    u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS[w], lane, 32u, WarpSync());
-    if (lane == 0) td[t].tree_len = blob;
-    __syncwarp();
-    { /* longest code: bounds the staging of the single-walk encoder (phy_fast.cuh) */
-      const u64 *cl = (const u64 *)(arena + D.cl_off);
-      u32 ml = 0;
-      for (u32 i = lane; i < D.n && blob; i += 32) ml = max(ml, (u32)(cl[i] >> 32));
-      ml = __reduce_max_sync(0xFFFFFFFFu, ml);
-      if (lane == 0) td[t].maxlen = ml;
+  if (blockIdx.x < HUFF_LARGE) { /* one warp, large scratch: the tables of more than 64 symbols */
+    if (w) return;
+    HuffScratch &HS = *(HuffScratch *)dyn_smem;
+    for (u32 t = blockIdx.x; t < C.ntab; t += HUFF_LARGE) {
+      const TableDesc D = td[t];
+      if (D.n <= HuffScratchSmall::CAP) continue;
+      const u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS, lane, 32u, WarpSync());
+      huff_finish(C, arena, td, t, D, blob, lane);
     }
-    if (t - C.tq0 <= C.max_qlen) { /* quality table: 16-bit copy (len << 12 | code, PK_ESC for the rare codes beyond 12 bits) for the shared-memory walkers */
-      u16 *pk = (u16 *)(arena + C.qpk_off) + (size_t)(t - C.tq0) * D.n;
-      const u64 *cl = (const u64 *)(arena + D.cl_off);
-      bool esc = false;
-      for (u32 i = lane; i < D.n && blob; i += 32) { u16 e; if (!qpack_entry(cl[i], e)) { e = (u16)PK_ESC; esc = true; } pk[i] = e; } /* longer than 12 bits: escape to the 64-bit entry */
-      if (blob == 0) atomicOr(&C.qpk_bad, 1u);
-      if (esc) atomicOr(&C.qpk_esc, 1u);
-    }
+    return;
+  }
+  HuffScratchSmall *HS = (HuffScratchSmall *)dyn_smem;
+  for (u32 t = (blockIdx.x - HUFF_LARGE) * HUFF_WARPS + w; t < C.ntab; t += (gridDim.x - HUFF_LARGE) * HUFF_WARPS) {
+    const TableDesc D = td[t];
+    if (D.n > HuffScratchSmall::CAP) continue;
+    const u32 blob = huff_table(arena + D.freq_off, D.n, (u64 *)(arena + D.cl_off), (u8 *)(arena + D.tree_off), HS[w], lane, 32u, WarpSync());
+    huff_finish(C, arena, td, t, D, blob, lane);
   }
 }
 

@@ -386,6 +386,13 @@ extern "C" int mirror_compress_window_fast(const u8 *b, u64 readable, i64 rsize,
 }
 
 extern "C" u32 mirror_huffman(const u32 *freq, u32 n, u64 *cl, u8 *tree) {
+  /* tables of up to 64 symbols take the small scratch on the GPU (k_huff's first launch): same function, other capacity */
+  if (n <= HuffScratchSmall::CAP) {
+    HuffScratchSmall *HS = new HuffScratchSmall;
+    u32 k = huff_table(freq, n, cl, tree, *HS, 0u, 1u, NoSync());
+    delete HS;
+    return k;
+  }
   HuffScratch *HS = new HuffScratch;
   u32 k = huff_table(freq, n, cl, tree, *HS, 0u, 1u, NoSync());
   delete HS;
